@@ -1,0 +1,340 @@
+// C ABI (include/ctag.h) over the sm_100a detection kernels: detector handle, workspace, batch pipeline.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <fstream>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace ctag {
+
+static thread_local char g_last_error[512] = "";
+
+void set_last_error(const char* what, cudaError_t e, const char* file, int line) {
+  snprintf(g_last_error, sizeof(g_last_error), "%s: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+}
+void set_last_error_text(const char* text) { snprintf(g_last_error, sizeof(g_last_error), "%s", text); }
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+static FrameGeom make_geom(int w, int h) {
+  FrameGeom g;
+  g.w = w;
+  g.h = h;
+  g.hw = w / 2;
+  g.hh = h / 2;
+  g.gpitch = round_up(w, 16);
+  g.bpitch = round_up(g.hw, 16);
+  g.cn = (g.hw + kWin - 1) / kWin;
+  g.rn = (g.hh + kWin - 1) / kWin;
+  g.bw = (g.hw + 1) / 2;
+  g.bh = (g.hh + 1) / 2;
+  g.nblocks = g.bw * g.bh;
+  g.area_max = (int)round(0.01 * g.hw * g.hh);  // corner_detector.cpp:88 (C round, half away from zero)
+  return g;
+}
+
+}  // namespace ctag
+
+using namespace ctag;
+
+struct ctag_detector {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  // dictionary (header/CylinderTag.h:44-45)
+  std::vector<int32_t> state;
+  int rows = 0, cols = 0, feature_size = 0;
+  int32_t* d_state = nullptr;
+
+  // workspace, sized for (cap_frames, w, h, channels)
+  int cap_frames = 0, w = 0, h = 0;
+  FrameGeom geo{};
+  uint8_t* d_stage = nullptr;  // staging for host inputs
+  size_t stage_bytes = 0;
+  uint8_t* d_gray = nullptr;   // [cap_frames][h][gpitch]   (BGR input only)
+  uint8_t* d_bin = nullptr;    // [cap_frames][hh][bpitch]
+  size_t gray_fstride = 0, bin_fstride = 0;
+
+  // state of the batch in flight / last batch
+  int cur_n = 0, cur_channels = 0;
+  const uint8_t* cur_gray = nullptr;  // full-res gray of the batch (input itself when channels == 1)
+  size_t cur_gray_pitch = 0, cur_gray_fstride = 0;
+  int launches = 0;
+  float stage_ms[CTAG_STAGE_COUNT] = {0, 0, 0, 0, 0};
+  cudaEvent_t ev[CTAG_STAGE_COUNT + 1] = {};
+  bool in_flight = false;
+};
+
+static int select_device(int cuda_device, int* chosen) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_last_error_text("no CUDA device available (the detection path has no CPU fallback)");
+    return CTAG_ERR_NO_DEVICE;
+  }
+  int dev = cuda_device;
+  if (dev < 0) CTAG_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev >= count) return CTAG_ERR_ARG;
+  cudaDeviceProp prop;
+  CTAG_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    snprintf(g_last_error, sizeof(g_last_error), "device %d is sm_%d%d; this library carries sm_100a code only", dev,
+             prop.major, prop.minor);
+    return CTAG_ERR_NO_DEVICE;
+  }
+  *chosen = dev;
+  return CTAG_OK;
+}
+
+static void free_workspace(ctag_detector* d) {
+  // d_stage is managed separately (ensure_stage): it may hold the batch that is about to be processed
+  cudaFree(d->d_gray);
+  cudaFree(d->d_bin);
+  d->d_gray = d->d_bin = nullptr;
+  d->cap_frames = 0;
+}
+
+static int ensure_workspace(ctag_detector* d, int n, int w, int h) {
+  if (d->cap_frames >= n && d->w == w && d->h == h) return CTAG_OK;
+  int cap = n > d->cap_frames || d->w != w || d->h != h ? n : d->cap_frames;
+  free_workspace(d);
+  d->geo = make_geom(w, h);
+  d->w = w;
+  d->h = h;
+  const FrameGeom& g = d->geo;
+  d->gray_fstride = (size_t)g.gpitch * g.h;
+  d->bin_fstride = (size_t)g.bpitch * g.hh;
+  CTAG_CUDA_CHECK(cudaMalloc(&d->d_gray, d->gray_fstride * cap));
+  CTAG_CUDA_CHECK(cudaMalloc(&d->d_bin, d->bin_fstride * cap));
+  d->cap_frames = cap;
+  return CTAG_OK;
+}
+
+static int ensure_stage(ctag_detector* d, size_t bytes) {
+  if (d->stage_bytes >= bytes) return CTAG_OK;
+  cudaFree(d->d_stage);
+  d->d_stage = nullptr;
+  d->stage_bytes = 0;
+  CTAG_CUDA_CHECK(cudaMalloc(&d->d_stage, bytes));
+  d->stage_bytes = bytes;
+  return CTAG_OK;
+}
+
+extern "C" {
+
+int ctag_create(ctag_detector** out, const int32_t* state, int rows, int cols, int feature_size, int cuda_device) {
+  if (!out || !state || rows <= 0 || cols <= 0 || feature_size <= 0) return CTAG_ERR_ARG;
+  *out = nullptr;
+  for (int i = 0; i < rows * cols; ++i)
+    if (!(state[i] >= 0 && state[i] <= 63)) return CTAG_ERR_DICTIONARY;  // check_dictionary, CylinderTag.cpp:56-65
+  int dev = 0;
+  int rc = select_device(cuda_device, &dev);
+  if (rc != CTAG_OK) return rc;
+  CTAG_CUDA_CHECK(cudaSetDevice(dev));
+  ctag_detector* d = new ctag_detector();
+  d->device = dev;
+  d->state.assign(state, state + rows * cols);
+  d->rows = rows;
+  d->cols = cols;
+  d->feature_size = feature_size;
+  if (cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMalloc(&d->d_state, sizeof(int32_t) * rows * cols) != cudaSuccess ||
+      cudaMemcpy(d->d_state, state, sizeof(int32_t) * rows * cols, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_last_error("detector setup", cudaGetLastError(), __FILE__, __LINE__);
+    ctag_destroy(d);
+    return CTAG_ERR_CUDA;
+  }
+  for (auto& e : d->ev) cudaEventCreate(&e);
+  *out = d;
+  return CTAG_OK;
+}
+
+int ctag_create_from_file(ctag_detector** out, const char* marker_path, int cuda_device) {
+  if (!out || !marker_path) return CTAG_ERR_ARG;
+  std::ifstream in(marker_path);
+  if (!in.is_open()) return CTAG_ERR_FILE;  // CylinderTag.cpp:19-22
+  int n = 0, cols = 0, fsz = 0;
+  in >> n >> cols >> fsz;  // CylinderTag.cpp:24-25
+  if (!in || n <= 0 || cols <= 0) return CTAG_ERR_FILE;
+  std::vector<int32_t> st((size_t)n * cols, 0);
+  for (auto& v : st) in >> v;  // missing values stay 0 like a failed operator>> on a zero-initialised Mat1i
+  return ctag_create(out, st.data(), n, cols, fsz, cuda_device);
+}
+
+void ctag_destroy(ctag_detector* d) {
+  if (!d) return;
+  cudaSetDevice(d->device);
+  if (d->stream) cudaStreamSynchronize(d->stream);
+  free_workspace(d);
+  cudaFree(d->d_stage);
+  cudaFree(d->d_state);
+  for (auto& e : d->ev)
+    if (e) cudaEventDestroy(e);
+  if (d->stream) cudaStreamDestroy(d->stream);
+  delete d;
+}
+
+int ctag_get_dictionary(const ctag_detector* d, int* rows, int* cols, int* feature_size, int32_t* state_out, int cap) {
+  if (!d) return CTAG_ERR_ARG;
+  if (rows) *rows = d->rows;
+  if (cols) *cols = d->cols;
+  if (feature_size) *feature_size = d->feature_size;
+  if (state_out) {
+    if (cap < d->rows * d->cols) return CTAG_ERR_ARG;
+    memcpy(state_out, d->state.data(), sizeof(int32_t) * d->state.size());
+  }
+  return CTAG_OK;
+}
+
+int ctag_detect_batch_enqueue(ctag_detector* d, const void* frames_dev, int n, int w, int h, size_t pitch,
+                              size_t frame_stride, int channels, int adaptive_thresh, int corner_subpix,
+                              int subpix_dist) {
+  if (!d || !frames_dev || n <= 0 || w <= 0 || h <= 0) return CTAG_ERR_ARG;
+  if ((w & 1) || (h & 1)) return CTAG_ERR_ARG;  // exact 2x decimation needs even sizes
+  if (channels != 1 && channels != 3) return CTAG_ERR_ARG;
+  if (adaptive_thresh != kWin) return CTAG_ERR_UNSUPPORTED;
+  if (d->in_flight) return CTAG_ERR_ARG;
+  (void)corner_subpix;
+  (void)subpix_dist;
+  CTAG_CUDA_CHECK(cudaSetDevice(d->device));
+  if (frame_stride == 0) frame_stride = pitch * (size_t)h;
+  int rc = ensure_workspace(d, n, w, h);
+  if (rc != CTAG_OK) return rc;
+  d->cur_n = n;
+  d->cur_channels = channels;
+  d->launches = 0;
+  if (channels == 1) {
+    d->cur_gray = static_cast<const uint8_t*>(frames_dev);
+    d->cur_gray_pitch = pitch;
+    d->cur_gray_fstride = frame_stride;
+  } else {
+    d->cur_gray = d->d_gray;
+    d->cur_gray_pitch = d->geo.gpitch;
+    d->cur_gray_fstride = d->gray_fstride;
+  }
+  CTAG_CUDA_CHECK(cudaEventRecord(d->ev[0], d->stream));
+  rc = launch_front(frames_dev, n, d->geo, channels, pitch, frame_stride, d->d_gray, d->gray_fstride, d->d_bin,
+                    d->bin_fstride, d->stream);
+  if (rc != CTAG_OK) return rc;
+  d->launches += 1;
+  CTAG_CUDA_CHECK(cudaEventRecord(d->ev[1], d->stream));
+  d->in_flight = true;
+  return CTAG_OK;
+}
+
+int ctag_detect_batch_collect(ctag_detector* d, ctag_marker* out, int cap_per_frame, int* n_out, ctag_frame_info* info) {
+  if (!d || !d->in_flight) return CTAG_ERR_ARG;
+  (void)out;
+  (void)cap_per_frame;
+  CTAG_CUDA_CHECK(cudaSetDevice(d->device));
+  d->in_flight = false;
+  CTAG_CUDA_CHECK(cudaStreamSynchronize(d->stream));
+  cudaEventElapsedTime(&d->stage_ms[0], d->ev[0], d->ev[1]);
+  for (int f = 0; f < d->cur_n; ++f) {
+    if (n_out) n_out[f] = 0;
+    if (info) memset(&info[f], 0, sizeof(ctag_frame_info));
+  }
+  return CTAG_OK;
+}
+
+int ctag_detect_batch(ctag_detector* d, const void* frames, int n, int w, int h, size_t pitch, size_t frame_stride,
+                      int channels, int is_device, int adaptive_thresh, int corner_subpix, int subpix_dist,
+                      ctag_marker* out, int cap_per_frame, int* n_out, ctag_frame_info* info) {
+  if (!d || !frames || n <= 0 || w <= 0 || h <= 0) return CTAG_ERR_ARG;
+  if (channels != 1 && channels != 3) return CTAG_ERR_ARG;
+  const void* src = frames;
+  if (frame_stride == 0) frame_stride = pitch * (size_t)h;
+  if (!is_device) {
+    CTAG_CUDA_CHECK(cudaSetDevice(d->device));
+    // host frames: copy into a 16B-pitched device staging buffer (2-D copy normalises any host pitch)
+    size_t dpitch = (size_t)round_up(w * channels, 16);
+    size_t dfs = dpitch * h;
+    int rc = ensure_stage(d, dfs * n);
+    if (rc != CTAG_OK) return rc;
+    if (pitch < (size_t)w * channels) return CTAG_ERR_ARG;
+    for (int f = 0; f < n; ++f)
+      CTAG_CUDA_CHECK(cudaMemcpy2DAsync(d->d_stage + dfs * f, dpitch, static_cast<const uint8_t*>(frames) + frame_stride * f,
+                                        pitch, (size_t)w * channels, h, cudaMemcpyHostToDevice, d->stream));
+    src = d->d_stage;
+    pitch = dpitch;
+    frame_stride = dfs;
+  }
+  int rc = ctag_detect_batch_enqueue(d, src, n, w, h, pitch, frame_stride, channels, adaptive_thresh, corner_subpix,
+                                     subpix_dist);
+  if (rc != CTAG_OK) return rc;
+  return ctag_detect_batch_collect(d, out, cap_per_frame, n_out, info);
+}
+
+int ctag_detect(ctag_detector* d, const uint8_t* gray, int w, int h, size_t pitch, int adaptive_thresh, int corner_subpix,
+                int subpix_dist, ctag_marker* out, int cap, int* n_out, int* frame_status) {
+  ctag_frame_info info;
+  int n = 0;
+  int rc = ctag_detect_batch(d, gray, 1, w, h, pitch, 0, 1, 0, adaptive_thresh, corner_subpix, subpix_dist, out, cap, &n,
+                             &info);
+  if (rc != CTAG_OK) return rc;
+  if (n_out) *n_out = n;
+  if (frame_status) *frame_status = info.status;
+  return CTAG_OK;
+}
+
+int ctag_stage_time_ms(const ctag_detector* d, float* ms_out) {
+  if (!d || !ms_out) return CTAG_ERR_ARG;
+  for (int i = 0; i < CTAG_STAGE_COUNT; ++i) ms_out[i] = d->stage_ms[i];
+  return CTAG_OK;
+}
+
+int ctag_last_launch_count(const ctag_detector* d) { return d ? d->launches : 0; }
+void* ctag_stream(const ctag_detector* d) { return d ? (void*)d->stream : nullptr; }
+
+int ctag_debug_get_gray(ctag_detector* d, int frame, uint8_t* out, size_t out_pitch) {
+  if (!d || !out || frame < 0 || frame >= d->cur_n || !d->cur_gray) return CTAG_ERR_ARG;
+  CTAG_CUDA_CHECK(cudaSetDevice(d->device));
+  CTAG_CUDA_CHECK(cudaMemcpy2D(out, out_pitch, d->cur_gray + d->cur_gray_fstride * frame, d->cur_gray_pitch, d->w, d->h,
+                               cudaMemcpyDeviceToHost));
+  return CTAG_OK;
+}
+
+int ctag_debug_get_binary(ctag_detector* d, int frame, uint8_t* out, size_t out_pitch) {
+  if (!d || !out || frame < 0 || frame >= d->cur_n) return CTAG_ERR_ARG;
+  CTAG_CUDA_CHECK(cudaSetDevice(d->device));
+  CTAG_CUDA_CHECK(cudaMemcpy2D(out, out_pitch, d->d_bin + d->bin_fstride * frame, d->geo.bpitch, d->geo.hw, d->geo.hh,
+                               cudaMemcpyDeviceToHost));
+  return CTAG_OK;
+}
+
+int ctag_debug_get_components(ctag_detector*, int, int32_t*, int, int* n_out) {
+  if (n_out) *n_out = 0;
+  return CTAG_ERR_UNSUPPORTED;
+}
+int ctag_debug_get_quads(ctag_detector*, int, int32_t*, float*, int, int* n_out) {
+  if (n_out) *n_out = 0;
+  return CTAG_ERR_UNSUPPORTED;
+}
+int ctag_debug_get_features(ctag_detector*, int, float*, float*, float*, int32_t*, int, int* n_out) {
+  if (n_out) *n_out = 0;
+  return CTAG_ERR_UNSUPPORTED;
+}
+
+const char* ctag_strerror(int code) {
+  switch (code) {
+    case CTAG_OK: return "ok";
+    case CTAG_ERR_ARG: return "invalid argument";
+    case CTAG_ERR_FILE: return "could not open the file";
+    case CTAG_ERR_DICTIONARY: return "the number in state matrix must between 0 to 63";
+    case CTAG_ERR_CUDA: return "CUDA error";
+    case CTAG_ERR_NO_DEVICE: return "no usable sm_100 CUDA device (no CPU fallback)";
+    case CTAG_ERR_UNSUPPORTED: return "unsupported configuration";
+    case CTAG_ERR_CAPACITY: return "internal capacity exceeded";
+    case CTAG_ERR_ALIGNMENT: return "device input must be 16-byte aligned with pitch % 16 == 0";
+    default: return "unknown error";
+  }
+}
+
+const char* ctag_last_error(void) { return g_last_error; }
+const char* ctag_version(void) { return "cylindertag_b200 0.1 sm_100a"; }
+
+}  // extern "C"

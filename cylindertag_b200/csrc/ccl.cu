@@ -1,0 +1,349 @@
+// K2/K3: connected-component labelling + stats + ordered compaction  (reference row a4, corner_detector.cpp:81-107)
+//
+// The reference calls connectedComponentsWithStats(8-connectivity, CCL_BBDT) and then keeps the components with
+// 30 <= area <= round(0.01*w*h) in OpenCV label order.  BBDT numbers components in ascending order of the smallest
+// 2x2-block raster index they touch, so a union-find over 2x2 blocks whose root is always the minimum
+// block index yields the reference order directly: component order == ascending root index.
+//
+//   ccl_local  : one CTA per 32x32-block tile (64x64 px).  Union-find in shared memory, partial stats per local
+//                root, one label word per 2x2 block written to HBM (not one per pixel).
+//   ccl_merge  : unions across tile borders (global atomicMin union-find over the local roots only).
+//   ccl_final  : flattens every block label to its global root, folds the partial stats of merged local roots
+//                into the global root, lists the global roots of each 1024-block span in ascending order
+//                (ballot + prefix scan).
+//   ccl_list   : one CTA per frame: scan of the per-span root counts -> ordered component list, area filter,
+//                second scan -> ordered list of legal components {root, area, bbox}.
+//
+// A pixel (x,y) belongs to component `root` iff binary(x,y) != 0 and label[(y>>1)*bw + (x>>1)] == root, because all
+// foreground pixels of one 2x2 block are mutually 8-connected.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace ctag {
+
+constexpr int kTag = 1 << 30;  // label entry of a non-root block: kTag | index of its tile-local root
+
+// pattern bits: a=1 (x,y)  b=2 (x+1,y)  c=4 (x,y+1)  d=8 (x+1,y+1)
+__device__ __forceinline__ int block_pattern(const uint8_t* __restrict__ bin, const FrameGeom& g, int bx, int by) {
+  int x = 2 * bx, y = 2 * by;
+  int p = 0;
+  const uint8_t* r0 = bin + (size_t)y * g.bpitch + x;
+  // bpitch is a multiple of 16 and columns >= hw inside the pitch are zero (front kernel), so the 2-byte read is safe
+  uint16_t v0 = *reinterpret_cast<const uint16_t*>(r0);
+  p |= (v0 & 0xFF) ? 1 : 0;
+  p |= (v0 >> 8) ? 2 : 0;
+  if (y + 1 < g.hh) {
+    uint16_t v1 = *reinterpret_cast<const uint16_t*>(r0 + g.bpitch);
+    p |= (v1 & 0xFF) ? 4 : 0;
+    p |= (v1 >> 8) ? 8 : 0;
+  }
+  return p;
+}
+
+__device__ __forceinline__ int uf_find(volatile int* L, int x) {
+  int p;
+  while ((p = L[x]) != x) x = p;
+  return x;
+}
+
+// union by minimum index (root of a set is always its smallest member)
+__device__ __forceinline__ void uf_unite(int* L, int a, int b) {
+  while (true) {
+    a = uf_find(L, a);
+    b = uf_find(L, b);
+    if (a == b) return;
+    if (a < b) {
+      int t = a;
+      a = b;
+      b = t;
+    }
+    int old = atomicMin(&L[a], b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+__global__ void __launch_bounds__(1024) ccl_local_kernel(const uint8_t* __restrict__ bin, size_t bin_fstride, FrameGeom g,
+                                                         int* __restrict__ labels, int* __restrict__ st_area,
+                                                         int* __restrict__ st_x0, int* __restrict__ st_y0,
+                                                         int* __restrict__ st_x1, int* __restrict__ st_y1) {
+  __shared__ int L[1024];
+  __shared__ uint8_t pat[1024];
+  __shared__ int sA[1024], sX0[1024], sY0[1024], sX1[1024], sY1[1024];
+  const int t = threadIdx.x, tx = t & 31, ty = t >> 5;
+  const int bx = blockIdx.x * 32 + tx, by = blockIdx.y * 32 + ty, fr = blockIdx.z;
+  const bool inside = bx < g.bw && by < g.bh;
+  int p = 0;
+  if (inside) p = block_pattern(bin + (size_t)fr * bin_fstride, g, bx, by);
+  pat[t] = (uint8_t)p;
+  L[t] = p ? t : -1;
+  sA[t] = 0;
+  sX0[t] = 0x7fffffff;
+  sY0[t] = 0x7fffffff;
+  sX1[t] = -1;
+  sY1[t] = -1;
+  __syncthreads();
+  if (p) {
+    if (ty > 0) {
+      int q = pat[t - 32];
+      if ((p & 3) && (q & 12)) uf_unite(L, t, t - 32);
+      if (tx > 0 && (p & 1) && (pat[t - 33] & 8)) uf_unite(L, t, t - 33);
+      if (tx < 31 && (p & 2) && (pat[t - 31] & 4)) uf_unite(L, t, t - 31);
+    }
+    if (tx > 0 && (p & 5) && (pat[t - 1] & 10)) uf_unite(L, t, t - 1);
+  }
+  __syncthreads();
+  int r = -1;
+  if (p) r = uf_find(L, t);
+  __syncthreads();
+  if (p) L[t] = r;
+  // partial stats per local root, aggregated per warp (one warp = one row of 32 blocks) before touching smem atomics
+  {
+    unsigned active = __ballot_sync(0xffffffffu, p != 0);
+    if (p) {
+      unsigned grp = __match_any_sync(active, r);
+      int x = 2 * bx, y = 2 * by;
+      int xmin = (p & 5) ? x : x + 1, xmax = (p & 10) ? x + 1 : x;
+      int ymin = (p & 3) ? y : y + 1, ymax = (p & 12) ? y + 1 : y;
+      int a = __reduce_add_sync(grp, __popc(p));
+      xmin = __reduce_min_sync(grp, xmin);
+      ymin = __reduce_min_sync(grp, ymin);
+      xmax = __reduce_max_sync(grp, xmax);
+      ymax = __reduce_max_sync(grp, ymax);
+      if ((int)(__ffs(grp) - 1) == tx) {
+        atomicAdd(&sA[r], a);
+        atomicMin(&sX0[r], xmin);
+        atomicMin(&sY0[r], ymin);
+        atomicMax(&sX1[r], xmax);
+        atomicMax(&sY1[r], ymax);
+      }
+    }
+  }
+  __syncthreads();
+  if (inside) {
+    size_t base = (size_t)fr * g.nblocks;
+    int gi = by * g.bw + bx;
+    int e = -1;
+    if (p) {
+      int gr = (blockIdx.y * 32 + (r >> 5)) * g.bw + blockIdx.x * 32 + (r & 31);
+      if (r == t) {
+        e = gi;
+        st_area[base + gi] = sA[t];
+        st_x0[base + gi] = sX0[t];
+        st_y0[base + gi] = sY0[t];
+        st_x1[base + gi] = sX1[t];
+        st_y1[base + gi] = sY1[t];
+      } else {
+        e = kTag | gr;
+      }
+    }
+    labels[base + gi] = e;
+  }
+}
+
+__device__ __forceinline__ int gfind(volatile int* lab, int x) {
+  int e = lab[x];
+  if (e & kTag) x = e & ~kTag;  // hop from a leaf to its tile-local root (e >= 0 here: callers pass foreground blocks)
+  int p;
+  while ((p = lab[x]) != x) x = p;
+  return x;
+}
+
+__device__ __forceinline__ void gunite(int* lab, int a, int b) {
+  while (true) {
+    a = gfind(lab, a);
+    b = gfind(lab, b);
+    if (a == b) return;
+    if (a < b) {
+      int t = a;
+      a = b;
+      b = t;
+    }
+    int old = atomicMin(&lab[a], b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+// 64 threads per tile: threads 0..31 = top row of the tile (checks UL,U,UR), 32..63 = left column (checks L,UL,DL)
+__global__ void __launch_bounds__(64) ccl_merge_kernel(const uint8_t* __restrict__ bin, size_t bin_fstride, FrameGeom g,
+                                                       int* __restrict__ labels) {
+  const int t = threadIdx.x, fr = blockIdx.z;
+  const uint8_t* b = bin + (size_t)fr * bin_fstride;
+  int* lab = labels + (size_t)fr * g.nblocks;
+  int bx, by;
+  const bool toprow = t < 32;
+  if (toprow) {
+    bx = blockIdx.x * 32 + t;
+    by = blockIdx.y * 32;
+  } else {
+    bx = blockIdx.x * 32;
+    by = blockIdx.y * 32 + (t - 32);
+  }
+  if (bx >= g.bw || by >= g.bh) return;
+  int p = block_pattern(b, g, bx, by);
+  if (!p) return;
+  int i = by * g.bw + bx;
+  if (toprow) {
+    if (by == 0) return;
+    int q = block_pattern(b, g, bx, by - 1);
+    if ((p & 3) && (q & 12)) gunite(lab, i, i - g.bw);
+    if (bx > 0 && (p & 1) && (block_pattern(b, g, bx - 1, by - 1) & 8)) gunite(lab, i, i - g.bw - 1);
+    if (bx < g.bw - 1 && (p & 2) && (block_pattern(b, g, bx + 1, by - 1) & 4)) gunite(lab, i, i - g.bw + 1);
+  } else {
+    if (bx == 0) return;
+    int q = block_pattern(b, g, bx - 1, by);
+    if ((p & 5) && (q & 10)) gunite(lab, i, i - 1);
+    if (by > 0 && (p & 1) && (block_pattern(b, g, bx - 1, by - 1) & 8)) gunite(lab, i, i - g.bw - 1);
+    if (by < g.bh - 1 && (p & 4) && (block_pattern(b, g, bx - 1, by + 1) & 2)) gunite(lab, i, i + g.bw - 1);
+  }
+}
+
+// One thread per block.  roots_tmp[span*1024 + k] = k-th global root (ascending) of the span; span_count[span].
+__global__ void __launch_bounds__(1024) ccl_final_kernel(FrameGeom g, int* __restrict__ labels, int* __restrict__ st_area,
+                                                         int* __restrict__ st_x0, int* __restrict__ st_y0,
+                                                         int* __restrict__ st_x1, int* __restrict__ st_y1,
+                                                         int* __restrict__ roots_tmp, int* __restrict__ span_count,
+                                                         int spans_per_frame) {
+  __shared__ int warp_cnt[32];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int fr = blockIdx.y;
+  const size_t base = (size_t)fr * g.nblocks;
+  int* lab = labels + base;
+  const int i = blockIdx.x * 1024 + t;
+  bool is_root = false;
+  if (i < g.nblocks) {
+    int e = lab[i];
+    if (e >= 0) {
+      int r = gfind(lab, i);
+      if (e & kTag) {
+        lab[i] = r;
+      } else if (r != i) {
+        // a tile-local root that was merged into another tree: fold its partial stats into the global root
+        atomicAdd(&st_area[base + r], st_area[base + i]);
+        atomicMin(&st_x0[base + r], st_x0[base + i]);
+        atomicMin(&st_y0[base + r], st_y0[base + i]);
+        atomicMax(&st_x1[base + r], st_x1[base + i]);
+        atomicMax(&st_y1[base + r], st_y1[base + i]);
+        lab[i] = r;
+      } else {
+        is_root = true;
+      }
+    }
+  }
+  unsigned bal = __ballot_sync(0xffffffffu, is_root);
+  if (lane == 0) warp_cnt[wid] = __popc(bal);
+  __syncthreads();
+  if (wid == 0) {
+    int v = warp_cnt[lane];
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int n = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += n;
+    }
+    warp_cnt[lane] = inc - v;  // exclusive
+    if (lane == 31) span_count[fr * spans_per_frame + blockIdx.x] = inc;
+  }
+  __syncthreads();
+  if (is_root) {
+    int pos = warp_cnt[wid] + __popc(bal & ((1u << lane) - 1));
+    roots_tmp[base + (size_t)blockIdx.x * 1024 + pos] = i;
+  }
+}
+
+__device__ __forceinline__ int block_exclusive_scan_1024(int v, int* total, int* sh /*33 ints*/) {
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int n = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += n;
+  }
+  __syncthreads();
+  if (lane == 31) sh[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int w = sh[lane];
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int n = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += n;
+    }
+    sh[lane] = winc - w;
+    if (lane == 31) sh[32] = winc;
+  }
+  __syncthreads();
+  *total = sh[32];
+  return sh[wid] + inc - v;
+}
+
+// One CTA per frame.  legal[frame][k] = {root, area, x0, y0, x1, y1} in ascending root order (= OpenCV label order).
+__global__ void __launch_bounds__(1024) ccl_list_kernel(FrameGeom g, const int* __restrict__ st_area,
+                                                        const int* __restrict__ st_x0, const int* __restrict__ st_y0,
+                                                        const int* __restrict__ st_x1, const int* __restrict__ st_y1,
+                                                        const int* __restrict__ roots_tmp, const int* __restrict__ span_count,
+                                                        int spans_per_frame, int* __restrict__ legal, int legal_cap,
+                                                        int* __restrict__ counters /* [frame][4]: n_comp, n_legal, overflow */) {
+  __shared__ int sh[33];
+  const int t = threadIdx.x, fr = blockIdx.x;
+  const size_t base = (size_t)fr * g.nblocks;
+  int comp_base = 0, legal_base = 0;
+  for (int s0 = 0; s0 < spans_per_frame; s0 += 1024) {
+    int s = s0 + t;
+    int c = (s < spans_per_frame) ? span_count[fr * spans_per_frame + s] : 0;
+    int lc = 0;
+    for (int k = 0; k < c; ++k) {
+      int a = st_area[base + roots_tmp[base + (size_t)s * 1024 + k]];
+      lc += (a >= kAreaMin && a <= g.area_max) ? 1 : 0;
+    }
+    int tot_c, tot_l;
+    (void)block_exclusive_scan_1024(c, &tot_c, sh);
+    int loff = block_exclusive_scan_1024(lc, &tot_l, sh);
+    int o = legal_base + loff;
+    for (int k = 0; k < c; ++k) {
+      int r = roots_tmp[base + (size_t)s * 1024 + k];
+      int a = st_area[base + r];
+      if (a >= kAreaMin && a <= g.area_max) {
+        if (o < legal_cap) {
+          int* dst = legal + ((size_t)fr * legal_cap + o) * 6;
+          dst[0] = r;
+          dst[1] = a;
+          dst[2] = st_x0[base + r];
+          dst[3] = st_y0[base + r];
+          dst[4] = st_x1[base + r];
+          dst[5] = st_y1[base + r];
+        }
+        ++o;
+      }
+    }
+    comp_base += tot_c;
+    legal_base += tot_l;
+    __syncthreads();
+  }
+  if (t == 0) {
+    counters[fr * 4 + 0] = comp_base;
+    counters[fr * 4 + 1] = legal_base < legal_cap ? legal_base : legal_cap;
+    counters[fr * 4 + 2] = legal_base > legal_cap ? 1 : 0;
+    counters[fr * 4 + 3] = 0;
+  }
+}
+
+int launch_ccl(const uint8_t* bin, size_t bin_fstride, int n, const FrameGeom& g, int* labels, int* st_area, int* st_x0,
+               int* st_y0, int* st_x1, int* st_y1, int* roots_tmp, int* span_count, int* legal, int legal_cap,
+               int* counters, cudaStream_t stream, int* launches) {
+  dim3 tiles((g.bw + 31) / 32, (g.bh + 31) / 32, n);
+  ccl_local_kernel<<<tiles, 1024, 0, stream>>>(bin, bin_fstride, g, labels, st_area, st_x0, st_y0, st_x1, st_y1);
+  ccl_merge_kernel<<<tiles, 64, 0, stream>>>(bin, bin_fstride, g, labels);
+  int spans = (g.nblocks + 1023) / 1024;
+  ccl_final_kernel<<<dim3(spans, n), 1024, 0, stream>>>(g, labels, st_area, st_x0, st_y0, st_x1, st_y1, roots_tmp,
+                                                        span_count, spans);
+  ccl_list_kernel<<<n, 1024, 0, stream>>>(g, st_area, st_x0, st_y0, st_x1, st_y1, roots_tmp, span_count, spans, legal,
+                                          legal_cap, counters);
+  CTAG_CUDA_CHECK(cudaGetLastError());
+  if (launches) *launches += 4;
+  return CTAG_OK;
+}
+
+}  // namespace ctag

@@ -1,0 +1,147 @@
+"""Python host-side mirror of the reference detect interface over the C ABI (include/ctag.h).
+
+`Detector` is the thin handle wrapper the parity tests and bench drive; `CylinderTag` (api.py) keeps the reference's
+class surface (header/CylinderTag.h:12-52).  Every call goes to the CUDA library; nothing here computes detections.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _capi as C
+
+
+def _ptr(arr):
+    return ctypes.c_void_p(arr.ctypes.data)
+
+
+class Detector:
+    """One detector per CUDA device / host thread (the reference object is not re-entrant either)."""
+
+    def __init__(self, state=None, feature_size=None, marker_path=None, device=-1):
+        self._lib = C.load()
+        self._h = ctypes.c_void_p()
+        if marker_path is not None:
+            C.check(self._lib.ctag_create_from_file(ctypes.byref(self._h), str(marker_path).encode(), device), "ctag_create_from_file")
+        else:
+            st = np.ascontiguousarray(state, dtype=np.int32)
+            if st.ndim != 2 or feature_size is None:
+                raise ValueError("state must be a 2-D int matrix and feature_size must be given")
+            C.check(self._lib.ctag_create(ctypes.byref(self._h), _ptr(st), st.shape[0], st.shape[1], int(feature_size), device), "ctag_create")
+        r, c, f = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        C.check(self._lib.ctag_get_dictionary(self._h, ctypes.byref(r), ctypes.byref(c), ctypes.byref(f), None, 0), "ctag_get_dictionary")
+        self.rows, self.cols, self.feature_size = r.value, c.value, f.value
+        self._shape = None
+        self._n = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ctag_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def state(self):
+        out = np.zeros((self.rows, self.cols), np.int32)
+        C.check(self._lib.ctag_get_dictionary(self._h, None, None, None, _ptr(out), out.size), "ctag_get_dictionary")
+        return out
+
+    # ---- detection ------------------------------------------------------------------------------------------
+    def detect_batch(self, frames, adaptive_thresh=5, corner_subpix=False, subpix_dist=3, cap_per_frame=16):
+        """frames: host uint8 array [n,h,w] (gray) or [n,h,w,3] (BGR).  Returns (markers, counts, info) numpy
+        structured arrays: markers[n, cap_per_frame], counts[n], info[n]."""
+        fr = np.ascontiguousarray(frames, dtype=np.uint8)
+        if fr.ndim == 3:
+            n, h, w = fr.shape
+            ch = 1
+        elif fr.ndim == 4 and fr.shape[3] == 3:
+            n, h, w, ch = fr.shape
+        else:
+            raise ValueError("frames must be [n,h,w] or [n,h,w,3] uint8")
+        out = np.zeros((n, cap_per_frame), C.MARKER_DTYPE)
+        cnt = np.zeros(n, np.int32)
+        info = np.zeros(n, C.INFO_DTYPE)
+        C.check(self._lib.ctag_detect_batch(self._h, _ptr(fr), n, w, h, w * ch, 0, ch, 0, int(adaptive_thresh),
+                                            int(bool(corner_subpix)), int(subpix_dist), _ptr(out), cap_per_frame,
+                                            _ptr(cnt), _ptr(info)), "ctag_detect_batch")
+        self._shape, self._n = (h, w), n
+        return out, cnt, info
+
+    def detect(self, gray, adaptive_thresh=5, corner_subpix=False, subpix_dist=3, cap=16):
+        """Single 8-bit gray host image through ctag_detect.  Returns (markers[count], frame_status)."""
+        g = np.ascontiguousarray(gray, dtype=np.uint8)
+        if g.ndim != 2:
+            raise ValueError("detect expects an 8-bit single-channel image (CylinderTag.cpp:67)")
+        h, w = g.shape
+        out = np.zeros(cap, C.MARKER_DTYPE)
+        n, st = ctypes.c_int(), ctypes.c_int()
+        C.check(self._lib.ctag_detect(self._h, _ptr(g), w, h, w, int(adaptive_thresh), int(bool(corner_subpix)),
+                                      int(subpix_dist), _ptr(out), cap, ctypes.byref(n), ctypes.byref(st)), "ctag_detect")
+        self._shape, self._n = (h, w), 1
+        return out[:min(n.value, cap)], st.value
+
+    def enqueue_device(self, dev_ptr, n, w, h, pitch, frame_stride, channels, adaptive_thresh=5, corner_subpix=False,
+                       subpix_dist=3):
+        C.check(self._lib.ctag_detect_batch_enqueue(self._h, ctypes.c_void_p(dev_ptr), n, w, h, pitch, frame_stride,
+                                                    channels, int(adaptive_thresh), int(bool(corner_subpix)),
+                                                    int(subpix_dist)), "ctag_detect_batch_enqueue")
+        self._shape, self._n = (h, w), n
+
+    def collect(self, cap_per_frame=16):
+        n = self._n
+        out = np.zeros((n, cap_per_frame), C.MARKER_DTYPE)
+        cnt = np.zeros(n, np.int32)
+        info = np.zeros(n, C.INFO_DTYPE)
+        C.check(self._lib.ctag_detect_batch_collect(self._h, _ptr(out), cap_per_frame, _ptr(cnt), _ptr(info)), "ctag_detect_batch_collect")
+        return out, cnt, info
+
+    # ---- instrumentation ------------------------------------------------------------------------------------
+    def stage_times_ms(self):
+        ms = (ctypes.c_float * len(C.STAGE_NAMES))()
+        C.check(self._lib.ctag_stage_time_ms(self._h, ms), "ctag_stage_time_ms")
+        return dict(zip(C.STAGE_NAMES, [float(v) for v in ms]))
+
+    def launch_count(self):
+        return int(self._lib.ctag_last_launch_count(self._h))
+
+    def stream(self):
+        return self._lib.ctag_stream(self._h)
+
+    def debug_gray(self, frame=0):
+        h, w = self._shape
+        out = np.zeros((h, w), np.uint8)
+        C.check(self._lib.ctag_debug_get_gray(self._h, frame, _ptr(out), w), "ctag_debug_get_gray")
+        return out
+
+    def debug_binary(self, frame=0):
+        h, w = self._shape
+        out = np.zeros((h // 2, w // 2), np.uint8)
+        C.check(self._lib.ctag_debug_get_binary(self._h, frame, _ptr(out), w // 2), "ctag_debug_get_binary")
+        return out
+
+    def debug_components(self, frame=0, cap=65536):
+        out = np.zeros((cap, 6), np.int32)
+        n = ctypes.c_int()
+        C.check(self._lib.ctag_debug_get_components(self._h, frame, _ptr(out), cap, ctypes.byref(n)), "ctag_debug_get_components")
+        return out[:n.value]
+
+    def debug_quads(self, frame=0, cap=4096):
+        idx = np.zeros(cap, np.int32)
+        cor = np.zeros((cap, 4, 2), np.float32)
+        n = ctypes.c_int()
+        C.check(self._lib.ctag_debug_get_quads(self._h, frame, _ptr(idx), _ptr(cor), cap, ctypes.byref(n)), "ctag_debug_get_quads")
+        return idx[:n.value], cor[:n.value]
+
+    def debug_features(self, frame=0, cap=256):
+        cor = np.zeros((cap, 8, 2), np.float32)
+        cen = np.zeros((cap, 2), np.float32)
+        ang = np.zeros(cap, np.float32)
+        qp = np.zeros((cap, 2), np.int32)
+        n = ctypes.c_int()
+        C.check(self._lib.ctag_debug_get_features(self._h, frame, _ptr(cor), _ptr(cen), _ptr(ang), _ptr(qp), cap, ctypes.byref(n)), "ctag_debug_get_features")
+        k = n.value
+        return cor[:k], cen[:k], ang[:k], qp[:k]

@@ -1,0 +1,174 @@
+/*
+ * ctag.h -- C ABI of the B200-native CylinderTag detection front end.
+ *
+ * This is the drop-in boundary for the reference's per-frame detect path
+ * (wsakobe/CylinderTag).  Every entry point names the reference interface it
+ * replaces (file:line in the reference tree).  Plain pointers and sizes only;
+ * no C++/torch/OpenCV types cross this boundary.  The C++ class
+ * `CylinderTag` in include/cylindertag/CylinderTag.h and the Python class
+ * `cylindertag_b200.CylinderTag` are thin wrappers over these calls.
+ *
+ * All compute runs in hand-written sm_100a CUDA kernels; there is no CPU
+ * fallback: if no CUDA device is usable every call fails with
+ * CTAG_ERR_CUDA / CTAG_ERR_NO_DEVICE.
+ *
+ * Threading: like the reference object (scratch members,
+ * header/corner_detector.h:61-156) a ctag_detector is NOT re-entrant.  Use
+ * one detector per host thread / CUDA device; calls on one handle are
+ * serialised by the caller.
+ */
+#ifndef CTAG_H
+#define CTAG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define CTAG_API __attribute__((visibility("default")))
+#else
+#define CTAG_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTAG_MAX_FEATURES 20 /* reference: code[20], header/corner_detector.h:152 */
+#define CTAG_MAX_FRAME_FEATURES 100 /* reference: father[100], header/corner_detector.h:143 */
+#define CTAG_MAX_FRAME_QUADS 1000 /* reference: isVisited[1000], header/corner_detector.h:124 */
+
+/* Return codes. 0 = OK (zero markers is not an error, CylinderTag.cpp:87-96). */
+enum {
+  CTAG_OK = 0,
+  CTAG_ERR_ARG = -1,         /* bad argument (null pointer, odd size, ...) */
+  CTAG_ERR_FILE = -2,        /* replaces `throw "... could not open the file"` (CylinderTag.cpp:21,165) */
+  CTAG_ERR_DICTIONARY = -3,  /* replaces `throw "... must between 0 to 63"` (CylinderTag.cpp:56-65) */
+  CTAG_ERR_CUDA = -4,        /* CUDA runtime/driver failure; see ctag_last_error() */
+  CTAG_ERR_NO_DEVICE = -5,   /* no usable sm_100 device: there is NO CPU fallback */
+  CTAG_ERR_UNSUPPORTED = -6, /* configuration outside the implemented envelope */
+  CTAG_ERR_CAPACITY = -7,    /* an internal device list overflowed its capacity */
+  CTAG_ERR_ALIGNMENT = -8    /* device input not 16-byte aligned / pitch not a multiple of 16 */
+};
+
+/* Per-frame status (reference early exits, CylinderTag.cpp:87-96). */
+enum {
+  CTAG_FRAME_OK = 0,
+  CTAG_FRAME_NO_CORNER = 1,  /* "No corner detected!"  -> reference leaves the output untouched */
+  CTAG_FRAME_NO_FEATURE = 2  /* "No feature detected!" -> reference leaves the output untouched */
+};
+
+typedef struct ctag_detector ctag_detector;
+
+/* POD image of the reference's MarkerInfo (header/corner_detector.h:16-22), one decoded marker. */
+typedef struct ctag_marker {
+  int32_t marker_id;  /* MarkerInfo::markerID = dictionary row */
+  int32_t n_features; /* cornerLists.size() */
+  int32_t inverse;    /* pos_with_ID::inverse; corner halves already swapped (corner_detector.cpp:1239-1246) */
+  int32_t frame;      /* index of the frame inside the batch */
+  int32_t feature_pos[CTAG_MAX_FEATURES];
+  int32_t feature_id[CTAG_MAX_FEATURES];
+  int32_t id_left[CTAG_MAX_FEATURES];
+  int32_t id_right[CTAG_MAX_FEATURES];
+  float cr_left[CTAG_MAX_FEATURES];
+  float cr_right[CTAG_MAX_FEATURES];
+  float edge_length[CTAG_MAX_FEATURES];
+  float center[CTAG_MAX_FEATURES][2];
+  float corners[CTAG_MAX_FEATURES][8][2]; /* full-resolution pixel coordinates, 8-corner order of SURVEY D.4 */
+} ctag_marker;
+
+/* Per-frame counters (the reference has no metrics; SURVEY 5 asks for per-stage counters). */
+typedef struct ctag_frame_info {
+  int32_t status;      /* CTAG_FRAME_* */
+  int32_t n_labels;    /* connected components incl. background (connectedComponentsWithStats return value) */
+  int32_t n_legal;     /* components passing the area test (corner_detector.cpp:88) */
+  int32_t n_quads;     /* corners_init.size() after edgeExtraction */
+  int32_t n_features;  /* features.size() after featureRecovery */
+  int32_t n_groups;    /* markers.size() after markerOrganization */
+  int32_t n_markers;   /* decoded markers */
+  int32_t flagged;     /* 1 if a reference fixed-array limit was exceeded (SURVEY C-4): frame excluded from parity */
+  int32_t stale_ids;   /* cross-ratio band misses that reuse the previous ID (SURVEY C-2) */
+  int32_t reserved[3];
+} ctag_frame_info;
+
+/* ---- construction -------------------------------------------------------------------------- */
+
+/* Replaces CylinderTag::CylinderTag(const Mat1i&) (CylinderTag.cpp:11-14,43-54).  `state` is rows x cols,
+ * row-major, every entry in [0,63].  `feature_size` must be given (the reference leaves it unset, SURVEY C-3).
+ * `cuda_device` < 0 selects the current device. */
+CTAG_API int ctag_create(ctag_detector** out, const int32_t* state, int rows, int cols, int feature_size, int cuda_device);
+
+/* Replaces CylinderTag::CylinderTag(const string&) / load_from_file (CylinderTag.cpp:6-9,16-41). */
+CTAG_API int ctag_create_from_file(ctag_detector** out, const char* marker_path, int cuda_device);
+
+CTAG_API void ctag_destroy(ctag_detector* det);
+
+/* Dictionary accessors (state matrix the detector holds, header/CylinderTag.h:44-45). */
+CTAG_API int ctag_get_dictionary(const ctag_detector* det, int* rows, int* cols, int* feature_size, int32_t* state_out, int cap);
+
+/* ---- detection ----------------------------------------------------------------------------- */
+
+/* Replaces CylinderTag::detect(img, markers, adaptiveThresh, cornerSubPix, cornerSubPixDist)
+ * (CylinderTag.cpp:67-128) for one 8-bit single-channel HOST image (any pitch), synchronous.
+ * Writes at most `cap` markers and the true count to *n_out.  *frame_status (optional) receives CTAG_FRAME_*:
+ * on the two reference early exits the C++ wrapper leaves the caller's vector untouched. */
+CTAG_API int ctag_detect(ctag_detector* det, const uint8_t* gray, int w, int h, size_t pitch, int adaptive_thresh,
+                int corner_subpix, int subpix_dist, ctag_marker* out, int cap, int* n_out, int* frame_status);
+
+/* Batched form of the same path: `n` independent frames (the reference's video loop main.cpp:52-60).
+ * frames      : host (is_device=0) or device (is_device=1) pointer to frame 0
+ * channels    : 1 = gray (detect's contract), 3 = BGR interleaved (then the caller's cvtColor, main.cpp:54, is fused in)
+ * pitch       : bytes between rows; frame_stride: bytes between frames (0 -> pitch*h)
+ * out         : host array of n*cap_per_frame markers, frame f's markers start at out[f*cap_per_frame]
+ * n_out       : host array of n counts; info (optional): host array of n ctag_frame_info
+ * Device inputs must be 16-byte aligned with pitch % 16 == 0 (TMA requirement). */
+CTAG_API int ctag_detect_batch(ctag_detector* det, const void* frames, int n, int w, int h, size_t pitch, size_t frame_stride,
+                      int channels, int is_device, int adaptive_thresh, int corner_subpix, int subpix_dist,
+                      ctag_marker* out, int cap_per_frame, int* n_out, ctag_frame_info* info);
+
+/* Asynchronous pair for device-resident throughput runs: enqueue the whole detect path for a batch on the detector's
+ * stream, then collect.  Between the two calls the host is free (e.g. to upload the next batch). */
+CTAG_API int ctag_detect_batch_enqueue(ctag_detector* det, const void* frames_dev, int n, int w, int h, size_t pitch,
+                              size_t frame_stride, int channels, int adaptive_thresh, int corner_subpix, int subpix_dist);
+CTAG_API int ctag_detect_batch_collect(ctag_detector* det, ctag_marker* out, int cap_per_frame, int* n_out, ctag_frame_info* info);
+
+/* ---- instrumentation ------------------------------------------------------------------------ */
+
+/* Stage identifiers for ctag_stage_time_ms / ctag_debug_*. */
+enum {
+  CTAG_STAGE_FRONT = 0,   /* a0-a3: gray + 2x cubic decimation + tile min/max + threshold (fused) */
+  CTAG_STAGE_CCL = 1,     /* a4: block-based union-find labelling + stats + ordered compaction */
+  CTAG_STAGE_QUAD = 2,    /* a5: per-component boundary trace, RDP, line fits, quad selection */
+  CTAG_STAGE_FEATURE = 3, /* a6-a8: pairing, coordinate lift, edge refinement */
+  CTAG_STAGE_DECODE = 4,  /* a9-a10: grouping, cross-ratio IDs, dictionary match */
+  CTAG_STAGE_COUNT = 5
+};
+
+/* GPU time (ms, CUDA events on the detector's stream) of each stage in the most recent collected batch. */
+CTAG_API int ctag_stage_time_ms(const ctag_detector* det, float* ms_out /* CTAG_STAGE_COUNT */);
+/* Number of kernel launches issued by the most recent batch. */
+CTAG_API int ctag_last_launch_count(const ctag_detector* det);
+/* CUDA stream (cudaStream_t) the detector launches on, for callers that time with their own events. */
+CTAG_API void* ctag_stream(const ctag_detector* det);
+
+/* Stage dumps of the most recent batch for parity tests (copied to host buffers). */
+CTAG_API int ctag_debug_get_gray(ctag_detector* det, int frame, uint8_t* out, size_t out_pitch);     /* w x h */
+CTAG_API int ctag_debug_get_binary(ctag_detector* det, int frame, uint8_t* out, size_t out_pitch);   /* (w/2) x (h/2), {0,255} */
+/* legal components in reference order: 6 ints each {root_block, area, x0, y0, x1, y1} (inclusive bbox, half-res) */
+CTAG_API int ctag_debug_get_components(ctag_detector* det, int frame, int32_t* out, int cap, int* n_out);
+/* quads in component order: comp index + 4 corners (half-res coords) */
+CTAG_API int ctag_debug_get_quads(ctag_detector* det, int frame, int32_t* comp_index, float* corners /* [cap][4][2] */, int cap,
+                         int* n_out);
+/* features after refinement: 8 corners, centre, angle, source quad indices */
+CTAG_API int ctag_debug_get_features(ctag_detector* det, int frame, float* corners /* [cap][8][2] */, float* center /* [cap][2] */,
+                            float* angle, int32_t* quad_pair /* [cap][2] */, int cap, int* n_out);
+
+CTAG_API const char* ctag_strerror(int code);
+/* Text of the last CUDA error seen by this thread (empty string if none). */
+CTAG_API const char* ctag_last_error(void);
+/* Library/build identification, e.g. "cylindertag_b200 0.1 sm_100a". */
+CTAG_API const char* ctag_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTAG_H */
