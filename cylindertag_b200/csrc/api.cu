@@ -58,6 +58,17 @@ struct ctag_detector {
   uint8_t* d_gray = nullptr;   // [cap_frames][h][gpitch]   (BGR input only)
   uint8_t* d_bin = nullptr;    // [cap_frames][hh][bpitch]
   size_t gray_fstride = 0, bin_fstride = 0;
+  // CCL (a4)
+  int *d_labels = nullptr, *d_st_area = nullptr, *d_st_x0 = nullptr, *d_st_y0 = nullptr, *d_st_x1 = nullptr,
+      *d_st_y1 = nullptr, *d_roots_tmp = nullptr, *d_span_count = nullptr, *d_legal = nullptr, *d_counters = nullptr;
+  int legal_cap = 0, spans = 0;
+  // quads (a5)
+  int *d_prefix = nullptr, *d_work_counter = nullptr, *d_quad_status = nullptr, *d_quad_comp = nullptr,
+      *d_n_quads = nullptr;
+  float *d_quad_corners = nullptr, *d_quads = nullptr;
+  uint8_t* d_quad_scratch = nullptr;
+  int scratch_warps = 0;
+  static constexpr int kQuadCap = CTAG_MAX_FRAME_QUADS;
 
   // state of the batch in flight / last batch
   int cur_n = 0, cur_channels = 0;
@@ -92,10 +103,21 @@ static int select_device(int cuda_device, int* chosen) {
 
 static void free_workspace(ctag_detector* d) {
   // d_stage is managed separately (ensure_stage): it may hold the batch that is about to be processed
-  cudaFree(d->d_gray);
-  cudaFree(d->d_bin);
-  d->d_gray = d->d_bin = nullptr;
+  void* ptrs[] = {d->d_gray, d->d_bin, d->d_labels, d->d_st_area, d->d_st_x0, d->d_st_y0, d->d_st_x1, d->d_st_y1,
+                  d->d_roots_tmp, d->d_span_count, d->d_legal, d->d_counters, d->d_prefix, d->d_work_counter,
+                  d->d_quad_status, d->d_quad_comp, d->d_n_quads, d->d_quad_corners, d->d_quads, d->d_quad_scratch};
+  for (void* p : ptrs) cudaFree(p);
+  d->d_gray = d->d_bin = d->d_quad_scratch = nullptr;
+  d->d_labels = d->d_st_area = d->d_st_x0 = d->d_st_y0 = d->d_st_x1 = d->d_st_y1 = d->d_roots_tmp = d->d_span_count =
+      d->d_legal = d->d_counters = d->d_prefix = d->d_work_counter = d->d_quad_status = d->d_quad_comp = d->d_n_quads =
+          nullptr;
+  d->d_quad_corners = d->d_quads = nullptr;
   d->cap_frames = 0;
+}
+
+template <typename T>
+static cudaError_t dev_alloc(T** p, size_t count) {
+  return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
 }
 
 static int ensure_workspace(ctag_detector* d, int n, int w, int h) {
@@ -110,6 +132,33 @@ static int ensure_workspace(ctag_detector* d, int n, int w, int h) {
   d->bin_fstride = (size_t)g.bpitch * g.hh;
   CTAG_CUDA_CHECK(cudaMalloc(&d->d_gray, d->gray_fstride * cap));
   CTAG_CUDA_CHECK(cudaMalloc(&d->d_bin, d->bin_fstride * cap));
+  const size_t nb = (size_t)g.nblocks * cap;
+  d->spans = (g.nblocks + 1023) / 1024;
+  d->legal_cap = g.hw * g.hh / kAreaMin + 1;  // every legal component has >= 30 pixels
+  if (d->legal_cap > 65536) d->legal_cap = 65536;
+  CTAG_CUDA_CHECK(dev_alloc(&d->d_labels, nb));
+  CTAG_CUDA_CHECK(dev_alloc(&d->d_st_area, nb));
+  CTAG_CUDA_CHECK(dev_alloc(&d->d_st_x0, nb));
+  CTAG_CUDA_CHECK(dev_alloc(&d->d_st_y0, nb));
+  CTAG_CUDA_CHECK(dev_alloc(&d->d_st_x1, nb));
+  CTAG_CUDA_CHECK(dev_alloc(&d->d_st_y1, nb));
+  CTAG_CUDA_CHECK(dev_alloc(&d->d_roots_tmp, nb));
+  CTAG_CUDA_CHECK(dev_alloc(&d->d_span_count, (size_t)d->spans * cap));
+  CTAG_CUDA_CHECK(dev_alloc(&d->d_legal, (size_t)d->legal_cap * 6 * cap));
+  CTAG_CUDA_CHECK(dev_alloc(&d->d_counters, (size_t)4 * cap));
+  CTAG_CUDA_CHECK(dev_alloc(&d->d_prefix, (size_t)cap + 1));
+  CTAG_CUDA_CHECK(dev_alloc(&d->d_work_counter, 4));
+  CTAG_CUDA_CHECK(dev_alloc(&d->d_quad_status, (size_t)d->legal_cap * cap));
+  CTAG_CUDA_CHECK(dev_alloc(&d->d_quad_corners, (size_t)d->legal_cap * 8 * cap));
+  CTAG_CUDA_CHECK(dev_alloc(&d->d_quads, (size_t)ctag_detector::kQuadCap * 8 * cap));
+  CTAG_CUDA_CHECK(dev_alloc(&d->d_quad_comp, (size_t)ctag_detector::kQuadCap * cap));
+  CTAG_CUDA_CHECK(dev_alloc(&d->d_n_quads, (size_t)cap));
+  {
+    cudaDeviceProp prop;
+    CTAG_CUDA_CHECK(cudaGetDeviceProperties(&prop, d->device));
+    d->scratch_warps = prop.multiProcessorCount * 16;  // persistent grid: 4 CTAs x 4 warps per SM
+    CTAG_CUDA_CHECK(cudaMalloc(&d->d_quad_scratch, quad_scratch_bytes_per_warp(g) * d->scratch_warps));
+  }
   d->cap_frames = cap;
   return CTAG_OK;
 }
@@ -222,6 +271,16 @@ int ctag_detect_batch_enqueue(ctag_detector* d, const void* frames_dev, int n, i
   if (rc != CTAG_OK) return rc;
   d->launches += 1;
   CTAG_CUDA_CHECK(cudaEventRecord(d->ev[1], d->stream));
+  rc = launch_ccl(d->d_bin, d->bin_fstride, n, d->geo, d->d_labels, d->d_st_area, d->d_st_x0, d->d_st_y0, d->d_st_x1,
+                  d->d_st_y1, d->d_roots_tmp, d->d_span_count, d->d_legal, d->legal_cap, d->d_counters, d->stream,
+                  &d->launches);
+  if (rc != CTAG_OK) return rc;
+  CTAG_CUDA_CHECK(cudaEventRecord(d->ev[2], d->stream));
+  rc = launch_quad(n, d->geo, d->d_bin, d->bin_fstride, d->d_labels, d->d_legal, d->legal_cap, d->d_counters, d->d_prefix,
+                   d->d_work_counter, d->d_quad_scratch, d->scratch_warps, d->d_quad_status, d->d_quad_corners,
+                   ctag_detector::kQuadCap, d->d_quads, d->d_quad_comp, d->d_n_quads, d->stream, &d->launches);
+  if (rc != CTAG_OK) return rc;
+  CTAG_CUDA_CHECK(cudaEventRecord(d->ev[3], d->stream));
   d->in_flight = true;
   return CTAG_OK;
 }
@@ -233,10 +292,19 @@ int ctag_detect_batch_collect(ctag_detector* d, ctag_marker* out, int cap_per_fr
   CTAG_CUDA_CHECK(cudaSetDevice(d->device));
   d->in_flight = false;
   CTAG_CUDA_CHECK(cudaStreamSynchronize(d->stream));
-  cudaEventElapsedTime(&d->stage_ms[0], d->ev[0], d->ev[1]);
+  for (int sidx = 0; sidx < 3; ++sidx) cudaEventElapsedTime(&d->stage_ms[sidx], d->ev[sidx], d->ev[sidx + 1]);
+  std::vector<int> counters((size_t)4 * d->cur_n), nq(d->cur_n);
+  CTAG_CUDA_CHECK(cudaMemcpy(counters.data(), d->d_counters, sizeof(int) * 4 * d->cur_n, cudaMemcpyDeviceToHost));
+  CTAG_CUDA_CHECK(cudaMemcpy(nq.data(), d->d_n_quads, sizeof(int) * d->cur_n, cudaMemcpyDeviceToHost));
   for (int f = 0; f < d->cur_n; ++f) {
     if (n_out) n_out[f] = 0;
-    if (info) memset(&info[f], 0, sizeof(ctag_frame_info));
+    if (info) {
+      memset(&info[f], 0, sizeof(ctag_frame_info));
+      info[f].n_labels = counters[4 * f] + 1;  // + background label 0
+      info[f].n_legal = counters[4 * f + 1];
+      info[f].n_quads = nq[f];
+      info[f].flagged = (counters[4 * f + 2] != 0) || nq[f] > ctag_detector::kQuadCap;
+    }
   }
   return CTAG_OK;
 }
@@ -306,13 +374,29 @@ int ctag_debug_get_binary(ctag_detector* d, int frame, uint8_t* out, size_t out_
   return CTAG_OK;
 }
 
-int ctag_debug_get_components(ctag_detector*, int, int32_t*, int, int* n_out) {
-  if (n_out) *n_out = 0;
-  return CTAG_ERR_UNSUPPORTED;
+int ctag_debug_get_components(ctag_detector* d, int frame, int32_t* out, int cap, int* n_out) {
+  if (!d || !out || !n_out || frame < 0 || frame >= d->cur_n) return CTAG_ERR_ARG;
+  CTAG_CUDA_CHECK(cudaSetDevice(d->device));
+  int c[4];
+  CTAG_CUDA_CHECK(cudaMemcpy(c, d->d_counters + 4 * frame, sizeof(c), cudaMemcpyDeviceToHost));
+  int n = c[1] < cap ? c[1] : cap;
+  CTAG_CUDA_CHECK(cudaMemcpy(out, d->d_legal + (size_t)frame * d->legal_cap * 6, sizeof(int) * 6 * n, cudaMemcpyDeviceToHost));
+  *n_out = n;
+  return CTAG_OK;
 }
-int ctag_debug_get_quads(ctag_detector*, int, int32_t*, float*, int, int* n_out) {
-  if (n_out) *n_out = 0;
-  return CTAG_ERR_UNSUPPORTED;
+int ctag_debug_get_quads(ctag_detector* d, int frame, int32_t* comp_index, float* corners, int cap, int* n_out) {
+  if (!d || !comp_index || !corners || !n_out || frame < 0 || frame >= d->cur_n) return CTAG_ERR_ARG;
+  CTAG_CUDA_CHECK(cudaSetDevice(d->device));
+  int nq = 0;
+  CTAG_CUDA_CHECK(cudaMemcpy(&nq, d->d_n_quads + frame, sizeof(int), cudaMemcpyDeviceToHost));
+  if (nq > ctag_detector::kQuadCap) nq = ctag_detector::kQuadCap;
+  if (nq > cap) nq = cap;
+  CTAG_CUDA_CHECK(cudaMemcpy(comp_index, d->d_quad_comp + (size_t)frame * ctag_detector::kQuadCap, sizeof(int) * nq,
+                             cudaMemcpyDeviceToHost));
+  CTAG_CUDA_CHECK(cudaMemcpy(corners, d->d_quads + (size_t)frame * ctag_detector::kQuadCap * 8, sizeof(float) * 8 * nq,
+                             cudaMemcpyDeviceToHost));
+  *n_out = nq;
+  return CTAG_OK;
 }
 int ctag_debug_get_features(ctag_detector*, int, float*, float*, float*, int32_t*, int, int* n_out) {
   if (n_out) *n_out = 0;

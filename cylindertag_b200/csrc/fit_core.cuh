@@ -1,0 +1,223 @@
+// Line-fit arithmetic shared by the device kernels and by the host-side logic tests (tests/host_harness).
+//
+// Restates cv::fitLine for 2-D points (OpenCV imgproc linefit.cpp as shipped in the 4.x series; the reference calls it
+// at corner_detector.cpp:136,151,163 with DIST_L2 and at :358 with DIST_WELSCH, param 0, reps = aeps = 0.01).
+// The OpenCV source is not part of the reference tree; the arithmetic below follows SURVEY Appendix B.4 and is
+// validated against cv2.fitLine in tests/test_fit_core.py.
+//
+// float/double placement matters and mirrors the library: points are float, moment sums are double, the angle is
+// rounded to float before cos/sin, residuals and weights are float, their sums are double.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "libm_core.cuh"
+
+#if defined(__CUDACC__)
+#define CT_HD __host__ __device__ __forceinline__
+#else
+#define CT_HD inline
+#endif
+
+namespace ctag {
+namespace core {
+
+// ---- cv::RNG (multiply-with-carry), operations.hpp: RNG::next / RNG::uniform(int,int) -------------------------------
+struct Rng {
+  uint64_t state;
+};
+CT_HD uint32_t rng_next(Rng& r) {
+  r.state = (uint64_t)(uint32_t)r.state * 4164903690U + (uint32_t)(r.state >> 32);
+  return (uint32_t)r.state;
+}
+CT_HD int rng_uniform(Rng& r, int a, int b) { return a == b ? a : (int)(rng_next(r) % (uint32_t)(b - a) + a); }
+
+// cos/sin/exp of a float argument: the library ends up in the C float routines; libm_core.cuh reproduces glibc's
+// results bit for bit on host and device alike (see the note there on why that matters for DIST_WELSCH).
+CT_HD float cos_f(float t) { return libm_cosf(t); }
+CT_HD float sin_f(float t) { return libm_sinf(t); }
+CT_HD float exp_f(float a) { return libm_expf(a); }
+
+// ---- moments -> line, the tail of fitLine2D_wods ------------------------------------------------------------------
+// x,y,x2,y2,xy are the (weighted) sums, w the weight sum.  line = (vx, vy, x0, y0).
+CT_HD void line_from_moments(double x, double y, double x2, double y2, double xy, double w, float* line) {
+  x /= w;
+  y /= w;
+  x2 /= w;
+  y2 /= w;
+  xy /= w;
+  double dx2 = x2 - x * x;
+  double dy2 = y2 - y * y;
+  double dxy = xy - x * y;
+  float t = (float)atan2(2 * dxy, dx2 - dy2) / 2;
+  line[0] = cos_f(t);
+  line[1] = sin_f(t);
+  line[2] = (float)x;
+  line[3] = (float)y;
+}
+
+// Unweighted fit over integer points: all sums are exact integers (|coord| < 4096, n < 2^20), so they can be kept
+// incrementally as 64-bit integers and still reproduce the library's double accumulation bit for bit.
+struct IntMoments {
+  long long sx, sy, sxx, syy, sxy;
+  int n;
+};
+CT_HD void im_reset(IntMoments& m) { m.sx = m.sy = m.sxx = m.syy = m.sxy = 0, m.n = 0; }
+CT_HD void im_add(IntMoments& m, int x, int y) {
+  m.sx += x;
+  m.sy += y;
+  m.sxx += (long long)x * x;
+  m.syy += (long long)y * y;
+  m.sxy += (long long)x * y;
+  m.n += 1;
+}
+CT_HD void im_fit(const IntMoments& m, float* line) {
+  line_from_moments((double)m.sx, (double)m.sy, (double)m.sxx, (double)m.syy, (double)m.sxy, (double)(float)m.n, line);
+}
+
+// packed point: x | y << 16 (absolute half-res coordinates, both < 4096)
+CT_HD int pt_x(int p) { return p & 0xFFFF; }
+CT_HD int pt_y(int p) { return (p >> 16) & 0xFFFF; }
+CT_HD int pt_pack(int x, int y) { return x | (y << 16); }
+
+CT_HD float welsch_exp(float a) { return exp_f(a); }
+
+// One of the 20 random restarts of fitLine2D(DIST_WELSCH).  `pts` are the cluster points in library order.
+// Visits at most 30 iterates; for each iterate i it reports err[i] and the line that produced it.
+// Returns the number of iterates visited.  `stop_eps` > 0 makes the restart stop after the first iterate whose error is
+// below it (the library's `err < EPS` early exit can only trigger then; see welsch_combine).
+struct WelschIter {
+  double err;
+  float line[4];
+};
+
+template <typename PtFn>
+CT_HD int welsch_restart(PtFn pt, int count, Rng rng_at_restart, WelschIter* out /*[30]*/, int out_stride, double eps) {
+  Rng rng = rng_at_restart;
+  // initial subset: min(count,10) distinct indices
+  int picked[10];
+  int np = 0;
+  const int need = count < 10 ? count : 10;
+  while (np < need) {
+    int j = rng_uniform(rng, 0, count);
+    bool dup = false;
+    for (int q = 0; q < np; ++q) dup |= (picked[q] == j);
+    if (!dup) picked[np++] = j;
+  }
+  // the library accumulates over i = 0..count-1 with w[i] in {0,1}: ascending index order
+  for (int a = 1; a < np; ++a) {
+    int v = picked[a], b = a - 1;
+    while (b >= 0 && picked[b] > v) {
+      picked[b + 1] = picked[b];
+      --b;
+    }
+    picked[b + 1] = v;
+  }
+  float line[4], prev[4] = {0, 0, 0, 0};
+  {
+    double x = 0, y = 0, x2 = 0, y2 = 0, xy = 0, w = 0;
+    for (int a = 0; a < np; ++a) {
+      int p = pt(picked[a]);
+      float px = (float)pt_x(p), py = (float)pt_y(p);
+      x += px;
+      y += py;
+      x2 += px * px;
+      y2 += py * py;
+      xy += px * py;
+      w += 1.0f;
+    }
+    line_from_moments(x, y, x2, y2, xy, w, line);
+  }
+  const float c = 1 / 2.9846f;
+  int nvis = 0;
+  for (int i = 0; i < 30; ++i) {
+    if (i > 0) {
+      double t = line[0] * prev[0] + line[1] * prev[1];
+      t = t > -1. ? t : -1.;
+      t = t < 1. ? t : 1.;
+      if (fabs(acos(t)) < 0.01f) {
+        float dx = (float)fabs(line[2] - prev[2]);
+        float dy = (float)fabs(line[3] - prev[3]);
+        float d = dx > dy ? dx : dy;
+        if (d < 0.01f) break;
+      }
+    }
+    // residuals, error, raw weights
+    const float px0 = line[2], py0 = line[3], nx = line[1], ny = -line[0];
+    double err = 0, sum_w = 0;
+    for (int j = 0; j < count; ++j) {
+      int p = pt(j);
+      float x = (float)pt_x(p) - px0, y = (float)pt_y(p) - py0;
+      float r = (float)fabs(nx * x + ny * y);
+      err += r;
+      sum_w += welsch_exp(-r * r * c * c);
+    }
+    WelschIter& o = out[nvis * out_stride];
+    o.err = err;
+    o.line[0] = line[0], o.line[1] = line[1], o.line[2] = line[2], o.line[3] = line[3];
+    ++nvis;
+    if (err < eps) break;  // optional early stop (callers that need the exact library bookkeeping pass eps = 0)
+    // normalised weights + refit (second pass recomputes the residuals instead of storing them)
+    double x = 0, y = 0, x2 = 0, y2 = 0, xy = 0, wsum = 0;
+    const bool norm = fabs(sum_w) > 1.1920928955078125e-07;
+    const double inv = norm ? 1. / sum_w : 0.;
+    for (int j = 0; j < count; ++j) {
+      int p = pt(j);
+      float fx = (float)pt_x(p), fy = (float)pt_y(p);
+      float xx = fx - px0, yy = fy - py0;
+      float r = (float)fabs(nx * xx + ny * yy);
+      float w = norm ? (float)(welsch_exp(-r * r * c * c) * inv) : 1.f;
+      x += w * fx;
+      y += w * fy;
+      x2 += w * fx * fx;
+      y2 += w * fy * fy;
+      xy += w * fx * fy;
+      wsum += w;
+    }
+    prev[0] = line[0], prev[1] = line[1], prev[2] = line[2], prev[3] = line[3];
+    line_from_moments(x, y, x2, y2, xy, wsum, line);
+  }
+  return nvis;
+}
+
+// Advances the generator over one restart's subset selection (so that restart k+1 can start from the right state).
+CT_HD void welsch_skip_restart(Rng& rng, int count) {
+  int picked[10];
+  int np = 0;
+  const int need = count < 10 ? count : 10;
+  while (np < need) {
+    int j = rng_uniform(rng, 0, count);
+    bool dup = false;
+    for (int q = 0; q < np; ++q) dup |= (picked[q] == j);
+    if (!dup) picked[np++] = j;
+  }
+}
+
+// Sequential bookkeeping of fitLine2D over the 20 restarts: `if (err < min_err) { keep; if (err < EPS) stop }`.
+// iters[k*30*stride ...] / nvis[k] come from welsch_restart.  mode 0: a sub-EPS error stops everything;
+// mode 1: it only ends the current restart.
+CT_HD void welsch_combine(const WelschIter* iters, int stride_k, int stride_i, const int* nvis, int nvis_stride, int count,
+                          int mode, float* line) {
+  const double EPS = count * 1.1920928955078125e-07;
+  double min_err = 1.7976931348623157e308;
+  line[0] = line[1] = line[2] = line[3] = 0.f;
+  for (int k = 0; k < 20; ++k) {
+    int nv = nvis[k * nvis_stride];
+    bool stop_all = false;
+    for (int i = 0; i < nv; ++i) {
+      const WelschIter& it = iters[k * stride_k + i * stride_i];
+      if (it.err < min_err) {
+        min_err = it.err;
+        line[0] = it.line[0], line[1] = it.line[1], line[2] = it.line[2], line[3] = it.line[3];
+        if (it.err < EPS) {
+          stop_all = (mode == 0);
+          break;
+        }
+      }
+    }
+    if (stop_all) break;
+  }
+}
+
+}  // namespace core
+}  // namespace ctag

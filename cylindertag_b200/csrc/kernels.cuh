@@ -9,4 +9,17 @@ int launch_front(const void* frames_dev, int n, const FrameGeom& geo, int channe
                  uint8_t* gray_out, size_t gray_fstride, uint8_t* bin_out, size_t bin_fstride, cudaStream_t stream);
 int front_smem_bytes(int channels);
 
+// K2/K3 (ccl.cu): block-based union-find labelling, stats, ordered legal-component list.
+// legal[frame][k] = {root, area, x0, y0, x1, y1}; counters[frame] = {n_components, n_legal, overflow, 0}.
+int launch_ccl(const uint8_t* bin, size_t bin_fstride, int n, const FrameGeom& g, int* labels, int* st_area, int* st_x0,
+               int* st_y0, int* st_x1, int* st_y1, int* roots_tmp, int* span_count, int* legal, int legal_cap,
+               int* counters, cudaStream_t stream, int* launches);
+
+// K4 (quad.cu): one warp per legal component -> quad or nothing; ordered compaction of the quads.
+size_t quad_scratch_bytes_per_warp(const FrameGeom& g);
+int launch_quad(int n, const FrameGeom& g, const uint8_t* bin, size_t bin_fstride, const int* labels, const int* legal,
+                int legal_cap, const int* counters, int* prefix, int* work_counter, uint8_t* scratch, int scratch_warps,
+                int* quad_status, float* quad_corners, int quad_cap, float* quads, int* quad_comp, int* n_quads,
+                cudaStream_t stream, int* launches);
+
 }  // namespace ctag

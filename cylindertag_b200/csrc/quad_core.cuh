@@ -1,0 +1,471 @@
+// Per-component quad extraction (reference row a5: corner_detector::edgeExtraction, corner_detector.cpp:171-405,
+// with get_orientedEdgePoints :407-418, expand_line :125-169, get_permutation/quadJudgment :420-463).
+//
+// The code is written once for a cooperating group of lanes: on the device one warp (32 lanes) executes it for one
+// component; the host build (tests/host_harness) runs it with a single lane so that the sequential logic can be
+// checked against the oracle without a GPU.  Scalar control flow is executed redundantly by all lanes (warp-uniform),
+// data-parallel sections stride over lanes and meet in warp reductions, and the two inherently serial chains
+// (boundary trace, span expansion) run on lane 0.
+//
+// Redesign notes versus the reference (same results, different work):
+//  * no per-component pixel lists / sorts: the bbox comes from the CCL stats, membership from (binary, block label);
+//  * the ray-cast "visited" image is a bit map; the four silhouettes are found in one coalesced sweep;
+//  * expand_line keeps exact integer moments, so the O(n) refit after every appended point becomes O(1) and is still
+//    bit-identical to refitting from scratch (all sums are exact in double);
+//  * the 20 random restarts of each DIST_WELSCH fit are independent given the generator state at their start, so the
+//    4 x 20 restarts of a component run on different lanes and are merged in library order afterwards.
+#pragma once
+#include "fit_core.cuh"
+
+namespace ctag {
+namespace core {
+
+struct Lanes {
+  int id, n;
+};
+
+CT_HD float kRdpLine() { return 1.8f; }  // threshold_line,   corner_detector.h:90
+CT_HD float kExpand() { return 1.2f; }   // threshold_expand, corner_detector.h:90
+CT_HD float kRac() { return 0.3f; }      // threshold_RAC,    corner_detector.h:110
+
+// ---- lane collectives --------------------------------------------------------------------------------------------
+CT_HD void w_sync() {
+#ifdef __CUDA_ARCH__
+  __syncwarp();
+#endif
+}
+CT_HD int w_min_i(int v) {
+#ifdef __CUDA_ARCH__
+  return __reduce_min_sync(0xffffffffu, v);
+#else
+  return v;
+#endif
+}
+CT_HD int w_max_i(int v) {
+#ifdef __CUDA_ARCH__
+  return __reduce_max_sync(0xffffffffu, v);
+#else
+  return v;
+#endif
+}
+CT_HD unsigned w_min_u(unsigned v) {
+#ifdef __CUDA_ARCH__
+  return __reduce_min_sync(0xffffffffu, v);
+#else
+  return v;
+#endif
+}
+CT_HD unsigned w_max_u(unsigned v) {
+#ifdef __CUDA_ARCH__
+  return __reduce_max_sync(0xffffffffu, v);
+#else
+  return v;
+#endif
+}
+CT_HD int w_sum_i(int v) {
+#ifdef __CUDA_ARCH__
+  return __reduce_add_sync(0xffffffffu, v);
+#else
+  return v;
+#endif
+}
+CT_HD int w_bcast_i(int v, int src) {
+#ifdef __CUDA_ARCH__
+  return __shfl_sync(0xffffffffu, v, src);
+#else
+  (void)src;
+  return v;
+#endif
+}
+CT_HD void bit_or(uint32_t* p, uint32_t v) {
+#ifdef __CUDA_ARCH__
+  atomicOr(p, v);
+#else
+  *p |= v;
+#endif
+}
+CT_HD uint32_t f2u(float f) { return as_u32(f); }
+
+// ---- inputs / scratch / result ------------------------------------------------------------------------------------
+struct CompView {
+  const uint8_t* bin;  // half-res binary image of the frame ({0,255})
+  int bpitch;
+  const int* labels;  // one label per 2x2 block: index of the component's root block, -1 = background
+  int bw;             // blocks per row
+  int cols, rows;     // half-res image size (what the reference passes as img.cols/img.rows)
+  int root, area, x0, y0, x1, y1;
+};
+
+struct QuadScratch {
+  uint32_t* vis;     // boundary bit map of the bbox, ((w+31)/32)*h words
+  int16_t* col_top;  // [cols]
+  int16_t* col_bot;  // [cols]
+  int* pts_a;        // [pmax + 8] packed points
+  int* pts_b;        // [pmax + 8]
+  int* stack;        // [pmax + 8] trace frames: x | y << 12 | next_dir << 24
+  int* cl;           // [pmax + 8] the four clusters back to back
+  uint64_t* rng;     // [80] generator state at the start of each (cluster, restart)
+  WelschIter* iters; // [80 * 30]
+  int* nvis;         // [80]
+  float* lines;      // [16]
+};
+
+enum { Q_OK = 0, Q_FEW_EDGES = 1, Q_NO_QUAD = 2 };
+
+struct QuadResult {
+  int status;
+  int n_trace;  // traced boundary points
+  int n_edges;  // accepted edges (cnt_boundary)
+  float c[8];   // 4 corners (x,y), angular order, half-res coordinates
+};
+
+CT_HD bool in_comp(const CompView& cv, int x, int y) {
+  int ax = cv.x0 + x, ay = cv.y0 + y;
+  return cv.bin[(size_t)ay * cv.bpitch + ax] != 0 && cv.labels[(ay >> 1) * cv.bw + (ax >> 1)] == cv.root;
+}
+
+// squared norm of p[i] + p[(i+2)%n] - 2 p[(i+1)%n]; the reference compares its float sqrt with 1.05:
+// cost > 1.05 <=> d2 >= 2, cost < 1.05 <=> d2 <= 1 (integer geometry).
+CT_HD int second_diff2(const int* P, int n, int i) {
+  int a = P[i], b = P[(i + 2) % n], c = P[(i + 1) % n];
+  int dx = pt_x(a) + pt_x(b) - 2 * pt_x(c);
+  int dy = pt_y(a) + pt_y(b) - 2 * pt_y(c);
+  return dx * dx + dy * dy;
+}
+
+// cv::solve / cv::determinant for 2x2 CV_32F
+CT_HD bool solve2x2(float a00, float a01, float a10, float a11, float b0, float b1, float* x0, float* x1) {
+  double det = (double)a00 * a11 - (double)a01 * a10;
+  if (det == 0) return false;
+  double d = 1. / det;
+  *x0 = (float)(((double)b0 * a11 - (double)b1 * a01) * d);
+  *x1 = (float)(((double)b1 * a00 - (double)b0 * a10) * d);
+  return true;
+}
+
+struct PtArray {
+  const int* p;
+  CT_HD int operator()(int j) const { return p[j]; }
+};
+
+CT_HD void quad_extract(const CompView& cv, const QuadScratch& sc, Lanes ln, QuadResult* res) {
+  const int w = cv.x1 - cv.x0 + 1, h = cv.y1 - cv.y0 + 1, wpr = (w + 31) >> 5;
+  res->status = Q_FEW_EDGES;
+  res->n_trace = 0;
+  res->n_edges = 0;
+
+  // ---- 1. four silhouettes -> boundary bit map (corner_detector.cpp:197-232) --------------------------------------
+  // The ray-cast's `if (visited) break` can never fire before the first mask pixel (visited is a subset of mask), so
+  // the result is the union of the top/bottom pixel of every column and the left/right pixel of every row.
+  for (int i = ln.id; i < h * wpr; i += ln.n) sc.vis[i] = 0;
+  for (int x = ln.id; x < w; x += ln.n) sc.col_top[x] = -1, sc.col_bot[x] = -1;
+  w_sync();
+  for (int y = 0; y < h; ++y) {
+    int lmin = 0x7fffffff, lmax = -1;
+    for (int x = ln.id; x < w; x += ln.n) {
+      if (in_comp(cv, x, y)) {
+        if (sc.col_top[x] < 0) sc.col_top[x] = (int16_t)y;
+        sc.col_bot[x] = (int16_t)y;
+        lmin = x < lmin ? x : lmin;
+        lmax = x > lmax ? x : lmax;
+      }
+    }
+    lmin = w_min_i(lmin);
+    lmax = w_max_i(lmax);
+    if (ln.id == 0 && lmax >= 0) {
+      sc.vis[y * wpr + (lmin >> 5)] |= 1u << (lmin & 31);
+      sc.vis[y * wpr + (lmax >> 5)] |= 1u << (lmax & 31);
+    }
+  }
+  w_sync();
+  for (int x = ln.id; x < w; x += ln.n) {
+    int t = sc.col_top[x], b = sc.col_bot[x];
+    if (t >= 0) {
+      bit_or(&sc.vis[t * wpr + (x >> 5)], 1u << (x & 31));
+      bit_or(&sc.vis[b * wpr + (x >> 5)], 1u << (x & 31));
+    }
+  }
+  w_sync();
+
+  // ---- 2. start pixel + oriented trace (corner_detector.cpp:235-247, 407-418) -------------------------------------
+  // get_orientedEdgePoints follows 8-neighbours in the order N,NE,E,SE,S,SW,W,NW, recursing on every hit; after the
+  // recursive call returns, the caller keeps scanning the remaining directions from the NEW position.  Frames of that
+  // recursion live on an explicit stack.
+  int* P = sc.pts_a;
+  int* Q = sc.pts_b;
+  int n = 0;
+  if (ln.id == 0) {
+    int fx = 0, fy = sc.col_top[0], fj = 0, sp = 0;
+    P[n++] = pt_pack(fx + cv.x0, fy + cv.y0);
+    sc.vis[fy * wpr] &= ~1u;
+    while (true) {
+      if (fj == 8) {
+        if (sp == 0) break;
+        int fr = sc.stack[--sp];
+        fx = fr & 0xFFF, fy = (fr >> 12) & 0xFFF, fj = fr >> 24;
+        continue;
+      }
+      int nx = fx + (int)((0x1A9u >> (2 * fj)) & 3u) - 1;
+      int ny = fy + (int)((0x1A90u >> (2 * fj)) & 3u) - 1;
+      ++fj;
+      if (nx >= 0 && nx < w && ny >= 0 && ny < h) {
+        uint32_t* wd = &sc.vis[ny * wpr + (nx >> 5)];
+        uint32_t m = 1u << (nx & 31);
+        if (*wd & m) {
+          *wd &= ~m;
+          P[n++] = pt_pack(nx + cv.x0, ny + cv.y0);
+          sc.stack[sp++] = nx | (ny << 12) | (fj << 24);  // caller resumes at direction fj from the new position
+          fx = nx, fy = ny, fj = 0;
+        }
+      }
+    }
+  }
+  w_sync();
+  n = w_bcast_i(n, 0);
+  res->n_trace = n;
+
+  // ---- 3. centre of the traced boundary, rotate the list to the point closest to it (:250-275) --------------------
+  float cx, cy;
+  {
+    int sx = 0, sy = 0;
+    for (int i = ln.id; i < n; i += ln.n) sx += pt_x(P[i]), sy += pt_y(P[i]);
+    sx = w_sum_i(sx);
+    sy = w_sum_i(sy);
+    cx = (float)(1.0 * sx / n);
+    cy = (float)(1.0 * sy / n);
+    float best = 3.0e38f;
+    int bidx = 0x7fffffff;
+    for (int i = ln.id; i < n; i += ln.n) {
+      float dx = (float)pt_x(P[i]) - cx, dy = (float)pt_y(P[i]) - cy;
+      float d = sqrtf(dx * dx + dy * dy);
+      if (d < best) best = d, bidx = i;  // strict: first minimum (stable ascending sort)
+    }
+    unsigned bm = w_min_u(f2u(best));  // distances are >= 0: unsigned order == float order
+    int b0 = w_min_i(f2u(best) == bm ? bidx : 0x7fffffff);
+    if (b0 > 0) {
+      for (int i = ln.id; i < n; i += ln.n) {
+        int s = i + b0;
+        Q[i] = P[s >= n ? s - n : s];
+      }
+      w_sync();
+      int* t = P;
+      P = Q;
+      Q = t;
+    }
+  }
+
+  // ---- 4. extended Ramer-Douglas-Peucker: up to four edges (:278-349) ----------------------------------------------
+  int cnt = 0, init = 0;
+  bool failed = false;
+  int cl_off[5] = {0, 0, 0, 0, 0};
+  while (n > 0 && !failed && cnt < 4) {
+    if (n > 2) {
+      while (second_diff2(P, n, init) >= 2 && init < n - 3) ++init;
+    } else {
+      failed = true;
+      break;
+    }
+    int end = init + n / 2;
+    if (end > n - 1) end = n - 1;
+    while (true) {
+      if (end <= init + 1) {
+        failed = true;
+        break;
+      }
+      const int xi = pt_x(P[init]), yi = pt_y(P[init]), xe = pt_x(P[end]), ye = pt_y(P[end]);
+      const float nl0 = (xi == xe) ? 100.f : (float)(1.0 * (ye - yi) / (xe - xi));  // C-13: vertical chord = slope 100
+      const float nl1 = -1.f;
+      const float d_line = -(nl0 * (float)xi + nl1 * (float)yi);
+      const float den = sqrtf(nl0 * nl0 + 1.f);
+      float best = 0.f;
+      int bidx = -1;
+      for (int it = init + 1 + ln.id; it < end; it += ln.n) {
+        float d = fabsf(nl0 * (float)pt_x(P[it]) + nl1 * (float)pt_y(P[it]) + d_line) / den;
+        if (d >= best) best = d, bidx = it;  // >=: last index among ties of the maximum (stable descending sort)
+      }
+      unsigned bm = w_max_u(f2u(best));
+      int last = w_max_i(f2u(best) == bm ? bidx : -1);
+      float dmax;
+      {
+        // recover the float from its bits without type punning through memory on the device
+#ifdef __CUDA_ARCH__
+        dmax = __uint_as_float(bm);
+#else
+        memcpy(&dmax, &bm, 4);
+#endif
+      }
+      const int m = end - init - 1;
+      if (dmax > kRdpLine() && m > 1) {
+        end = last - (init + 1);  // C-5: the index relative to init+1 is used as an absolute index
+        continue;
+      }
+      // ---- expand_line (:125-169) on lane 0, exact incremental moments -----------------------------------------
+      int nl = 0, nr = 0;
+      if (ln.id == 0) {
+        IntMoments mom;
+        im_reset(mom);
+        for (int i = init; i <= end; ++i) im_add(mom, pt_x(P[i]), pt_y(P[i]));
+        float line[4];
+        im_fit(mom, line);
+        bool fl = false, fr = false;
+        int left = init - 1, right = end + 1;
+        while ((!fl || !fr) && left != right) {
+          if (!fl) {
+            if (left == -1) left = n - 1;
+            int px = pt_x(P[left]), py = pt_y(P[left]);
+            float d = fabsf((float)px * line[1] - (float)py * line[0] + line[0] * line[3] - line[1] * line[2]);
+            if (d > kExpand()) {
+              fl = true;
+              continue;
+            }
+            im_add(mom, px, py);
+            ++nl;
+            --left;
+            im_fit(mom, line);
+            if (mom.n == n) break;
+          }
+          if (!fr) {
+            if (right == n) right = 0;
+            int px = pt_x(P[right]), py = pt_y(P[right]);
+            float d = fabsf((float)px * line[1] - (float)py * line[0] + line[0] * line[3] - line[1] * line[2]);
+            if (d > kExpand()) {
+              fr = true;
+              continue;
+            }
+            im_add(mom, px, py);
+            ++nr;
+            ++right;
+            im_fit(mom, line);
+            if (mom.n == n) break;
+          }
+        }
+      }
+      nl = w_bcast_i(nl, 0);
+      nr = w_bcast_i(nr, 0);
+      // the span is the cyclic interval [a, a+len) of indices; the reference sorts it descending
+      const int len = (end - init + 1) + nl + nr;
+      int a = init - nl;
+      if (a < 0) a += n;
+      const bool wrap = a + len > n;
+      const int nhi = n - a;              // wrap: indices a..n-1 come first in descending order
+      const int e = a + len - n - 1;      // wrap: then e..0
+      const int s0 = wrap ? n - 1 : a + len - 1;
+      int* cl = sc.cl + cl_off[cnt];
+      for (int q = ln.id; q < len; q += ln.n) {
+        int idx = !wrap ? (a + len - 1 - q) : (q < nhi ? n - 1 - q : e - (q - nhi));
+        cl[q] = P[idx];
+      }
+      cl_off[cnt + 1] = cl_off[cnt] + len;
+      // endpoint keeping judgment (:337-339): the largest index stays in the list if the boundary is straight there
+      const int keep = second_diff2(P, n, s0) <= 1 ? 1 : 0;
+      for (int i = ln.id; i < n; i += ln.n) {
+        if (!wrap) {
+          if (i < a) Q[i] = P[i];
+          else if (i == s0) { if (keep) Q[a] = P[i]; }
+          else if (i > s0) Q[i - len + keep] = P[i];
+        } else {
+          if (i > e && i < a) Q[i - (e + 1)] = P[i];
+          else if (i == s0 && keep) Q[a - e - 1] = P[i];
+        }
+      }
+      w_sync();
+      {
+        int* t = P;
+        P = Q;
+        Q = t;
+      }
+      n = n - len + keep;
+      const int back = wrap ? 0 : a;  // smallest erased index
+      ++cnt;
+      init = back >= n ? 0 : back;
+      break;
+    }
+  }
+  res->n_edges = cnt;
+  if (cnt < 4) return;  // some cluster has < 2 points (:351-361)
+
+  // ---- 5. four DIST_WELSCH fits (:358); 4 x 20 independent restarts spread over the lanes -------------------------
+  for (int c = ln.id; c < 4; c += ln.n) {
+    Rng rng{0xFFFFFFFFFFFFFFFFull};
+    const int count = cl_off[c + 1] - cl_off[c];
+    for (int k = 0; k < 20; ++k) {
+      sc.rng[c * 20 + k] = rng.state;
+      welsch_skip_restart(rng, count);
+    }
+  }
+  w_sync();
+  for (int t = ln.id; t < 80; t += ln.n) {
+    const int c = t / 20;
+    PtArray pa{sc.cl + cl_off[c]};
+    sc.nvis[t] = welsch_restart(pa, cl_off[c + 1] - cl_off[c], Rng{sc.rng[t]}, sc.iters + t * 30, 1, 0.0);
+  }
+  w_sync();
+  for (int c = ln.id; c < 4; c += ln.n)
+    welsch_combine(sc.iters + c * 600, 30, 1, sc.nvis + c * 20, 1, cl_off[c + 1] - cl_off[c], 1, sc.lines + 4 * c);
+  w_sync();
+
+  // ---- 6. six intersections, angular sort, best 4-subset (:362-403, 420-463) --------------------------------------
+  float ix[6], iy[6], ia[6];
+  int nc = 0;
+  for (int j = 0; j < 3; ++j)
+    for (int k = j + 1; k < 4; ++k) {
+      const float* lj = sc.lines + 4 * j;
+      const float* lk = sc.lines + 4 * k;
+      float b0 = lj[1] * lj[2] - lj[0] * lj[3];
+      float b1 = lk[1] * lk[2] - lk[0] * lk[3];
+      float sx, sy;
+      if (!solve2x2(lj[1], -lj[0], lk[1], -lk[0], b0, b1, &sx, &sy)) continue;
+      float dx = sx - cx, dy = sy - cy;
+      float dis = sqrtf(dx * dx + dy * dy);
+      float ang = (float)atan2_deg(dy, dx);
+      if (dis < (float)cv.cols && dis < (float)cv.rows) {
+        // insertion keeps the list sorted by angle, stable for ties (C-11)
+        int pos = nc;
+        while (pos > 0 && ang < ia[pos - 1]) {
+          ix[pos] = ix[pos - 1], iy[pos] = iy[pos - 1], ia[pos] = ia[pos - 1];
+          --pos;
+        }
+        ix[pos] = sx, iy[pos] = sy, ia[pos] = ang;
+        ++nc;
+      }
+    }
+  float rac_min = kRac();
+  int best[4] = {-1, -1, -1, -1};
+  for (int a = 0; a < nc; ++a)
+    for (int b = a + 1; b < nc; ++b)
+      for (int c = b + 1; c < nc; ++c)
+        for (int d = c + 1; d < nc; ++d) {
+          const float X[4] = {ix[a], ix[b], ix[c], ix[d]}, Y[4] = {iy[a], iy[b], iy[c], iy[d]};
+          auto tri = [&](int i0, int i1, int i2) {
+            return X[i0] * Y[i1] + X[i1] * Y[i2] + X[i2] * Y[i0] - X[i0] * Y[i2] - X[i1] * Y[i0] - X[i2] * Y[i1];
+          };
+          if (fabsf(tri(0, 1, 2)) < 1 || fabsf(tri(1, 2, 3)) < 1 || fabsf(tri(2, 3, 0)) < 1 || fabsf(tri(0, 1, 3)) < 1)
+            continue;
+          float qa = 0;
+          for (int i = 0; i < 3; ++i) qa += X[i] * Y[i + 1] - Y[i] * X[i + 1];
+          qa += X[3] * Y[0] - Y[3] * X[0];
+          qa /= 2;
+          float rac = fabsf(fabsf(qa) - (float)cv.area) / (float)cv.area;
+          if (rac < rac_min) {
+            rac_min = rac;
+            best[0] = a, best[1] = b, best[2] = c, best[3] = d;
+          }
+        }
+  if (best[0] < 0) {
+    res->status = Q_NO_QUAD;
+    return;
+  }
+  for (int k = 0; k < 4; ++k) {
+    float x = ix[best[k]], y = iy[best[k]];
+    if (x < 0 || y < 0 || x > (float)cv.cols || y > (float)cv.rows) {
+      res->status = Q_NO_QUAD;
+      return;
+    }
+    res->c[2 * k] = x;
+    res->c[2 * k + 1] = y;
+  }
+  res->status = Q_OK;
+}
+
+}  // namespace core
+}  // namespace ctag
