@@ -69,6 +69,15 @@ struct ctag_detector {
   uint8_t* d_quad_scratch = nullptr;
   int scratch_warps = 0;
   static constexpr int kQuadCap = CTAG_MAX_FRAME_QUADS;
+  // features / markers (a6-a10)
+  void *d_geom = nullptr, *d_feats = nullptr;
+  int *d_fstate = nullptr, *d_packed_count = nullptr, *d_summary = nullptr;
+  ctag_marker *d_markers = nullptr, *d_packed = nullptr;
+  int* h_summary = nullptr;         // pinned
+  ctag_marker* h_packed = nullptr;  // pinned
+  static constexpr int kFeatCap = CTAG_MAX_FRAME_FEATURES;
+  static constexpr int kMarkerCap = CTAG_MAX_FRAME_FEATURES / 2;
+  int cur_subpix = 0;
 
   // state of the batch in flight / last batch
   int cur_n = 0, cur_channels = 0;
@@ -105,8 +114,16 @@ static void free_workspace(ctag_detector* d) {
   // d_stage is managed separately (ensure_stage): it may hold the batch that is about to be processed
   void* ptrs[] = {d->d_gray, d->d_bin, d->d_labels, d->d_st_area, d->d_st_x0, d->d_st_y0, d->d_st_x1, d->d_st_y1,
                   d->d_roots_tmp, d->d_span_count, d->d_legal, d->d_counters, d->d_prefix, d->d_work_counter,
-                  d->d_quad_status, d->d_quad_comp, d->d_n_quads, d->d_quad_corners, d->d_quads, d->d_quad_scratch};
+                  d->d_quad_status, d->d_quad_comp, d->d_n_quads, d->d_quad_corners, d->d_quads, d->d_quad_scratch,
+                  d->d_geom, d->d_feats, d->d_fstate, d->d_packed_count, d->d_summary, d->d_markers, d->d_packed};
   for (void* p : ptrs) cudaFree(p);
+  cudaFreeHost(d->h_summary);
+  cudaFreeHost(d->h_packed);
+  d->h_summary = nullptr;
+  d->h_packed = nullptr;
+  d->d_geom = d->d_feats = nullptr;
+  d->d_fstate = d->d_packed_count = d->d_summary = nullptr;
+  d->d_markers = d->d_packed = nullptr;
   d->d_gray = d->d_bin = d->d_quad_scratch = nullptr;
   d->d_labels = d->d_st_area = d->d_st_x0 = d->d_st_y0 = d->d_st_x1 = d->d_st_y1 = d->d_roots_tmp = d->d_span_count =
       d->d_legal = d->d_counters = d->d_prefix = d->d_work_counter = d->d_quad_status = d->d_quad_comp = d->d_n_quads =
@@ -153,6 +170,15 @@ static int ensure_workspace(ctag_detector* d, int n, int w, int h) {
   CTAG_CUDA_CHECK(dev_alloc(&d->d_quads, (size_t)ctag_detector::kQuadCap * 8 * cap));
   CTAG_CUDA_CHECK(dev_alloc(&d->d_quad_comp, (size_t)ctag_detector::kQuadCap * cap));
   CTAG_CUDA_CHECK(dev_alloc(&d->d_n_quads, (size_t)cap));
+  CTAG_CUDA_CHECK(cudaMalloc(&d->d_geom, sizeof_quad_geom() * ctag_detector::kQuadCap * cap));
+  CTAG_CUDA_CHECK(cudaMalloc(&d->d_feats, sizeof_feature_rec() * ctag_detector::kFeatCap * cap));
+  CTAG_CUDA_CHECK(dev_alloc(&d->d_fstate, (size_t)4 * cap));
+  CTAG_CUDA_CHECK(dev_alloc(&d->d_packed_count, 4));
+  CTAG_CUDA_CHECK(dev_alloc(&d->d_summary, (size_t)12 * cap));
+  CTAG_CUDA_CHECK(dev_alloc(&d->d_markers, (size_t)ctag_detector::kMarkerCap * cap));
+  CTAG_CUDA_CHECK(dev_alloc(&d->d_packed, (size_t)ctag_detector::kMarkerCap * cap));
+  CTAG_CUDA_CHECK(cudaMallocHost(&d->h_summary, sizeof(int) * 12 * cap));
+  CTAG_CUDA_CHECK(cudaMallocHost(&d->h_packed, sizeof(ctag_marker) * ctag_detector::kMarkerCap * cap));
   {
     cudaDeviceProp prop;
     CTAG_CUDA_CHECK(cudaGetDeviceProperties(&prop, d->device));
@@ -247,8 +273,8 @@ int ctag_detect_batch_enqueue(ctag_detector* d, const void* frames_dev, int n, i
   if (channels != 1 && channels != 3) return CTAG_ERR_ARG;
   if (adaptive_thresh != kWin) return CTAG_ERR_UNSUPPORTED;
   if (d->in_flight) return CTAG_ERR_ARG;
-  (void)corner_subpix;
-  (void)subpix_dist;
+  if (corner_subpix && (subpix_dist < 0 || subpix_dist > 64)) return CTAG_ERR_ARG;
+  if (decode_smem_bytes(d->rows, d->cols) > 200 * 1024) return CTAG_ERR_UNSUPPORTED;
   CTAG_CUDA_CHECK(cudaSetDevice(d->device));
   if (frame_stride == 0) frame_stride = pitch * (size_t)h;
   int rc = ensure_workspace(d, n, w, h);
@@ -281,6 +307,18 @@ int ctag_detect_batch_enqueue(ctag_detector* d, const void* frames_dev, int n, i
                    ctag_detector::kQuadCap, d->d_quads, d->d_quad_comp, d->d_n_quads, d->stream, &d->launches);
   if (rc != CTAG_OK) return rc;
   CTAG_CUDA_CHECK(cudaEventRecord(d->ev[3], d->stream));
+  rc = launch_features(n, d->geo, d->d_quads, d->d_n_quads, ctag_detector::kQuadCap, d->d_geom, d->d_feats,
+                       ctag_detector::kFeatCap, d->feature_size, d->d_fstate, d->cur_gray, d->cur_gray_pitch,
+                       d->cur_gray_fstride, corner_subpix, subpix_dist, d->stream, &d->launches);
+  if (rc != CTAG_OK) return rc;
+  CTAG_CUDA_CHECK(cudaEventRecord(d->ev[4], d->stream));
+  rc = launch_decode(n, d->d_feats, ctag_detector::kFeatCap, d->d_fstate, d->d_state, d->rows, d->cols, d->feature_size,
+                     d->d_markers, ctag_detector::kMarkerCap, d->d_counters, d->d_n_quads, ctag_detector::kQuadCap,
+                     d->d_packed, d->d_packed_count, d->d_summary, d->stream, &d->launches);
+  if (rc != CTAG_OK) return rc;
+  CTAG_CUDA_CHECK(cudaEventRecord(d->ev[5], d->stream));
+  CTAG_CUDA_CHECK(cudaMemcpyAsync(d->h_summary, d->d_summary, sizeof(int) * 12 * n, cudaMemcpyDeviceToHost, d->stream));
+  d->cur_subpix = corner_subpix;
   d->in_flight = true;
   return CTAG_OK;
 }
@@ -292,18 +330,31 @@ int ctag_detect_batch_collect(ctag_detector* d, ctag_marker* out, int cap_per_fr
   CTAG_CUDA_CHECK(cudaSetDevice(d->device));
   d->in_flight = false;
   CTAG_CUDA_CHECK(cudaStreamSynchronize(d->stream));
-  for (int sidx = 0; sidx < 3; ++sidx) cudaEventElapsedTime(&d->stage_ms[sidx], d->ev[sidx], d->ev[sidx + 1]);
-  std::vector<int> counters((size_t)4 * d->cur_n), nq(d->cur_n);
-  CTAG_CUDA_CHECK(cudaMemcpy(counters.data(), d->d_counters, sizeof(int) * 4 * d->cur_n, cudaMemcpyDeviceToHost));
-  CTAG_CUDA_CHECK(cudaMemcpy(nq.data(), d->d_n_quads, sizeof(int) * d->cur_n, cudaMemcpyDeviceToHost));
+  for (int sidx = 0; sidx < CTAG_STAGE_COUNT; ++sidx) cudaEventElapsedTime(&d->stage_ms[sidx], d->ev[sidx], d->ev[sidx + 1]);
+  int total = 0;
+  for (int f = 0; f < d->cur_n; ++f) total += d->h_summary[12 * f + 10];
+  if (total > 0) {
+    CTAG_CUDA_CHECK(cudaMemcpyAsync(d->h_packed, d->d_packed, sizeof(ctag_marker) * total, cudaMemcpyDeviceToHost, d->stream));
+    CTAG_CUDA_CHECK(cudaStreamSynchronize(d->stream));
+  }
   for (int f = 0; f < d->cur_n; ++f) {
-    if (n_out) n_out[f] = 0;
+    const int* sm = d->h_summary + 12 * f;
+    if (n_out) n_out[f] = sm[6];
     if (info) {
       memset(&info[f], 0, sizeof(ctag_frame_info));
-      info[f].n_labels = counters[4 * f] + 1;  // + background label 0
-      info[f].n_legal = counters[4 * f + 1];
-      info[f].n_quads = nq[f];
-      info[f].flagged = (counters[4 * f + 2] != 0) || nq[f] > ctag_detector::kQuadCap;
+      info[f].status = sm[0];
+      info[f].n_labels = sm[1];
+      info[f].n_legal = sm[2];
+      info[f].n_quads = sm[3];
+      info[f].n_features = sm[4];
+      info[f].n_groups = sm[5];
+      info[f].n_markers = sm[6];
+      info[f].flagged = sm[7];
+      info[f].stale_ids = sm[8];
+    }
+    if (out && cap_per_frame > 0) {
+      int ncopy = sm[10] < cap_per_frame ? sm[10] : cap_per_frame;
+      if (ncopy > 0) memcpy(out + (size_t)f * cap_per_frame, d->h_packed + sm[9], sizeof(ctag_marker) * ncopy);
     }
   }
   return CTAG_OK;
@@ -398,9 +449,32 @@ int ctag_debug_get_quads(ctag_detector* d, int frame, int32_t* comp_index, float
   *n_out = nq;
   return CTAG_OK;
 }
-int ctag_debug_get_features(ctag_detector*, int, float*, float*, float*, int32_t*, int, int* n_out) {
-  if (n_out) *n_out = 0;
-  return CTAG_ERR_UNSUPPORTED;
+int ctag_debug_get_features(ctag_detector* d, int frame, float* corners, float* center, float* angle, int32_t* quad_pair,
+                            int cap, int* n_out) {
+  if (!d || !n_out || frame < 0 || frame >= d->cur_n) return CTAG_ERR_ARG;
+  CTAG_CUDA_CHECK(cudaSetDevice(d->device));
+  int fs[4];
+  CTAG_CUDA_CHECK(cudaMemcpy(fs, d->d_fstate + 4 * frame, sizeof(fs), cudaMemcpyDeviceToHost));
+  int nf = fs[1] < ctag_detector::kFeatCap ? fs[1] : ctag_detector::kFeatCap;
+  if (nf > cap) nf = cap;
+  struct Rec {
+    float c[16];
+    float cx, cy, angle;
+    int qi, qj;
+  };
+  if (sizeof(Rec) != sizeof_feature_rec()) return CTAG_ERR_UNSUPPORTED;
+  std::vector<Rec> recs(nf);
+  if (nf)
+    CTAG_CUDA_CHECK(cudaMemcpy(recs.data(), static_cast<const uint8_t*>(d->d_feats) + sizeof(Rec) * ctag_detector::kFeatCap * frame,
+                               sizeof(Rec) * nf, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < nf; ++i) {
+    if (corners) memcpy(corners + 16 * i, recs[i].c, sizeof(float) * 16);
+    if (center) center[2 * i] = recs[i].cx, center[2 * i + 1] = recs[i].cy;
+    if (angle) angle[i] = recs[i].angle;
+    if (quad_pair) quad_pair[2 * i] = recs[i].qi, quad_pair[2 * i + 1] = recs[i].qj;
+  }
+  *n_out = nf;
+  return CTAG_OK;
 }
 
 const char* ctag_strerror(int code) {

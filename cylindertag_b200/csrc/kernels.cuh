@@ -22,4 +22,19 @@ int launch_quad(int n, const FrameGeom& g, const uint8_t* bin, size_t bin_fstrid
                 int* quad_status, float* quad_corners, int quad_cap, float* quads, int* quad_comp, int* n_quads,
                 cudaStream_t stream, int* launches);
 
+// K5/K6 (feature.cu): quad pairing, coordinate lift, edge refinement.  fstate[frame] = {status, n_features,
+// n_features going on, overflow}.
+size_t sizeof_quad_geom();
+size_t sizeof_feature_rec();
+int launch_features(int n, const FrameGeom& g, const float* quads, const int* n_quads, int quad_cap, void* geom, void* feats,
+                    int feat_cap, int feature_size, int* fstate, const uint8_t* gray, size_t gray_pitch, size_t gray_fstride,
+                    int corner_subpix, int subpix_dist, cudaStream_t stream, int* launches);
+
+// K7 (feature.cu): grouping, cross-ratio IDs, dictionary decode; packs the markers of the batch and writes
+// summary[frame][12] = {status, n_labels, n_legal, n_quads, n_features, n_groups, n_markers, flagged, stale, offset, stored}.
+size_t decode_smem_bytes(int srows, int scols);
+int launch_decode(int n, const void* feats, int feat_cap, const int* fstate, const int* state, int srows, int scols, int fsz,
+                  ctag_marker* markers, int marker_cap, const int* counters, const int* n_quads, int quad_cap,
+                  ctag_marker* packed, int* packed_count, int* summary, cudaStream_t stream, int* launches);
+
 }  // namespace ctag

@@ -6,6 +6,8 @@
 
 #include "../../cylindertag_b200/csrc/fit_core.cuh"
 #include "../../cylindertag_b200/csrc/quad_core.cuh"
+#include "../../cylindertag_b200/csrc/feature_core.cuh"
+#include "../../cylindertag_b200/csrc/decode_core.cuh"
 
 using namespace ctag::core;
 
@@ -60,4 +62,77 @@ void hh_quad_extract(const uint8_t* bin, int bpitch, const int32_t* labels, int 
   info[2] = r.n_edges;
   for (int i = 0; i < 8; ++i) corners[i] = r.status == Q_OK ? r.c[i] : 0.f;
 }
+
+// featureRecovery over an ordered quad list (half-res coords).  feats_out: [cap] FeatureRec.  Returns the feature count.
+int hh_feature_recovery(const float* quads, int nq, FeatureRec* feats_out, int cap) {
+  std::vector<QuadGeom> g(nq);
+  for (int i = 0; i < nq; ++i) quad_geom(quads + 8 * i, &g[i]);
+  std::vector<char> vis(nq, 0);
+  int nf = 0;
+  for (int i = 0; i + 1 < nq; ++i) {
+    if (vis[i]) continue;
+    for (int j = i + 1; j < nq; ++j) {
+      if (vis[j]) continue;
+      float fa;
+      if (pair_test(quads + 8 * i, g[i], quads + 8 * j, g[j], &fa)) {
+        vis[i] = vis[j] = 1;
+        if (nf < cap) {
+          FeatureRec& f = feats_out[nf];
+          float cen[2];
+          feature_organize(quads + 8 * i, quads + 8 * j, g[i], g[j], fa, f.c, cen);
+          f.cx = cen[0], f.cy = cen[1], f.angle = fa, f.qi = i, f.qj = j;
+        }
+        ++nf;
+        break;
+      }
+    }
+  }
+  return nf;
+}
+
+void hh_corner_obtain(FeatureRec* feats, int nf) {
+  for (int i = 0; i < nf; ++i) {
+    float cen[2];
+    corner_obtain(feats[i].c, cen);
+    feats[i].cx = cen[0], feats[i].cy = cen[1];
+  }
+}
+
+void hh_edge_refine(const uint8_t* gray, int pitch, int cols, int rows, FeatureRec* feats, int nf, int win) {
+  for (int i = 0; i < nf; ++i) {
+    float* c = feats[i].c;
+    for (int base = 0; base < 8; base += 4) {
+      double nxt[4][4], lst[4][4];
+      for (int e = 0; e < 4; ++e) {
+        int a = base + e, b = base + ((e + 1) & 3);
+        double nx, ny;
+        int ns;
+        edge_setup(c[2 * a], c[2 * a + 1], c[2 * b], c[2 * b + 1], &nx, &ny, &ns);
+        EdgeMoments mn, ml;
+        em_zero(mn), em_zero(ml);
+        edge_samples(gray, pitch, cols, rows, c[2 * a], c[2 * a + 1], c[2 * b], c[2 * b + 1], win, 0, 1, nx, ny, ns, mn, ml);
+        edge_line(mn, nxt[e]);
+        edge_line(ml, lst[e]);
+      }
+      float nc[4][2];
+      bool upd[4];
+      for (int it = 0; it < 4; ++it) upd[it] = edge_corner(nxt[it], lst[(it + 1) & 3], &nc[it][0], &nc[it][1]);
+      for (int it = 0; it < 4; ++it)
+        if (upd[it]) {
+          int k = base + ((it + 1) & 3);
+          c[2 * k] = nc[it][0], c[2 * k + 1] = nc[it][1];
+        }
+    }
+  }
+}
+
+int hh_organize_decode(const FeatureRec* feats, int nf, const int32_t* state, int rows, int cols, int fsz, ctag_marker* out,
+                       int cap, int32_t* info /* n_groups, flagged, stale */) {
+  std::vector<int> father(128), group_of(128), order(128), cover(2 * rows * cols + 32);
+  std::vector<uint8_t> link(128);
+  DecodeScratch sc{father.data(), link.data(), group_of.data(), order.data(), cover.data()};
+  return organize_and_decode(feats, nf, state, rows, cols, fsz, Lanes{0, 1}, sc, out, cap, 0, &info[0], &info[1], &info[2]);
+}
+
+int hh_sizeof_feature(void) { return (int)sizeof(FeatureRec); }
 }
