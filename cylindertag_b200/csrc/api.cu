@@ -182,7 +182,7 @@ static int ensure_workspace(ctag_detector* d, int n, int w, int h) {
   {
     cudaDeviceProp prop;
     CTAG_CUDA_CHECK(cudaGetDeviceProperties(&prop, d->device));
-    d->scratch_warps = prop.multiProcessorCount * 16;  // persistent grid: 4 CTAs x 4 warps per SM
+    d->scratch_warps = prop.multiProcessorCount * 6;  // persistent grid: 6 CTAs (96 threads each) per SM
     CTAG_CUDA_CHECK(cudaMalloc(&d->d_quad_scratch, quad_scratch_bytes_per_warp(g) * d->scratch_warps));
   }
   d->cap_frames = cap;

@@ -92,8 +92,7 @@ CT_HD float libm_sinf(float y) {
   }
   int n;
   x = sincos_reduce(x, &n);
-  const double sg[4] = {1.0, -1.0, -1.0, 1.0};
-  double s = sg[n & 3];
+  double s = ((n + 1) & 2) ? -1.0 : 1.0;  // sign table {1,-1,-1,1}[n & 3]
   return sincos_poly(x * s, x * x, n, (n & 2) != 0);
 }
 
@@ -105,24 +104,32 @@ CT_HD float libm_cosf(float y) {
   }
   int n;
   x = sincos_reduce(x, &n);
-  const double sg[4] = {1.0, -1.0, -1.0, 1.0};
-  double s = sg[n & 3];
+  double s = ((n + 1) & 2) ? -1.0 : 1.0;
   return sincos_poly(x * s, x * x, n ^ 1, (n & 2) != 0);
 }
 
-// 2^(i/32) as IEEE doubles minus (i << 47): the exp2f table (values are the correctly rounded 2^(i/32))
+// 2^(i/32) as IEEE doubles minus (i << 47): the exp2f table (values are the correctly rounded 2^(i/32)).
+// Kept in global memory on the device: a function-local array indexed per lane would be rebuilt on the stack on
+// every call (measured: ~45 % of the quad kernel's instructions were those stores).
+#define CTAG_EXP2F_TAB \
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull, \
+    0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull, \
+    0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull, \
+    0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull, \
+    0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull, \
+    0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull, \
+    0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull, \
+    0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull
+#if defined(__CUDACC__)
+static __device__ const uint64_t kExp2fTabDev[32] = {CTAG_EXP2F_TAB};
+#endif
+static const uint64_t kExp2fTabHost[32] = {CTAG_EXP2F_TAB};
 CT_HD uint64_t exp2f_tab(int i) {
-  const uint64_t T[32] = {
-      0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,
-      0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,
-      0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
-      0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull,
-      0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,
-      0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,
-      0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
-      0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull,
-  };
-  return T[i];
+#ifdef __CUDA_ARCH__
+  return kExp2fTabDev[i];
+#else
+  return kExp2fTabHost[i];
+#endif
 }
 
 CT_HD float libm_expf(float x) {

@@ -148,11 +148,20 @@ struct PtArray {
   CT_HD int operator()(int j) const { return p[j]; }
 };
 
-CT_HD void quad_extract(const CompView& cv, const QuadScratch& sc, Lanes ln, QuadResult* res) {
+// Result of the edge stage: the four point clusters (in sc.cl, back to back) and the boundary centre.
+struct QuadEdges {
+  int cnt;        // accepted edges (cnt_boundary); a quad needs 4
+  int cl_off[5];  // cluster c = sc.cl[cl_off[c] .. cl_off[c+1])
+  float cx, cy;   // area_center
+  int n_trace;
+};
+
+// Steps 1-4: silhouettes, oriented trace, centre/rotation, extended RDP with span expansion.  One lane group.
+CT_HD void quad_stage_edges(const CompView& cv, const QuadScratch& sc, Lanes ln, QuadEdges* out) {
   const int w = cv.x1 - cv.x0 + 1, h = cv.y1 - cv.y0 + 1, wpr = (w + 31) >> 5;
-  res->status = Q_FEW_EDGES;
+  QuadEdges* res = out;
+  res->cnt = 0;
   res->n_trace = 0;
-  res->n_edges = 0;
 
   // ---- 1. four silhouettes -> boundary bit map (corner_detector.cpp:197-232) --------------------------------------
   // The ray-cast's `if (visited) break` can never fire before the first mask pixel (visited is a subset of mask), so
@@ -381,30 +390,46 @@ CT_HD void quad_extract(const CompView& cv, const QuadScratch& sc, Lanes ln, Qua
       break;
     }
   }
-  res->n_edges = cnt;
-  if (cnt < 4) return;  // some cluster has < 2 points (:351-361)
+  res->cnt = cnt;
+  res->cx = cx;
+  res->cy = cy;
+  for (int c = 0; c < 5; ++c) res->cl_off[c] = cl_off[c];
+}
 
-  // ---- 5. four DIST_WELSCH fits (:358); 4 x 20 independent restarts spread over the lanes -------------------------
-  for (int c = ln.id; c < 4; c += ln.n) {
-    Rng rng{0xFFFFFFFFFFFFFFFFull};
-    const int count = cl_off[c + 1] - cl_off[c];
-    for (int k = 0; k < 20; ++k) {
-      sc.rng[c * 20 + k] = rng.state;
-      welsch_skip_restart(rng, count);
-    }
+// ---- 5. four DIST_WELSCH fits (:358): 4 x 20 independent restarts = 80 tasks ----------------------------------------
+// (a) generator state at the start of every (cluster, restart): run by 4 lanes, one per cluster
+CT_HD void quad_welsch_prepare(const QuadEdges& ed, const QuadScratch& sc, int c) {
+  Rng rng{0xFFFFFFFFFFFFFFFFull};
+  const int count = ed.cl_off[c + 1] - ed.cl_off[c];
+  for (int k = 0; k < 20; ++k) {
+    sc.rng[c * 20 + k] = rng.state;
+    welsch_skip_restart(rng, count);
   }
-  w_sync();
-  for (int t = ln.id; t < 80; t += ln.n) {
-    const int c = t / 20;
-    PtArray pa{sc.cl + cl_off[c]};
-    sc.nvis[t] = welsch_restart(pa, cl_off[c + 1] - cl_off[c], Rng{sc.rng[t]}, sc.iters + t * 30, 1, 0.0);
+}
+// (b) one restart, t = cluster * 20 + restart.  With <= 10 points every restart starts from all points and follows the
+//     same trajectory, so only restart 0 is computed and the others report no iterates (the bookkeeping only ever
+//     takes strictly smaller errors, so repeats never change it).
+CT_HD void quad_welsch_task(const QuadEdges& ed, const QuadScratch& sc, int t) {
+  const int c = t / 20, k = t - 20 * c;
+  const int count = ed.cl_off[c + 1] - ed.cl_off[c];
+  if (count <= 10 && k > 0) {
+    sc.nvis[t] = 0;
+    return;
   }
-  w_sync();
-  for (int c = ln.id; c < 4; c += ln.n)
-    welsch_combine(sc.iters + c * 600, 30, 1, sc.nvis + c * 20, 1, cl_off[c + 1] - cl_off[c], 1, sc.lines + 4 * c);
-  w_sync();
+  PtArray pa{sc.cl + ed.cl_off[c]};
+  sc.nvis[t] = welsch_restart(pa, count, Rng{sc.rng[t]}, sc.iters + t * 30, 1, 0.0);
+}
+// (c) library bookkeeping over the 20 restarts of cluster c
+CT_HD void quad_welsch_combine(const QuadEdges& ed, const QuadScratch& sc, int c) {
+  welsch_combine(sc.iters + c * 600, 30, 1, sc.nvis + c * 20, 1, ed.cl_off[c + 1] - ed.cl_off[c], 1, sc.lines + 4 * c);
+}
 
-  // ---- 6. six intersections, angular sort, best 4-subset (:362-403, 420-463) --------------------------------------
+// ---- 6. six intersections, angular sort, best 4-subset (:362-403, 420-463); scalar, any single lane ----------------
+CT_HD void quad_stage_select(const CompView& cv, const QuadScratch& sc, const QuadEdges& ed, QuadResult* res) {
+  const float cx = ed.cx, cy = ed.cy;
+  res->status = Q_NO_QUAD;
+  res->n_trace = ed.n_trace;
+  res->n_edges = ed.cnt;
   float ix[6], iy[6], ia[6];
   int nc = 0;
   for (int j = 0; j < 3; ++j)
@@ -465,6 +490,23 @@ CT_HD void quad_extract(const CompView& cv, const QuadScratch& sc, Lanes ln, Qua
     res->c[2 * k + 1] = y;
   }
   res->status = Q_OK;
+}
+
+// All stages with one lane group (host harness; the device kernel spreads stage 5 over a whole CTA instead).
+CT_HD void quad_extract(const CompView& cv, const QuadScratch& sc, Lanes ln, QuadResult* res) {
+  QuadEdges ed;
+  quad_stage_edges(cv, sc, ln, &ed);
+  res->status = Q_FEW_EDGES;
+  res->n_trace = ed.n_trace;
+  res->n_edges = ed.cnt;
+  if (ed.cnt < 4) return;  // some cluster has < 2 points (:351-361)
+  for (int c = ln.id; c < 4; c += ln.n) quad_welsch_prepare(ed, sc, c);
+  w_sync();
+  for (int t = ln.id; t < 80; t += ln.n) quad_welsch_task(ed, sc, t);
+  w_sync();
+  for (int c = ln.id; c < 4; c += ln.n) quad_welsch_combine(ed, sc, c);
+  w_sync();
+  quad_stage_select(cv, sc, ed, res);
 }
 
 }  // namespace core
