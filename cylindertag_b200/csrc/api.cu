@@ -67,7 +67,10 @@ struct ctag_detector {
       *d_n_quads = nullptr;
   float *d_quad_corners = nullptr, *d_quads = nullptr;
   uint8_t* d_quad_scratch = nullptr;
-  int scratch_warps = 0;
+  int edge_warps = 0, fit_warps = 0, fit_cap = 0, pool_cap = 0;
+  void *d_fits = nullptr, *d_traj = nullptr;
+  int* d_pool = nullptr;
+  float* d_lines = nullptr;
   static constexpr int kQuadCap = CTAG_MAX_FRAME_QUADS;
   // features / markers (a6-a10)
   void *d_geom = nullptr, *d_feats = nullptr;
@@ -115,13 +118,16 @@ static void free_workspace(ctag_detector* d) {
   void* ptrs[] = {d->d_gray, d->d_bin, d->d_labels, d->d_st_area, d->d_st_x0, d->d_st_y0, d->d_st_x1, d->d_st_y1,
                   d->d_roots_tmp, d->d_span_count, d->d_legal, d->d_counters, d->d_prefix, d->d_work_counter,
                   d->d_quad_status, d->d_quad_comp, d->d_n_quads, d->d_quad_corners, d->d_quads, d->d_quad_scratch,
-                  d->d_geom, d->d_feats, d->d_fstate, d->d_packed_count, d->d_summary, d->d_markers, d->d_packed};
+                  d->d_geom, d->d_feats, d->d_fstate, d->d_packed_count, d->d_summary, d->d_markers, d->d_packed,
+                  d->d_fits, d->d_traj, d->d_pool, d->d_lines};
   for (void* p : ptrs) cudaFree(p);
   cudaFreeHost(d->h_summary);
   cudaFreeHost(d->h_packed);
   d->h_summary = nullptr;
   d->h_packed = nullptr;
-  d->d_geom = d->d_feats = nullptr;
+  d->d_geom = d->d_feats = d->d_fits = d->d_traj = nullptr;
+  d->d_pool = nullptr;
+  d->d_lines = nullptr;
   d->d_fstate = d->d_packed_count = d->d_summary = nullptr;
   d->d_markers = d->d_packed = nullptr;
   d->d_gray = d->d_bin = d->d_quad_scratch = nullptr;
@@ -164,7 +170,7 @@ static int ensure_workspace(ctag_detector* d, int n, int w, int h) {
   CTAG_CUDA_CHECK(dev_alloc(&d->d_legal, (size_t)d->legal_cap * 6 * cap));
   CTAG_CUDA_CHECK(dev_alloc(&d->d_counters, (size_t)4 * cap));
   CTAG_CUDA_CHECK(dev_alloc(&d->d_prefix, (size_t)cap + 1));
-  CTAG_CUDA_CHECK(dev_alloc(&d->d_work_counter, 4));
+  CTAG_CUDA_CHECK(dev_alloc(&d->d_work_counter, 8));
   CTAG_CUDA_CHECK(dev_alloc(&d->d_quad_status, (size_t)d->legal_cap * cap));
   CTAG_CUDA_CHECK(dev_alloc(&d->d_quad_corners, (size_t)d->legal_cap * 8 * cap));
   CTAG_CUDA_CHECK(dev_alloc(&d->d_quads, (size_t)ctag_detector::kQuadCap * 8 * cap));
@@ -182,8 +188,18 @@ static int ensure_workspace(ctag_detector* d, int n, int w, int h) {
   {
     cudaDeviceProp prop;
     CTAG_CUDA_CHECK(cudaGetDeviceProperties(&prop, d->device));
-    d->scratch_warps = prop.multiProcessorCount * 6;  // persistent grid: 6 CTAs (96 threads each) per SM
-    CTAG_CUDA_CHECK(cudaMalloc(&d->d_quad_scratch, quad_scratch_bytes_per_warp(g) * d->scratch_warps));
+    d->edge_warps = quad_edge_warps(prop.multiProcessorCount);
+    d->fit_warps = quad_fit_warps(prop.multiProcessorCount);
+    CTAG_CUDA_CHECK(cudaMalloc(&d->d_quad_scratch, quad_scratch_bytes_per_warp(g) * d->edge_warps));
+    CTAG_CUDA_CHECK(cudaMalloc(&d->d_traj, quad_traj_bytes_per_warp() * d->fit_warps));
+    // components that reach four edges / their cluster points: generous bounds, overflow drops the component and
+    // flags the frame instead of writing out of bounds
+    d->fit_cap = cap * (d->legal_cap < 8192 ? d->legal_cap : 8192);
+    const long long per_frame_pts = (long long)g.hw * g.hh < 262144 ? (long long)g.hw * g.hh : 262144;
+    d->pool_cap = (int)(per_frame_pts * cap < 0x7fffffff ? per_frame_pts * cap : 0x7fffffff);
+    CTAG_CUDA_CHECK(cudaMalloc(&d->d_fits, quad_fitrec_bytes() * d->fit_cap));
+    CTAG_CUDA_CHECK(dev_alloc(&d->d_lines, (size_t)16 * d->fit_cap));
+    CTAG_CUDA_CHECK(dev_alloc(&d->d_pool, (size_t)d->pool_cap));
   }
   d->cap_frames = cap;
   return CTAG_OK;
@@ -303,8 +319,9 @@ int ctag_detect_batch_enqueue(ctag_detector* d, const void* frames_dev, int n, i
   if (rc != CTAG_OK) return rc;
   CTAG_CUDA_CHECK(cudaEventRecord(d->ev[2], d->stream));
   rc = launch_quad(n, d->geo, d->d_bin, d->bin_fstride, d->d_labels, d->d_legal, d->legal_cap, d->d_counters, d->d_prefix,
-                   d->d_work_counter, d->d_quad_scratch, d->scratch_warps, d->d_quad_status, d->d_quad_corners,
-                   ctag_detector::kQuadCap, d->d_quads, d->d_quad_comp, d->d_n_quads, d->stream, &d->launches);
+                   d->d_work_counter, d->d_quad_scratch, d->edge_warps, d->d_fits, d->fit_cap, d->d_pool, d->pool_cap,
+                   d->d_traj, d->fit_warps, d->d_lines, d->d_quad_status, d->d_quad_corners, ctag_detector::kQuadCap,
+                   d->d_quads, d->d_quad_comp, d->d_n_quads, d->stream, &d->launches);
   if (rc != CTAG_OK) return rc;
   CTAG_CUDA_CHECK(cudaEventRecord(d->ev[3], d->stream));
   rc = launch_features(n, d->geo, d->d_quads, d->d_n_quads, ctag_detector::kQuadCap, d->d_geom, d->d_feats,
@@ -314,7 +331,7 @@ int ctag_detect_batch_enqueue(ctag_detector* d, const void* frames_dev, int n, i
   CTAG_CUDA_CHECK(cudaEventRecord(d->ev[4], d->stream));
   rc = launch_decode(n, d->d_feats, ctag_detector::kFeatCap, d->d_fstate, d->d_state, d->rows, d->cols, d->feature_size,
                      d->d_markers, ctag_detector::kMarkerCap, d->d_counters, d->d_n_quads, ctag_detector::kQuadCap,
-                     d->d_packed, d->d_packed_count, d->d_summary, d->stream, &d->launches);
+                     d->d_work_counter + 4 /* QC_OVERFLOW */, d->d_packed, d->d_packed_count, d->d_summary, d->stream, &d->launches);
   if (rc != CTAG_OK) return rc;
   CTAG_CUDA_CHECK(cudaEventRecord(d->ev[5], d->stream));
   CTAG_CUDA_CHECK(cudaMemcpyAsync(d->h_summary, d->d_summary, sizeof(int) * 12 * n, cudaMemcpyDeviceToHost, d->stream));

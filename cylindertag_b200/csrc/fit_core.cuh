@@ -91,19 +91,60 @@ struct WelschIter {
   float line[4];
 };
 
-template <typename PtFn>
-CT_HD int welsch_restart(PtFn pt, int count, Rng rng_at_restart, WelschIter* out /*[30]*/, int out_stride, double eps) {
-  Rng rng = rng_at_restart;
-  // initial subset: min(count,10) distinct indices
-  int picked[10];
-  int np = 0;
+// x % d for 32-bit x without the integer-division sequence: one double multiply and a +-1 correction (exact).
+struct FastMod {
+  uint32_t d;
+  double inv;
+};
+CT_HD FastMod fastmod_make(int d) { return FastMod{(uint32_t)d, 1.0 / (double)d}; }
+CT_HD uint32_t fastmod(uint32_t x, const FastMod& m) {
+  uint32_t q = (uint32_t)((double)x * m.inv);
+  int64_t r = (int64_t)x - (int64_t)q * m.d;
+  if (r < 0) r += m.d;
+  else if (r >= (int64_t)m.d) r -= m.d;
+  return (uint32_t)r;
+}
+
+// Subset selection of one restart: draws indices until min(count,10) distinct ones are marked (the library's
+// `w[j] < FLT_EPSILON` test on a zeroed weight array).  Advances the generator; returns the picks in draw order.
+CT_HD int welsch_pick(Rng& rng, int count, const FastMod& fm, int* picked /*[10]*/) {
   const int need = count < 10 ? count : 10;
-  while (np < need) {
-    int j = rng_uniform(rng, 0, count);
-    bool dup = false;
-    for (int q = 0; q < np; ++q) dup |= (picked[q] == j);
-    if (!dup) picked[np++] = j;
+  int np = 0;
+  if (count <= 64) {
+    uint64_t seen = 0;
+    while (np < need) {
+      int j = (int)fastmod(rng_next(rng), fm);  // RNG::uniform(0, count) = next() % count
+      uint64_t b = 1ull << j;
+      if (!(seen & b)) {
+        seen |= b;
+        picked[np++] = j;
+      }
+    }
+  } else {
+    while (np < need) {
+      int j = (int)fastmod(rng_next(rng), fm);
+      bool dup = false;
+      for (int q = 0; q < np; ++q) dup |= (picked[q] == j);
+      if (!dup) picked[np++] = j;
+    }
   }
+  return np;
+}
+
+// Advances the generator over one restart's subset selection (so that restart k+1 can start from the right state).
+CT_HD void welsch_skip_restart(Rng& rng, int count) {
+  int picked[10];
+  FastMod fm = fastmod_make(count);
+  welsch_pick(rng, count, fm, picked);
+}
+
+// One restart; `visit(i, err, line)` is called for every iterate (at most 30).  Returns the number of iterates.
+template <typename PtFn, typename Visitor>
+CT_HD int welsch_restart_visit(PtFn pt, int count, Rng rng_at_restart, Visitor& visit) {
+  Rng rng = rng_at_restart;
+  int picked[10];
+  FastMod fm = fastmod_make(count);
+  int np = welsch_pick(rng, count, fm, picked);
   // the library accumulates over i = 0..count-1 with w[i] in {0,1}: ascending index order
   for (int a = 1; a < np; ++a) {
     int v = picked[a], b = a - 1;
@@ -152,11 +193,8 @@ CT_HD int welsch_restart(PtFn pt, int count, Rng rng_at_restart, WelschIter* out
       err += r;
       sum_w += welsch_exp(-r * r * c * c);
     }
-    WelschIter& o = out[nvis * out_stride];
-    o.err = err;
-    o.line[0] = line[0], o.line[1] = line[1], o.line[2] = line[2], o.line[3] = line[3];
+    visit(nvis, err, line);
     ++nvis;
-    if (err < eps) break;  // optional early stop (callers that need the exact library bookkeeping pass eps = 0)
     // normalised weights + refit (second pass recomputes the residuals instead of storing them)
     double x = 0, y = 0, x2 = 0, y2 = 0, xy = 0, wsum = 0;
     const bool norm = fabs(sum_w) > 1.1920928955078125e-07;
@@ -180,17 +218,37 @@ CT_HD int welsch_restart(PtFn pt, int count, Rng rng_at_restart, WelschIter* out
   return nvis;
 }
 
-// Advances the generator over one restart's subset selection (so that restart k+1 can start from the right state).
-CT_HD void welsch_skip_restart(Rng& rng, int count) {
-  int picked[10];
-  int np = 0;
-  const int need = count < 10 ? count : 10;
-  while (np < need) {
-    int j = rng_uniform(rng, 0, count);
-    bool dup = false;
-    for (int q = 0; q < np; ++q) dup |= (picked[q] == j);
-    if (!dup) picked[np++] = j;
+// Visitor that stores the whole trajectory (exact library bookkeeping through welsch_combine).
+struct WelschStore {
+  WelschIter* out;
+  int stride;
+  CT_HD void operator()(int i, double err, const float* line) {
+    WelschIter& o = out[i * stride];
+    o.err = err;
+    o.line[0] = line[0], o.line[1] = line[1], o.line[2] = line[2], o.line[3] = line[3];
   }
+};
+
+// Visitor that keeps only the restart's first minimum and whether any error fell below EPS.  When no restart of a fit
+// sees a sub-EPS error the library's result is simply the first occurrence of the global minimum, so nothing else has
+// to be stored; otherwise the caller recomputes with WelschStore and runs welsch_combine.
+struct WelschBest {
+  double err, eps;
+  float line[4];
+  bool sub_eps;
+  CT_HD void operator()(int, double e, const float* l) {
+    if (e < err) {
+      err = e;
+      line[0] = l[0], line[1] = l[1], line[2] = l[2], line[3] = l[3];
+    }
+    if (e < eps) sub_eps = true;
+  }
+};
+
+template <typename PtFn>
+CT_HD int welsch_restart(PtFn pt, int count, Rng rng_at_restart, WelschIter* out /*[30]*/, int out_stride, double) {
+  WelschStore st{out, out_stride};
+  return welsch_restart_visit(pt, count, rng_at_restart, st);
 }
 
 // Sequential bookkeeping of fitLine2D over the 20 restarts: `if (err < min_err) { keep; if (err < EPS) stop }`.

@@ -15,12 +15,17 @@ int launch_ccl(const uint8_t* bin, size_t bin_fstride, int n, const FrameGeom& g
                int* st_y0, int* st_x1, int* st_y1, int* roots_tmp, int* span_count, int* legal, int legal_cap,
                int* counters, cudaStream_t stream, int* launches);
 
-// K4 (quad.cu): one warp per legal component -> quad or nothing; ordered compaction of the quads.
+// K4 (quad.cu): edges (warp per component) -> Welsch fits (warp per edge) -> corner selection -> ordered compaction.
 size_t quad_scratch_bytes_per_warp(const FrameGeom& g);
+size_t quad_fitrec_bytes();
+size_t quad_traj_bytes_per_warp();
+int quad_edge_warps(int sms);
+int quad_fit_warps(int sms);
 int launch_quad(int n, const FrameGeom& g, const uint8_t* bin, size_t bin_fstride, const int* labels, const int* legal,
-                int legal_cap, const int* counters, int* prefix, int* work_counter, uint8_t* scratch, int scratch_warps,
-                int* quad_status, float* quad_corners, int quad_cap, float* quads, int* quad_comp, int* n_quads,
-                cudaStream_t stream, int* launches);
+                int legal_cap, const int* counters, int* prefix, int* qctl, uint8_t* scratch, int edge_warps, void* fits,
+                int fit_cap, int* pool, int pool_cap, void* traj, int fit_warps, float* lines, int* quad_status,
+                float* quad_corners, int quad_cap, float* quads, int* quad_comp, int* n_quads, cudaStream_t stream,
+                int* launches);
 
 // K5/K6 (feature.cu): quad pairing, coordinate lift, edge refinement.  fstate[frame] = {status, n_features,
 // n_features going on, overflow}.
@@ -35,6 +40,7 @@ int launch_features(int n, const FrameGeom& g, const float* quads, const int* n_
 size_t decode_smem_bytes(int srows, int scols);
 int launch_decode(int n, const void* feats, int feat_cap, const int* fstate, const int* state, int srows, int scols, int fsz,
                   ctag_marker* markers, int marker_cap, const int* counters, const int* n_quads, int quad_cap,
-                  ctag_marker* packed, int* packed_count, int* summary, cudaStream_t stream, int* launches);
+                  const int* batch_overflow, ctag_marker* packed, int* packed_count, int* summary, cudaStream_t stream,
+                  int* launches);
 
 }  // namespace ctag

@@ -143,6 +143,26 @@ CT_HD bool solve2x2(float a00, float a01, float a10, float a11, float b0, float 
   return true;
 }
 
+// bits (x-1, x, x+1) of bit-map row y as bits 0..2; rows outside the box and columns outside the row read as 0
+CT_HD uint32_t row_bits3(const uint32_t* vis, int wpr, int h, int y, int x) {
+  if (y < 0 || y >= h) return 0u;
+  const uint32_t* row = vis + y * wpr;
+  const int xm = x - 1;
+  if (xm < 0) return (row[0] << 1) & 7u;
+  const int wi = xm >> 5, sh = xm & 31;
+  uint64_t v = row[wi];
+  if (sh > 29 && wi + 1 < wpr) v |= (uint64_t)row[wi + 1] << 32;
+  return (uint32_t)(v >> sh) & 7u;
+}
+
+// 8-neighbour occupancy of (x,y) in the reference's probing order N,NE,E,SE,S,SW,W,NW (corner_detector.h:84-85)
+CT_HD uint32_t nbr_mask(const uint32_t* vis, int wpr, int h, int x, int y) {
+  const uint32_t t0 = row_bits3(vis, wpr, h, y - 1, x), t1 = row_bits3(vis, wpr, h, y, x),
+                 t2 = row_bits3(vis, wpr, h, y + 1, x);
+  return ((t0 >> 1) & 1u) | (((t0 >> 2) & 1u) << 1) | (((t1 >> 2) & 1u) << 2) | (((t2 >> 2) & 1u) << 3) |
+         (((t2 >> 1) & 1u) << 4) | ((t2 & 1u) << 5) | ((t1 & 1u) << 6) | ((t0 & 1u) << 7);
+}
+
 struct PtArray {
   const int* p;
   CT_HD int operator()(int j) const { return p[j]; }
@@ -208,25 +228,26 @@ CT_HD void quad_stage_edges(const CompView& cv, const QuadScratch& sc, Lanes ln,
     P[n++] = pt_pack(fx + cv.x0, fy + cv.y0);
     sc.vis[fy * wpr] &= ~1u;
     while (true) {
-      if (fj == 8) {
+      // Directions fj..7 are probed at a fixed position and the bit map only changes inside a recursive call, so
+      // the first hit is the first set bit of the 8-neighbour mask at or after fj.
+      uint32_t m = fj < 8 ? (nbr_mask(sc.vis, wpr, h, fx, fy) >> fj) : 0u;
+      if (m == 0) {
         if (sp == 0) break;
         int fr = sc.stack[--sp];
         fx = fr & 0xFFF, fy = (fr >> 12) & 0xFFF, fj = fr >> 24;
         continue;
       }
-      int nx = fx + (int)((0x1A9u >> (2 * fj)) & 3u) - 1;
-      int ny = fy + (int)((0x1A90u >> (2 * fj)) & 3u) - 1;
-      ++fj;
-      if (nx >= 0 && nx < w && ny >= 0 && ny < h) {
-        uint32_t* wd = &sc.vis[ny * wpr + (nx >> 5)];
-        uint32_t m = 1u << (nx & 31);
-        if (*wd & m) {
-          *wd &= ~m;
-          P[n++] = pt_pack(nx + cv.x0, ny + cv.y0);
-          sc.stack[sp++] = nx | (ny << 12) | (fj << 24);  // caller resumes at direction fj from the new position
-          fx = nx, fy = ny, fj = 0;
-        }
-      }
+#ifdef __CUDA_ARCH__
+      const int j = fj + __ffs(m) - 1;
+#else
+      const int j = fj + __builtin_ctz(m);
+#endif
+      const int nx = fx + (int)((0x1A9u >> (2 * j)) & 3u) - 1;
+      const int ny = fy + (int)((0x1A90u >> (2 * j)) & 3u) - 1;
+      sc.vis[ny * wpr + (nx >> 5)] &= ~(1u << (nx & 31));
+      P[n++] = pt_pack(nx + cv.x0, ny + cv.y0);
+      sc.stack[sp++] = nx | (ny << 12) | ((j + 1) << 24);  // caller resumes at direction j+1 from the new position
+      fx = nx, fy = ny, fj = 0;
     }
   }
   w_sync();
