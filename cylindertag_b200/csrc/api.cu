@@ -67,8 +67,11 @@ struct ctag_detector {
       *d_n_quads = nullptr;
   float *d_quad_corners = nullptr, *d_quads = nullptr;
   uint8_t* d_quad_scratch = nullptr;
-  int edge_warps = 0, fit_warps = 0, fit_cap = 0, pool_cap = 0;
-  void *d_fits = nullptr, *d_traj = nullptr;
+  int edge_warps = 0, exact_ctas = 0, sms = 0, fit_cap = 0, pool_cap = 0;
+  void *d_fits = nullptr, *d_traj = nullptr, *d_fit_results = nullptr;
+  int* d_exact_list = nullptr;
+  uint16_t* d_pick_table = nullptr;  // per detector, independent of the frame geometry
+  static constexpr int kPickTableMax = 1024;
   int* d_pool = nullptr;
   float* d_lines = nullptr;
   static constexpr int kQuadCap = CTAG_MAX_FRAME_QUADS;
@@ -119,13 +122,14 @@ static void free_workspace(ctag_detector* d) {
                   d->d_roots_tmp, d->d_span_count, d->d_legal, d->d_counters, d->d_prefix, d->d_work_counter,
                   d->d_quad_status, d->d_quad_comp, d->d_n_quads, d->d_quad_corners, d->d_quads, d->d_quad_scratch,
                   d->d_geom, d->d_feats, d->d_fstate, d->d_packed_count, d->d_summary, d->d_markers, d->d_packed,
-                  d->d_fits, d->d_traj, d->d_pool, d->d_lines};
+                  d->d_fits, d->d_traj, d->d_pool, d->d_lines, d->d_fit_results, d->d_exact_list};
   for (void* p : ptrs) cudaFree(p);
   cudaFreeHost(d->h_summary);
   cudaFreeHost(d->h_packed);
   d->h_summary = nullptr;
   d->h_packed = nullptr;
-  d->d_geom = d->d_feats = d->d_fits = d->d_traj = nullptr;
+  d->d_geom = d->d_feats = d->d_fits = d->d_traj = d->d_fit_results = nullptr;
+  d->d_exact_list = nullptr;
   d->d_pool = nullptr;
   d->d_lines = nullptr;
   d->d_fstate = d->d_packed_count = d->d_summary = nullptr;
@@ -188,13 +192,17 @@ static int ensure_workspace(ctag_detector* d, int n, int w, int h) {
   {
     cudaDeviceProp prop;
     CTAG_CUDA_CHECK(cudaGetDeviceProperties(&prop, d->device));
-    d->edge_warps = quad_edge_warps(prop.multiProcessorCount);
-    d->fit_warps = quad_fit_warps(prop.multiProcessorCount);
+    d->sms = prop.multiProcessorCount;
+    d->edge_warps = quad_edge_warps(d->sms);
+    d->exact_ctas = quad_exact_ctas(d->sms);
     CTAG_CUDA_CHECK(cudaMalloc(&d->d_quad_scratch, quad_scratch_bytes_per_warp(g) * d->edge_warps));
-    CTAG_CUDA_CHECK(cudaMalloc(&d->d_traj, quad_traj_bytes_per_warp() * d->fit_warps));
-    // components that reach four edges / their cluster points: generous bounds, overflow drops the component and
-    // flags the frame instead of writing out of bounds
-    d->fit_cap = cap * (d->legal_cap < 8192 ? d->legal_cap : 8192);
+    CTAG_CUDA_CHECK(cudaMalloc(&d->d_traj, quad_traj_bytes_per_cta() * d->exact_ctas));
+    // components that reach four edges / their cluster points: the reference caps a frame at 1000 quads
+    // (isVisited[1000]), so 1024 four-edge components per frame is already past its envelope; overflow drops the
+    // component and flags the frame instead of writing out of bounds
+    d->fit_cap = cap * (d->legal_cap < 1024 ? d->legal_cap : 1024);
+    CTAG_CUDA_CHECK(cudaMalloc(&d->d_fit_results, quad_fitresult_bytes() * 80 * (size_t)d->fit_cap));
+    CTAG_CUDA_CHECK(dev_alloc(&d->d_exact_list, (size_t)4 * d->fit_cap));
     const long long per_frame_pts = (long long)g.hw * g.hh < 262144 ? (long long)g.hw * g.hh : 262144;
     d->pool_cap = (int)(per_frame_pts * cap < 0x7fffffff ? per_frame_pts * cap : 0x7fffffff);
     CTAG_CUDA_CHECK(cudaMalloc(&d->d_fits, quad_fitrec_bytes() * d->fit_cap));
@@ -240,6 +248,17 @@ int ctag_create(ctag_detector** out, const int32_t* state, int rows, int cols, i
     return CTAG_ERR_CUDA;
   }
   for (auto& e : d->ev) cudaEventCreate(&e);
+  {
+    // initial subsets of cv::fitLine's 20 restarts for every point count up to kPickTableMax (fit_core.cuh)
+    std::vector<uint16_t> table((size_t)ctag_detector::kPickTableMax * 200);
+    quad_build_pick_table(table.data(), ctag_detector::kPickTableMax);
+    if (cudaMalloc(&d->d_pick_table, table.size() * sizeof(uint16_t)) != cudaSuccess ||
+        cudaMemcpy(d->d_pick_table, table.data(), table.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_last_error("pick table", cudaGetLastError(), __FILE__, __LINE__);
+      ctag_destroy(d);
+      return CTAG_ERR_CUDA;
+    }
+  }
   *out = d;
   return CTAG_OK;
 }
@@ -263,6 +282,7 @@ void ctag_destroy(ctag_detector* d) {
   free_workspace(d);
   cudaFree(d->d_stage);
   cudaFree(d->d_state);
+  cudaFree(d->d_pick_table);
   for (auto& e : d->ev)
     if (e) cudaEventDestroy(e);
   if (d->stream) cudaStreamDestroy(d->stream);
@@ -320,7 +340,8 @@ int ctag_detect_batch_enqueue(ctag_detector* d, const void* frames_dev, int n, i
   CTAG_CUDA_CHECK(cudaEventRecord(d->ev[2], d->stream));
   rc = launch_quad(n, d->geo, d->d_bin, d->bin_fstride, d->d_labels, d->d_legal, d->legal_cap, d->d_counters, d->d_prefix,
                    d->d_work_counter, d->d_quad_scratch, d->edge_warps, d->d_fits, d->fit_cap, d->d_pool, d->pool_cap,
-                   d->d_traj, d->fit_warps, d->d_lines, d->d_quad_status, d->d_quad_corners, ctag_detector::kQuadCap,
+                   d->d_pick_table, ctag_detector::kPickTableMax, d->d_fit_results, d->d_exact_list, d->d_traj,
+                   d->exact_ctas, d->sms, d->d_lines, d->d_quad_status, d->d_quad_corners, ctag_detector::kQuadCap,
                    d->d_quads, d->d_quad_comp, d->d_n_quads, d->stream, &d->launches);
   if (rc != CTAG_OK) return rc;
   CTAG_CUDA_CHECK(cudaEventRecord(d->ev[3], d->stream));

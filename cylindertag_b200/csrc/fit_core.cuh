@@ -138,14 +138,10 @@ CT_HD void welsch_skip_restart(Rng& rng, int count) {
   welsch_pick(rng, count, fm, picked);
 }
 
-// One restart; `visit(i, err, line)` is called for every iterate (at most 30).  Returns the number of iterates.
-template <typename PtFn, typename Visitor>
-CT_HD int welsch_restart_visit(PtFn pt, int count, Rng rng_at_restart, Visitor& visit) {
-  Rng rng = rng_at_restart;
-  int picked[10];
-  FastMod fm = fastmod_make(count);
-  int np = welsch_pick(rng, count, fm, picked);
-  // the library accumulates over i = 0..count-1 with w[i] in {0,1}: ascending index order
+// The generator is re-seeded with the same constant for every fitLine call, so the subset picked by restart k depends
+// on the point count only.  welsch_pick_table fills table[(count-1)*200 + k*10 + a] with the picks of every restart for
+// count = 1..max_count, sorted ascending (the order in which the library accumulates them).
+CT_HD void welsch_sort_picks(int* picked, int np) {
   for (int a = 1; a < np; ++a) {
     int v = picked[a], b = a - 1;
     while (b >= 0 && picked[b] > v) {
@@ -154,6 +150,37 @@ CT_HD int welsch_restart_visit(PtFn pt, int count, Rng rng_at_restart, Visitor& 
     }
     picked[b + 1] = v;
   }
+}
+inline void welsch_pick_table(uint16_t* table, int max_count) {
+  for (int count = 1; count <= max_count; ++count) {
+    Rng rng{0xFFFFFFFFFFFFFFFFull};
+    FastMod fm = fastmod_make(count);
+    for (int k = 0; k < 20; ++k) {
+      int picked[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      int np = welsch_pick(rng, count, fm, picked);
+      welsch_sort_picks(picked, np);
+      for (int a = 0; a < 10; ++a) table[(size_t)(count - 1) * 200 + k * 10 + a] = (uint16_t)(a < np ? picked[a] : 0);
+    }
+  }
+}
+
+// One restart from its (sorted) initial subset; `visit(i, err, line)` is called for every iterate (at most 30).
+template <typename PtFn, typename Visitor>
+CT_HD int welsch_restart_from_picks(PtFn pt, int count, const int* picked, int np, Visitor& visit);
+
+// One restart; the subset is drawn from the generator state at the start of the restart.
+template <typename PtFn, typename Visitor>
+CT_HD int welsch_restart_visit(PtFn pt, int count, Rng rng_at_restart, Visitor& visit) {
+  Rng rng = rng_at_restart;
+  int picked[10];
+  FastMod fm = fastmod_make(count);
+  int np = welsch_pick(rng, count, fm, picked);
+  welsch_sort_picks(picked, np);  // the library accumulates over i = 0..count-1 with w[i] in {0,1}: ascending order
+  return welsch_restart_from_picks(pt, count, picked, np, visit);
+}
+
+template <typename PtFn, typename Visitor>
+CT_HD int welsch_restart_from_picks(PtFn pt, int count, const int* picked, int np, Visitor& visit) {
   float line[4], prev[4] = {0, 0, 0, 0};
   {
     double x = 0, y = 0, x2 = 0, y2 = 0, xy = 0, w = 0;

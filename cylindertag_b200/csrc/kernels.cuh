@@ -15,17 +15,20 @@ int launch_ccl(const uint8_t* bin, size_t bin_fstride, int n, const FrameGeom& g
                int* st_y0, int* st_x1, int* st_y1, int* roots_tmp, int* span_count, int* legal, int legal_cap,
                int* counters, cudaStream_t stream, int* launches);
 
-// K4 (quad.cu): edges (warp per component) -> Welsch fits (warp per edge) -> corner selection -> ordered compaction.
+// K4 (quad.cu): edges (warp per component) -> Welsch fits (thread per restart, merge, exact fallback) -> corner
+// selection -> ordered compaction.
 size_t quad_scratch_bytes_per_warp(const FrameGeom& g);
 size_t quad_fitrec_bytes();
-size_t quad_traj_bytes_per_warp();
+size_t quad_fitresult_bytes();
+size_t quad_traj_bytes_per_cta();
 int quad_edge_warps(int sms);
-int quad_fit_warps(int sms);
+int quad_exact_ctas(int sms);
+void quad_build_pick_table(uint16_t* host_table, int max_count);
 int launch_quad(int n, const FrameGeom& g, const uint8_t* bin, size_t bin_fstride, const int* labels, const int* legal,
                 int legal_cap, const int* counters, int* prefix, int* qctl, uint8_t* scratch, int edge_warps, void* fits,
-                int fit_cap, int* pool, int pool_cap, void* traj, int fit_warps, float* lines, int* quad_status,
-                float* quad_corners, int quad_cap, float* quads, int* quad_comp, int* n_quads, cudaStream_t stream,
-                int* launches);
+                int fit_cap, int* pool, int pool_cap, const uint16_t* pick_table, int table_max, void* results,
+                int* exact_list, void* traj, int exact_ctas, int sms, float* lines, int* quad_status, float* quad_corners,
+                int quad_cap, float* quads, int* quad_comp, int* n_quads, cudaStream_t stream, int* launches);
 
 // K5/K6 (feature.cu): quad pairing, coordinate lift, edge refinement.  fstate[frame] = {status, n_features,
 // n_features going on, overflow}.

@@ -1,6 +1,6 @@
 // K4: quad extraction (reference row a5, corner_detector.cpp:171-405) as three kernels over device work lists:
 //   quad_edges_kernel  one warp per legal component: silhouettes, oriented trace, extended RDP -> four clusters
-//   quad_fit_kernel    one warp per (component, edge): the 20 Welsch restarts of cv::fitLine on 20 lanes
+//   quad_fit_kernel    one thread per (component, edge, restart) of cv::fitLine(DIST_WELSCH) + merge / exact fallback
 //   quad_select_kernel one thread per component: six intersections, best 4-subset
 // plus the ordered compaction of the surviving quads.  The per-component arithmetic lives in quad_core.cuh /
 // fit_core.cuh (shared with the host logic tests).
@@ -52,7 +52,7 @@ static QuadScratchLayout make_layout(const FrameGeom& g) {
 size_t quad_scratch_bytes_per_warp(const FrameGeom& g) { return make_layout(g).total; }  // per persistent CTA
 
 // control words of the quad stage (device ints)
-enum { QC_WORK_EDGES = 0, QC_WORK_FITS = 1, QC_FIT_COUNT = 2, QC_POOL_CURSOR = 3, QC_OVERFLOW = 4, QC_WORDS = 8 };
+enum { QC_WORK_EDGES = 0, QC_EXACT_COUNT = 1, QC_FIT_COUNT = 2, QC_POOL_CURSOR = 3, QC_OVERFLOW = 4, QC_WORDS = 8 };
 
 // Component that reached four edges: what the line fits and the corner selection need.
 struct FitRec {
@@ -181,89 +181,125 @@ __global__ void __launch_bounds__(32 * kEdgeWarps) quad_edges_kernel(
   }
 }
 
-// ---- K4b: DIST_WELSCH fits, one warp per (component, edge) -------------------------------------------------------------
-// Lane 0 replays the generator to get the state at the start of each of the 20 restarts; lanes 0..19 then run one
-// restart each.  If no restart sees an error below EPS the library result is the first occurrence of the minimum
-// error (warp arg-min, ties to the lower restart).  Otherwise the restarts are replayed with their trajectories
-// stored and the library's exact bookkeeping runs on lane 0.
-constexpr int kFitWarps = 4;
-constexpr int kFitSmemPts = 256;
+// ---- K4b: DIST_WELSCH fits (cv::fitLine, corner_detector.cpp:358) -----------------------------------------------------
+// quad_fit_kernel     one THREAD per (component, edge, restart): the 80 restarts of a component are independent given
+//                     their initial subsets, which depend on the point count only and come from a table built once
+//                     per detector.  Each thread reports its first minimum and whether any error fell below EPS.
+// quad_fitmerge_kernel one thread per (component, edge): without a sub-EPS error the library result is the first
+//                     occurrence of the minimum (lowest restart on ties); otherwise the edge is queued for ...
+// quad_fitexact_kernel one warp per queued edge: restarts replayed with stored trajectories, then the library's exact
+//                     sequential bookkeeping (welsch_combine).
+struct FitResult {
+  double err;
+  float line[4];
+  int sub_eps;
+  int pad;
+};
 
-struct SmemOrGlobalPts {
+struct PoolPts {
   const int* p;
   __device__ __forceinline__ int operator()(int j) const { return p[j]; }
 };
 
-__global__ void __launch_bounds__(32 * kFitWarps) quad_fit_kernel(int* __restrict__ qctl, const FitRec* __restrict__ fits,
-                                                                  int fit_cap, const int* __restrict__ pool,
-                                                                  WelschIter* __restrict__ traj /* per warp 20*30 */,
-                                                                  float* __restrict__ lines /* [fit][16] */) {
-  __shared__ int s_pts[kFitWarps][kFitSmemPts];
-  __shared__ uint64_t s_rng[kFitWarps][20];
-  __shared__ int s_nvis[kFitWarps][20];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int warp_global = blockIdx.x * kFitWarps + warp;
+__device__ __forceinline__ int load_picks(const uint16_t* __restrict__ table, int table_max, int count, int k, int* picked) {
+  const int np = count < 10 ? count : 10;
+  if (count <= table_max) {
+    const uint16_t* t = table + (size_t)(count - 1) * 200 + k * 10;
+    for (int a = 0; a < np; ++a) picked[a] = t[a];
+  } else {
+    // beyond the table: replay the generator from the seed (rare: > table_max boundary points on one edge)
+    Rng rng{0xFFFFFFFFFFFFFFFFull};
+    FastMod fm = fastmod_make(count);
+    for (int q = 0; q <= k; ++q) welsch_pick(rng, count, fm, picked);
+    welsch_sort_picks(picked, np);
+  }
+  return np;
+}
+
+__global__ void __launch_bounds__(128) quad_fit_kernel(const int* __restrict__ qctl, const FitRec* __restrict__ fits,
+                                                       int fit_cap, const int* __restrict__ pool,
+                                                       const uint16_t* __restrict__ pick_table, int table_max,
+                                                       FitResult* __restrict__ results) {
   int nfit = qctl[QC_FIT_COUNT];
   if (nfit > fit_cap) nfit = fit_cap;
-  const int total = 4 * nfit;
-  while (true) {
-    int item = 0;
-    if (lane == 0) item = atomicAdd(&qctl[QC_WORK_FITS], 1);
-    item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= total) break;
-    const int slot = item >> 2, c = item & 3;
+  const int total = 80 * nfit;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int slot = t / 80, r = t - 80 * slot, c = r / 20, k = r - 20 * c;
     const FitRec* fr = fits + slot;
-    const int off = fr->pool_off + fr->cl_off[c];
     const int count = fr->cl_off[c + 1] - fr->cl_off[c];
-    const int* src = pool + off;
-    if (count <= kFitSmemPts) {
-      for (int i = lane; i < count; i += 32) s_pts[warp][i] = src[i];
-      src = s_pts[warp];
-    }
-    if (lane == 0) {
-      Rng rng{0xFFFFFFFFFFFFFFFFull};
-      const int nk = count <= 10 ? 1 : 20;  // <= 10 points: every restart picks all points, only restart 0 is needed
-      for (int k = 0; k < nk; ++k) {
-        s_rng[warp][k] = rng.state;
-        welsch_skip_restart(rng, count);
-      }
-    }
-    __syncwarp();
-    SmemOrGlobalPts pa{src};
-    const bool active = lane < 20 && (count > 10 || lane == 0);
     WelschBest best;
     best.err = 1.7976931348623157e308;
     best.eps = count * 1.1920928955078125e-07;
     best.sub_eps = false;
     best.line[0] = best.line[1] = best.line[2] = best.line[3] = 0.f;
-    if (active) welsch_restart_visit(pa, count, Rng{s_rng[warp][lane]}, best);
-    float out4[4];
-    if (__ballot_sync(0xffffffffu, active && best.sub_eps) == 0u) {
-      // first occurrence of the global minimum: min error, ties to the lowest restart index
-      double e = active ? best.err : 1.7976931348623157e308;
-      int k = lane;
-#pragma unroll
-      for (int s = 16; s > 0; s >>= 1) {
-        double e2 = __shfl_xor_sync(0xffffffffu, e, s);
-        int k2 = __shfl_xor_sync(0xffffffffu, k, s);
-        if (e2 < e || (e2 == e && k2 < k)) e = e2, k = k2;
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) out4[q] = __shfl_sync(0xffffffffu, best.line[q], k);
-    } else {
-      WelschIter* tw = traj + (size_t)warp_global * 600;
-      if (lane < 20) s_nvis[warp][lane] = 0;
-      __syncwarp();
-      if (active) {
-        WelschStore st{tw + lane * 30, 1};
-        s_nvis[warp][lane] = welsch_restart_visit(pa, count, Rng{s_rng[warp][lane]}, st);
-      }
-      __syncwarp();
-      if (lane == 0) welsch_combine(tw, 30, 1, s_nvis[warp], 1, count, 1, out4);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) out4[q] = __shfl_sync(0xffffffffu, out4[q], 0);
+    // <= 10 points: every restart starts from all points and follows the same trajectory; restart 0 stands for all
+    if (count > 10 || k == 0) {
+      int picked[10];
+      const int np = load_picks(pick_table, table_max, count, k, picked);
+      PoolPts pa{pool + fr->pool_off + fr->cl_off[c]};
+      welsch_restart_from_picks(pa, count, picked, np, best);
     }
-    if (lane == 0) *reinterpret_cast<float4*>(lines + (size_t)slot * 16 + 4 * c) = make_float4(out4[0], out4[1], out4[2], out4[3]);
+    FitResult o;
+    o.err = best.err;
+    o.line[0] = best.line[0], o.line[1] = best.line[1], o.line[2] = best.line[2], o.line[3] = best.line[3];
+    o.sub_eps = best.sub_eps ? 1 : 0;
+    o.pad = 0;
+    results[t] = o;
+  }
+}
+
+__global__ void __launch_bounds__(128) quad_fitmerge_kernel(int* __restrict__ qctl, int fit_cap,
+                                                            const FitResult* __restrict__ results, float* __restrict__ lines,
+                                                            int* __restrict__ exact_list) {
+  int nfit = qctl[QC_FIT_COUNT];
+  if (nfit > fit_cap) nfit = fit_cap;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;  // edge id = slot * 4 + c
+  if (e >= 4 * nfit) return;
+  const FitResult* r = results + (size_t)e * 20;
+  double best = 1.7976931348623157e308;
+  int bk = 0, any_sub = 0;
+  for (int k = 0; k < 20; ++k) {
+    const double err = r[k].err;
+    any_sub |= r[k].sub_eps;
+    if (err < best) best = err, bk = k;  // strict: first occurrence wins, as in `if (err < min_err)`
+  }
+  if (any_sub) {
+    exact_list[atomicAdd(&qctl[QC_EXACT_COUNT], 1)] = e;
+    return;
+  }
+  *reinterpret_cast<float4*>(lines + (size_t)e * 4) = make_float4(r[bk].line[0], r[bk].line[1], r[bk].line[2], r[bk].line[3]);
+}
+
+__global__ void __launch_bounds__(32) quad_fitexact_kernel(int* __restrict__ qctl, const int* __restrict__ exact_list,
+                                                           const FitRec* __restrict__ fits, const int* __restrict__ pool,
+                                                           const uint16_t* __restrict__ pick_table, int table_max,
+                                                           WelschIter* __restrict__ traj /* per CTA 20*30 */,
+                                                           float* __restrict__ lines) {
+  __shared__ int s_nvis[20];
+  const int lane = threadIdx.x;
+  const int total = qctl[QC_EXACT_COUNT];
+  WelschIter* tw = traj + (size_t)blockIdx.x * 600;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int e = exact_list[item], slot = e >> 2, c = e & 3;
+    const FitRec* fr = fits + slot;
+    const int count = fr->cl_off[c + 1] - fr->cl_off[c];
+    if (lane < 20) {
+      int nv = 0;
+      if (count > 10 || lane == 0) {
+        int picked[10];
+        const int np = load_picks(pick_table, table_max, count, lane, picked);
+        PoolPts pa{pool + fr->pool_off + fr->cl_off[c]};
+        WelschStore st{tw + lane * 30, 1};
+        nv = welsch_restart_from_picks(pa, count, picked, np, st);
+      }
+      s_nvis[lane] = nv;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      float out4[4];
+      welsch_combine(tw, 30, 1, s_nvis, 1, count, 1, out4);
+      *reinterpret_cast<float4*>(lines + (size_t)e * 4) = make_float4(out4[0], out4[1], out4[2], out4[3]);
+    }
     __syncwarp();
   }
 }
@@ -325,28 +361,34 @@ __global__ void __launch_bounds__(32) quad_compact_kernel(const int* __restrict_
 }
 
 size_t quad_fitrec_bytes() { return sizeof(FitRec); }
-size_t quad_traj_bytes_per_warp() { return sizeof(WelschIter) * 600; }
-int quad_edge_warps(int sms) { return sms * 4 * kEdgeWarps; }   // persistent: 4 CTAs x 4 warps per SM
-int quad_fit_warps(int sms) { return sms * 8 * kFitWarps; }     // persistent: 8 CTAs x 4 warps per SM
+size_t quad_fitresult_bytes() { return sizeof(FitResult); }
+size_t quad_traj_bytes_per_cta() { return sizeof(WelschIter) * 600; }
+int quad_edge_warps(int sms) { return sms * 4 * kEdgeWarps; }  // persistent: 4 CTAs x 4 warps per SM
+int quad_exact_ctas(int sms) { return sms * 8; }
+void quad_build_pick_table(uint16_t* host_table, int max_count) { welsch_pick_table(host_table, max_count); }
 
 int launch_quad(int n, const FrameGeom& g, const uint8_t* bin, size_t bin_fstride, const int* labels, const int* legal,
                 int legal_cap, const int* counters, int* prefix, int* qctl, uint8_t* scratch, int edge_warps, void* fits,
-                int fit_cap, int* pool, int pool_cap, void* traj, int fit_warps, float* lines, int* quad_status,
-                float* quad_corners, int quad_cap, float* quads, int* quad_comp, int* n_quads, cudaStream_t stream,
-                int* launches) {
+                int fit_cap, int* pool, int pool_cap, const uint16_t* pick_table, int table_max, void* results,
+                int* exact_list, void* traj, int exact_ctas, int sms, float* lines, int* quad_status, float* quad_corners,
+                int quad_cap, float* quads, int* quad_comp, int* n_quads, cudaStream_t stream, int* launches) {
   QuadScratchLayout L = make_layout(g);
   quad_prefix_kernel<<<1, 32, 0, stream>>>(counters, n, prefix, qctl);
   quad_edges_kernel<<<edge_warps / kEdgeWarps, 32 * kEdgeWarps, 0, stream>>>(
       n, g, bin, bin_fstride, labels, legal, legal_cap, prefix, qctl, scratch, L, quad_status, static_cast<FitRec*>(fits),
       fit_cap, pool, pool_cap);
-  quad_fit_kernel<<<fit_warps / kFitWarps, 32 * kFitWarps, 0, stream>>>(qctl, static_cast<const FitRec*>(fits), fit_cap, pool,
-                                                                        static_cast<WelschIter*>(traj), lines);
+  quad_fit_kernel<<<sms * 16, 128, 0, stream>>>(qctl, static_cast<const FitRec*>(fits), fit_cap, pool, pick_table, table_max,
+                                                static_cast<FitResult*>(results));
+  quad_fitmerge_kernel<<<(4 * fit_cap + 127) / 128, 128, 0, stream>>>(qctl, fit_cap, static_cast<const FitResult*>(results),
+                                                                     lines, exact_list);
+  quad_fitexact_kernel<<<exact_ctas, 32, 0, stream>>>(qctl, exact_list, static_cast<const FitRec*>(fits), pool, pick_table,
+                                                      table_max, static_cast<WelschIter*>(traj), lines);
   quad_select_kernel<<<(fit_cap + 127) / 128, 128, 0, stream>>>(qctl, static_cast<const FitRec*>(fits), fit_cap, lines,
                                                                 quad_status, quad_corners);
   quad_compact_kernel<<<n, 32, 0, stream>>>(counters, legal_cap, quad_status, quad_corners, quad_cap, quads, quad_comp,
                                             n_quads);
   CTAG_CUDA_CHECK(cudaGetLastError());
-  if (launches) *launches += 5;
+  if (launches) *launches += 7;
   return CTAG_OK;
 }
 

@@ -168,6 +168,202 @@ struct PtArray {
   CT_HD int operator()(int j) const { return p[j]; }
 };
 
+CT_HD float expand_dist(int px, int py, const float* line) {  // dist_expand of expand_line (:144,:156)
+  return fabsf((float)px * line[1] - (float)py * line[0] + line[0] * line[3] - line[1] * line[2]);
+}
+
+// expand_line (:125-169), literal sequential form with exact incremental moments.  Returns how many points were
+// appended on the left (indices init-1, init-2, ... wrapping) and on the right (end+1, ... wrapping).
+CT_HD void expand_span_seq(const int* P, int n, int init, int end, int* nl_out, int* nr_out) {
+  IntMoments mom;
+  im_reset(mom);
+  for (int i = init; i <= end; ++i) im_add(mom, pt_x(P[i]), pt_y(P[i]));
+  float line[4];
+  im_fit(mom, line);
+  bool fl = false, fr = false;
+  int left = init - 1, right = end + 1, nl = 0, nr = 0;
+  while ((!fl || !fr) && left != right) {
+    if (!fl) {
+      if (left == -1) left = n - 1;
+      int px = pt_x(P[left]), py = pt_y(P[left]);
+      if (expand_dist(px, py, line) > kExpand()) {
+        fl = true;
+        continue;
+      }
+      im_add(mom, px, py);
+      ++nl;
+      --left;
+      im_fit(mom, line);
+      if (mom.n == n) break;
+    }
+    if (!fr) {
+      if (right == n) right = 0;
+      int px = pt_x(P[right]), py = pt_y(P[right]);
+      if (expand_dist(px, py, line) > kExpand()) {
+        fr = true;
+        continue;
+      }
+      im_add(mom, px, py);
+      ++nr;
+      ++right;
+      im_fit(mom, line);
+      if (mom.n == n) break;
+    }
+  }
+  *nl_out = nl;
+  *nr_out = nr;
+}
+
+// The same function, speculatively parallel: the order in which points would be appended is known as long as no
+// distance test fails (left/right alternately, or one side only), so 32 lanes each assume "everything before me was
+// accepted", build that prefix fit from exact integer prefix moments and test their own candidate.  The first failing
+// lane ends the round; everything before it is accepted exactly as the sequential loop would have.  A span of k points
+// costs about k/32 + 3 fits of latency instead of k.  (The host build emulates the 32 lanes with a loop.)
+CT_HD void expand_span(const int* P, int n, int init, int end, Lanes ln, int* nl_out, int* nr_out) {
+  const int SW = 32;
+  IntMoments mom;
+  im_reset(mom);
+#ifdef __CUDA_ARCH__
+  {
+    int sx = 0, sy = 0;
+    long long sxx = 0, syy = 0, sxy = 0;
+    for (int i = init + ln.id; i <= end; i += ln.n) {
+      int x = pt_x(P[i]), y = pt_y(P[i]);
+      sx += x, sy += y, sxx += x * x, syy += y * y, sxy += x * y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sx += __shfl_xor_sync(0xffffffffu, sx, o);
+      sy += __shfl_xor_sync(0xffffffffu, sy, o);
+      sxx += __shfl_xor_sync(0xffffffffu, sxx, o);
+      syy += __shfl_xor_sync(0xffffffffu, syy, o);
+      sxy += __shfl_xor_sync(0xffffffffu, sxy, o);
+    }
+    mom.sx = sx, mom.sy = sy, mom.sxx = sxx, mom.syy = syy, mom.sxy = sxy, mom.n = end - init + 1;
+  }
+#else
+  (void)ln;
+  for (int i = init; i <= end; ++i) im_add(mom, pt_x(P[i]), pt_y(P[i]));
+#endif
+  bool fl = false, fr = false;
+  int nl = 0, nr = 0;
+  int frozen_l = 0, frozen_r = 0;  // a finished side keeps the (normalised) index of the candidate that failed
+  const int left0 = init - 1, right0 = end + 1;
+  // raw cursor values as the reference's `left != right` sees them: an active cursor that has just stepped past the
+  // end is still -1 / n (it is normalised at its next use), a finished one stays on its failed candidate
+#define CT_RAW_L(q) (fl ? frozen_l : ((left0 - (q)) >= -1 ? (left0 - (q)) : (left0 - (q)) + n))
+#define CT_RAW_R(q) (fr ? frozen_r : ((right0 + (q)) <= n ? (right0 + (q)) : (right0 + (q)) - n))
+  while (true) {
+    if ((fl && fr) || CT_RAW_L(nl) == CT_RAW_R(nr)) break;
+    const bool both = !fl && !fr;
+    const int m0 = mom.n;
+    int limit = n - m0 < SW ? n - m0 : SW;  // candidates that exist before the list is fully covered
+    int acc, fail_at = -1, fail_idx = 0;
+    IntMoments add;  // moments of the accepted candidates of this round
+    im_reset(add);
+#ifdef __CUDA_ARCH__
+    {
+      const int i = ln.id;
+      const bool is_left = both ? !(i & 1) : !fl;
+      const int q = both ? (i >> 1) : i;
+      int raw = is_left ? left0 - (nl + q) : right0 + (nr + q);
+      int idx = is_left ? (raw >= 0 ? raw : raw + n) : (raw < n ? raw : raw - n);
+      // loop-top equality in front of the iteration this candidate starts
+      bool topstop = false;
+      if (i > 0 && (!both || !(i & 1)))
+        topstop = CT_RAW_L(nl + (both ? q : (is_left ? q : 0))) == CT_RAW_R(nr + (both ? q : (is_left ? 0 : q)));
+      unsigned tmask = __ballot_sync(0xffffffffu, topstop);
+      if (tmask) {
+        int t = __ffs(tmask) - 1;
+        limit = t < limit ? t : limit;
+      }
+      const bool exist = i < limit;
+      int px = 0, py = 0;
+      if (exist) px = pt_x(P[idx]), py = pt_y(P[idx]);
+      // inclusive prefix sums over lanes (all fit 32 bits: 32 points, coordinates < 4096)
+      int sx = px, sy = py, sxx = px * px, syy = py * py, sxy = px * py;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int a = __shfl_up_sync(0xffffffffu, sx, o), b = __shfl_up_sync(0xffffffffu, sy, o);
+        int c = __shfl_up_sync(0xffffffffu, sxx, o), d = __shfl_up_sync(0xffffffffu, syy, o);
+        int e = __shfl_up_sync(0xffffffffu, sxy, o);
+        if (i >= o) sx += a, sy += b, sxx += c, syy += d, sxy += e;
+      }
+      bool fail = false;
+      if (exist) {
+        IntMoments pm = mom;  // exclusive prefix: everything before this candidate
+        pm.sx += sx - px, pm.sy += sy - py, pm.sxx += sxx - px * px, pm.syy += syy - py * py, pm.sxy += sxy - px * py;
+        pm.n += i;
+        float line[4];
+        im_fit(pm, line);
+        fail = expand_dist(px, py, line) > kExpand();
+      }
+      unsigned fmask = __ballot_sync(0xffffffffu, fail);
+      if (fmask) {
+        fail_at = __ffs(fmask) - 1;
+        fail_idx = __shfl_sync(0xffffffffu, idx, fail_at);
+      }
+      acc = fail_at >= 0 ? fail_at : limit;
+      if (acc > 0) {
+        add.sx = __shfl_sync(0xffffffffu, sx, acc - 1);
+        add.sy = __shfl_sync(0xffffffffu, sy, acc - 1);
+        add.sxx = __shfl_sync(0xffffffffu, sxx, acc - 1);
+        add.syy = __shfl_sync(0xffffffffu, syy, acc - 1);
+        add.sxy = __shfl_sync(0xffffffffu, sxy, acc - 1);
+      }
+    }
+#else
+    {
+      IntMoments run;
+      im_reset(run);
+      acc = -1;
+      for (int i = 0; i < SW && acc < 0; ++i) {
+        const bool is_left = both ? !(i & 1) : !fl;
+        const int q = both ? (i >> 1) : i;
+        if (i > 0 && (!both || !(i & 1)) &&
+            CT_RAW_L(nl + (both ? q : (is_left ? q : 0))) == CT_RAW_R(nr + (both ? q : (is_left ? 0 : q))) && i < limit)
+          limit = i;
+        if (i >= limit) {
+          acc = limit;
+          break;
+        }
+        int raw = is_left ? left0 - (nl + q) : right0 + (nr + q);
+        int idx = is_left ? (raw >= 0 ? raw : raw + n) : (raw < n ? raw : raw - n);
+        int px = pt_x(P[idx]), py = pt_y(P[idx]);
+        IntMoments pm = mom;
+        pm.sx += run.sx, pm.sy += run.sy, pm.sxx += run.sxx, pm.syy += run.syy, pm.sxy += run.sxy, pm.n += i;
+        float line[4];
+        im_fit(pm, line);
+        if (expand_dist(px, py, line) > kExpand()) {
+          fail_at = i;
+          fail_idx = idx;
+          acc = i;
+          break;
+        }
+        im_add(run, px, py);
+      }
+      if (acc < 0) acc = limit;
+      add = run;
+    }
+#endif
+    mom.sx += add.sx, mom.sy += add.sy, mom.sxx += add.sxx, mom.syy += add.syy, mom.sxy += add.sxy, mom.n += acc;
+    if (both) nl += (acc + 1) >> 1, nr += acc >> 1;
+    else if (!fl) nl += acc;
+    else nr += acc;
+    if (fail_at >= 0) {
+      const bool left_failed = both ? !(fail_at & 1) : !fl;
+      if (left_failed) fl = true, frozen_l = fail_idx;
+      else fr = true, frozen_r = fail_idx;
+      continue;  // the reference's `continue`: back to the loop top, the failed side is finished
+    }
+    if (mom.n == n) break;  // Slide.size() == edge_point.size()
+  }
+#undef CT_RAW_L
+#undef CT_RAW_R
+  *nl_out = nl;
+  *nr_out = nr;
+}
+
 // Result of the edge stage: the four point clusters (in sc.cl, back to back) and the boundary centre.
 struct QuadEdges {
   int cnt;        // accepted edges (cnt_boundary); a quad needs 4
@@ -329,49 +525,9 @@ CT_HD void quad_stage_edges(const CompView& cv, const QuadScratch& sc, Lanes ln,
         end = last - (init + 1);  // C-5: the index relative to init+1 is used as an absolute index
         continue;
       }
-      // ---- expand_line (:125-169) on lane 0, exact incremental moments -----------------------------------------
+      // ---- expand_line (:125-169): speculative lane-parallel form, exact incremental moments ---------------------
       int nl = 0, nr = 0;
-      if (ln.id == 0) {
-        IntMoments mom;
-        im_reset(mom);
-        for (int i = init; i <= end; ++i) im_add(mom, pt_x(P[i]), pt_y(P[i]));
-        float line[4];
-        im_fit(mom, line);
-        bool fl = false, fr = false;
-        int left = init - 1, right = end + 1;
-        while ((!fl || !fr) && left != right) {
-          if (!fl) {
-            if (left == -1) left = n - 1;
-            int px = pt_x(P[left]), py = pt_y(P[left]);
-            float d = fabsf((float)px * line[1] - (float)py * line[0] + line[0] * line[3] - line[1] * line[2]);
-            if (d > kExpand()) {
-              fl = true;
-              continue;
-            }
-            im_add(mom, px, py);
-            ++nl;
-            --left;
-            im_fit(mom, line);
-            if (mom.n == n) break;
-          }
-          if (!fr) {
-            if (right == n) right = 0;
-            int px = pt_x(P[right]), py = pt_y(P[right]);
-            float d = fabsf((float)px * line[1] - (float)py * line[0] + line[0] * line[3] - line[1] * line[2]);
-            if (d > kExpand()) {
-              fr = true;
-              continue;
-            }
-            im_add(mom, px, py);
-            ++nr;
-            ++right;
-            im_fit(mom, line);
-            if (mom.n == n) break;
-          }
-        }
-      }
-      nl = w_bcast_i(nl, 0);
-      nr = w_bcast_i(nr, 0);
+      expand_span(P, n, init, end, ln, &nl, &nr);
       // the span is the cyclic interval [a, a+len) of indices; the reference sorts it descending
       const int len = (end - init + 1) + nl + nr;
       int a = init - nl;

@@ -135,4 +135,12 @@ int hh_organize_decode(const FeatureRec* feats, int nf, const int32_t* state, in
 }
 
 int hh_sizeof_feature(void) { return (int)sizeof(FeatureRec); }
+
+// expand_line in its literal sequential form and in the speculative form used by the kernels (lanes emulated by a loop)
+void hh_expand_both(const int32_t* pts, int n, int init, int end, int32_t* out4) {
+  std::vector<int> packed(n);
+  for (int i = 0; i < n; ++i) packed[i] = pt_pack(pts[2 * i], pts[2 * i + 1]);
+  expand_span_seq(packed.data(), n, init, end, &out4[0], &out4[1]);
+  expand_span(packed.data(), n, init, end, Lanes{0, 1}, &out4[2], &out4[3]);
+}
 }

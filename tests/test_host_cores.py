@@ -150,3 +150,39 @@ def test_fast_atan2_close_to_cv2():
         y, x = rng.uniform(-100, 100, 2)
         ref = cv2.fastAtan2(float(np.float32(y)), float(np.float32(x)))
         assert abs(ref - (math.degrees(math.atan2(y, x)) % 360)) < 0.35
+
+
+def test_speculative_expand_equals_sequential():
+    """expand_line: the lane-speculative form (as run by the kernels) against the literal sequential loop on closed
+    boundaries with straight runs, wrap-arounds and early coverage."""
+    lib = H.lib()
+    rng = np.random.default_rng(5)
+    out = np.zeros(4, np.int32)
+    for trial in range(3000):
+        kind = trial % 4
+        if kind == 0:  # rectangle outline
+            a, b = rng.integers(3, 40), rng.integers(3, 40)
+            pts = [(x, 0) for x in range(a)] + [(a - 1, y) for y in range(1, b)] + [(x, b - 1) for x in range(a - 2, -1, -1)] + \
+                  [(0, y) for y in range(b - 2, 0, -1)]
+        elif kind == 1:  # noisy circle-ish polygon
+            m = int(rng.integers(8, 150))
+            t = np.linspace(0, 2 * np.pi, m, endpoint=False)
+            r = rng.uniform(5, 60)
+            pts = list({(int(round(100 + r * np.cos(u))), int(round(100 + r * np.sin(u)))) for u in t})
+        elif kind == 2:  # one long straight run (coverage break)
+            m = int(rng.integers(5, 120))
+            pts = [(10 + i, 50 + (i // int(rng.integers(3, 30)))) for i in range(m)]
+        else:  # random walk
+            m = int(rng.integers(6, 100))
+            steps = rng.integers(-1, 2, (m, 2))
+            pts = list(map(tuple, (np.cumsum(steps, 0) + 200).tolist()))
+        n = len(pts)
+        if n < 4:
+            continue
+        arr = np.ascontiguousarray(np.array(pts, np.int32))
+        init = int(rng.integers(0, n - 2))
+        end = int(min(n - 1, init + rng.integers(2, max(3, n // 2 + 1))))
+        if end <= init + 1:
+            continue
+        lib.hh_expand_both(H.vp(arr), n, init, end, H.vp(out))
+        assert out[0] == out[2] and out[1] == out[3], (trial, n, init, end, out)
