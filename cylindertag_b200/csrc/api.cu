@@ -1,4 +1,8 @@
-// C ABI (include/ctag.h) over the sm_100a detection kernels: detector handle, workspace, batch pipeline.
+// C ABI (include/ctag.h) over the sm_100a detection kernels: detector handle, workspaces, batch pipeline.
+//
+// A detector owns kSlots independent workspaces ("slots"), each with its own CUDA stream, so that two batches can be
+// in flight: the latency-bound sparse kernels of batch i overlap the bandwidth-bound dense kernels of batch i+1
+// (ctag_detect_batch_enqueue may be called twice before ctag_detect_batch_collect; results come back in FIFO order).
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -38,64 +42,61 @@ static FrameGeom make_geom(int w, int h) {
   return g;
 }
 
+constexpr int kSlots = 2;
+constexpr int kQuadCap = CTAG_MAX_FRAME_QUADS;
+constexpr int kFeatCap = CTAG_MAX_FRAME_FEATURES;
+constexpr int kMarkerCap = CTAG_MAX_FRAME_FEATURES / 2;
+constexpr int kPickTableMax = 1024;
+
+// Everything one batch needs on the device, plus its stream, events and pinned result buffers.
+struct Slot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[CTAG_STAGE_COUNT + 1] = {};
+  int cap_frames = 0, w = 0, h = 0;
+  FrameGeom geo{};
+  uint8_t* d_stage = nullptr;  // staging for host inputs
+  size_t stage_bytes = 0;
+  std::vector<void*> owned;  // device allocations of the workspace (freed together)
+  uint8_t *d_gray = nullptr, *d_bin = nullptr, *d_quad_scratch = nullptr;
+  size_t gray_fstride = 0, bin_fstride = 0;
+  int *d_labels = nullptr, *d_st_area = nullptr, *d_st_x0 = nullptr, *d_st_y0 = nullptr, *d_st_x1 = nullptr,
+      *d_st_y1 = nullptr, *d_roots_tmp = nullptr, *d_span_count = nullptr, *d_legal = nullptr, *d_counters = nullptr;
+  int legal_cap = 0, spans = 0;
+  int *d_prefix = nullptr, *d_qctl = nullptr, *d_quad_status = nullptr, *d_quad_comp = nullptr, *d_n_quads = nullptr,
+      *d_exact_list = nullptr, *d_pool = nullptr;
+  float *d_quad_corners = nullptr, *d_quads = nullptr, *d_lines = nullptr;
+  void *d_fits = nullptr, *d_traj = nullptr, *d_fit_results = nullptr, *d_geom = nullptr, *d_feats = nullptr;
+  int edge_warps = 0, exact_ctas = 0, fit_cap = 0, pool_cap = 0;
+  int *d_fstate = nullptr, *d_packed_count = nullptr, *d_summary = nullptr;
+  ctag_marker *d_markers = nullptr, *d_packed = nullptr;
+  int* h_summary = nullptr;         // pinned
+  ctag_marker* h_packed = nullptr;  // pinned
+  // the batch this slot holds
+  int n = 0, channels = 0, subpix = 0, launches = 0;
+  const uint8_t* gray = nullptr;  // full-res gray of the batch (the input itself when channels == 1)
+  size_t gray_pitch = 0, gray_fs = 0;
+  bool busy = false;
+};
+
 }  // namespace ctag
 
 using namespace ctag;
 
 struct ctag_detector {
-  int device = 0;
-  cudaStream_t stream = nullptr;
+  int device = 0, sms = 0;
   // dictionary (header/CylinderTag.h:44-45)
   std::vector<int32_t> state;
   int rows = 0, cols = 0, feature_size = 0;
   int32_t* d_state = nullptr;
-
-  // workspace, sized for (cap_frames, w, h, channels)
-  int cap_frames = 0, w = 0, h = 0;
-  FrameGeom geo{};
-  uint8_t* d_stage = nullptr;  // staging for host inputs
-  size_t stage_bytes = 0;
-  uint8_t* d_gray = nullptr;   // [cap_frames][h][gpitch]   (BGR input only)
-  uint8_t* d_bin = nullptr;    // [cap_frames][hh][bpitch]
-  size_t gray_fstride = 0, bin_fstride = 0;
-  // CCL (a4)
-  int *d_labels = nullptr, *d_st_area = nullptr, *d_st_x0 = nullptr, *d_st_y0 = nullptr, *d_st_x1 = nullptr,
-      *d_st_y1 = nullptr, *d_roots_tmp = nullptr, *d_span_count = nullptr, *d_legal = nullptr, *d_counters = nullptr;
-  int legal_cap = 0, spans = 0;
-  // quads (a5)
-  int *d_prefix = nullptr, *d_work_counter = nullptr, *d_quad_status = nullptr, *d_quad_comp = nullptr,
-      *d_n_quads = nullptr;
-  float *d_quad_corners = nullptr, *d_quads = nullptr;
-  uint8_t* d_quad_scratch = nullptr;
-  int edge_warps = 0, exact_ctas = 0, sms = 0, fit_cap = 0, pool_cap = 0;
-  void *d_fits = nullptr, *d_traj = nullptr, *d_fit_results = nullptr;
-  int* d_exact_list = nullptr;
-  uint16_t* d_pick_table = nullptr;  // per detector, independent of the frame geometry
-  static constexpr int kPickTableMax = 1024;
-  int* d_pool = nullptr;
-  float* d_lines = nullptr;
-  static constexpr int kQuadCap = CTAG_MAX_FRAME_QUADS;
-  // features / markers (a6-a10)
-  void *d_geom = nullptr, *d_feats = nullptr;
-  int *d_fstate = nullptr, *d_packed_count = nullptr, *d_summary = nullptr;
-  ctag_marker *d_markers = nullptr, *d_packed = nullptr;
-  int* h_summary = nullptr;         // pinned
-  ctag_marker* h_packed = nullptr;  // pinned
-  static constexpr int kFeatCap = CTAG_MAX_FRAME_FEATURES;
-  static constexpr int kMarkerCap = CTAG_MAX_FRAME_FEATURES / 2;
-  int cur_subpix = 0;
-
-  // state of the batch in flight / last batch
-  int cur_n = 0, cur_channels = 0;
-  const uint8_t* cur_gray = nullptr;  // full-res gray of the batch (input itself when channels == 1)
-  size_t cur_gray_pitch = 0, cur_gray_fstride = 0;
-  int launches = 0;
+  uint16_t* d_pick_table = nullptr;  // cv::fitLine restart subsets per point count (fit_core.cuh)
+  Slot slot[kSlots];
+  int next_enqueue = 0, next_collect = 0, in_flight = 0;
+  int last = -1;  // slot of the most recently collected batch (debug getters, stage times)
   float stage_ms[CTAG_STAGE_COUNT] = {0, 0, 0, 0, 0};
-  cudaEvent_t ev[CTAG_STAGE_COUNT + 1] = {};
-  bool in_flight = false;
+  int last_launches = 0;
 };
 
-static int select_device(int cuda_device, int* chosen) {
+static int select_device(int cuda_device, int* chosen, int* sms) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0) {
@@ -113,113 +114,202 @@ static int select_device(int cuda_device, int* chosen) {
     return CTAG_ERR_NO_DEVICE;
   }
   *chosen = dev;
+  *sms = prop.multiProcessorCount;
   return CTAG_OK;
 }
 
-static void free_workspace(ctag_detector* d) {
+static void free_workspace(Slot* s) {
   // d_stage is managed separately (ensure_stage): it may hold the batch that is about to be processed
-  void* ptrs[] = {d->d_gray, d->d_bin, d->d_labels, d->d_st_area, d->d_st_x0, d->d_st_y0, d->d_st_x1, d->d_st_y1,
-                  d->d_roots_tmp, d->d_span_count, d->d_legal, d->d_counters, d->d_prefix, d->d_work_counter,
-                  d->d_quad_status, d->d_quad_comp, d->d_n_quads, d->d_quad_corners, d->d_quads, d->d_quad_scratch,
-                  d->d_geom, d->d_feats, d->d_fstate, d->d_packed_count, d->d_summary, d->d_markers, d->d_packed,
-                  d->d_fits, d->d_traj, d->d_pool, d->d_lines, d->d_fit_results, d->d_exact_list};
-  for (void* p : ptrs) cudaFree(p);
-  cudaFreeHost(d->h_summary);
-  cudaFreeHost(d->h_packed);
-  d->h_summary = nullptr;
-  d->h_packed = nullptr;
-  d->d_geom = d->d_feats = d->d_fits = d->d_traj = d->d_fit_results = nullptr;
-  d->d_exact_list = nullptr;
-  d->d_pool = nullptr;
-  d->d_lines = nullptr;
-  d->d_fstate = d->d_packed_count = d->d_summary = nullptr;
-  d->d_markers = d->d_packed = nullptr;
-  d->d_gray = d->d_bin = d->d_quad_scratch = nullptr;
-  d->d_labels = d->d_st_area = d->d_st_x0 = d->d_st_y0 = d->d_st_x1 = d->d_st_y1 = d->d_roots_tmp = d->d_span_count =
-      d->d_legal = d->d_counters = d->d_prefix = d->d_work_counter = d->d_quad_status = d->d_quad_comp = d->d_n_quads =
-          nullptr;
-  d->d_quad_corners = d->d_quads = nullptr;
-  d->cap_frames = 0;
+  for (void* p : s->owned) cudaFree(p);
+  s->owned.clear();
+  cudaFreeHost(s->h_summary);
+  cudaFreeHost(s->h_packed);
+  s->h_summary = nullptr;
+  s->h_packed = nullptr;
+  s->cap_frames = 0;
 }
 
 template <typename T>
-static cudaError_t dev_alloc(T** p, size_t count) {
-  return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+static cudaError_t slot_alloc(Slot* s, T** p, size_t count) {
+  void* raw = nullptr;
+  cudaError_t e = cudaMalloc(&raw, count * sizeof(T) > 0 ? count * sizeof(T) : 16);
+  if (e == cudaSuccess) {
+    s->owned.push_back(raw);
+    *p = static_cast<T*>(raw);
+  }
+  return e;
+}
+static cudaError_t slot_alloc_bytes(Slot* s, void** p, size_t bytes) {
+  uint8_t* q = nullptr;
+  cudaError_t e = slot_alloc(s, &q, bytes);
+  *p = q;
+  return e;
 }
 
-static int ensure_workspace(ctag_detector* d, int n, int w, int h) {
-  if (d->cap_frames >= n && d->w == w && d->h == h) return CTAG_OK;
-  int cap = n > d->cap_frames || d->w != w || d->h != h ? n : d->cap_frames;
-  free_workspace(d);
-  d->geo = make_geom(w, h);
-  d->w = w;
-  d->h = h;
-  const FrameGeom& g = d->geo;
-  d->gray_fstride = (size_t)g.gpitch * g.h;
-  d->bin_fstride = (size_t)g.bpitch * g.hh;
-  CTAG_CUDA_CHECK(cudaMalloc(&d->d_gray, d->gray_fstride * cap));
-  CTAG_CUDA_CHECK(cudaMalloc(&d->d_bin, d->bin_fstride * cap));
+static int ensure_workspace(ctag_detector* d, Slot* s, int n, int w, int h) {
+  if (s->cap_frames >= n && s->w == w && s->h == h) return CTAG_OK;
+  const int cap = n;
+  free_workspace(s);
+  s->geo = make_geom(w, h);
+  s->w = w;
+  s->h = h;
+  const FrameGeom& g = s->geo;
+  s->gray_fstride = (size_t)g.gpitch * g.h;
+  s->bin_fstride = (size_t)g.bpitch * g.hh;
   const size_t nb = (size_t)g.nblocks * cap;
-  d->spans = (g.nblocks + 1023) / 1024;
-  d->legal_cap = g.hw * g.hh / kAreaMin + 1;  // every legal component has >= 30 pixels
-  if (d->legal_cap > 65536) d->legal_cap = 65536;
-  CTAG_CUDA_CHECK(dev_alloc(&d->d_labels, nb));
-  CTAG_CUDA_CHECK(dev_alloc(&d->d_st_area, nb));
-  CTAG_CUDA_CHECK(dev_alloc(&d->d_st_x0, nb));
-  CTAG_CUDA_CHECK(dev_alloc(&d->d_st_y0, nb));
-  CTAG_CUDA_CHECK(dev_alloc(&d->d_st_x1, nb));
-  CTAG_CUDA_CHECK(dev_alloc(&d->d_st_y1, nb));
-  CTAG_CUDA_CHECK(dev_alloc(&d->d_roots_tmp, nb));
-  CTAG_CUDA_CHECK(dev_alloc(&d->d_span_count, (size_t)d->spans * cap));
-  CTAG_CUDA_CHECK(dev_alloc(&d->d_legal, (size_t)d->legal_cap * 6 * cap));
-  CTAG_CUDA_CHECK(dev_alloc(&d->d_counters, (size_t)4 * cap));
-  CTAG_CUDA_CHECK(dev_alloc(&d->d_prefix, (size_t)cap + 1));
-  CTAG_CUDA_CHECK(dev_alloc(&d->d_work_counter, 8));
-  CTAG_CUDA_CHECK(dev_alloc(&d->d_quad_status, (size_t)d->legal_cap * cap));
-  CTAG_CUDA_CHECK(dev_alloc(&d->d_quad_corners, (size_t)d->legal_cap * 8 * cap));
-  CTAG_CUDA_CHECK(dev_alloc(&d->d_quads, (size_t)ctag_detector::kQuadCap * 8 * cap));
-  CTAG_CUDA_CHECK(dev_alloc(&d->d_quad_comp, (size_t)ctag_detector::kQuadCap * cap));
-  CTAG_CUDA_CHECK(dev_alloc(&d->d_n_quads, (size_t)cap));
-  CTAG_CUDA_CHECK(cudaMalloc(&d->d_geom, sizeof_quad_geom() * ctag_detector::kQuadCap * cap));
-  CTAG_CUDA_CHECK(cudaMalloc(&d->d_feats, sizeof_feature_rec() * ctag_detector::kFeatCap * cap));
-  CTAG_CUDA_CHECK(dev_alloc(&d->d_fstate, (size_t)4 * cap));
-  CTAG_CUDA_CHECK(dev_alloc(&d->d_packed_count, 4));
-  CTAG_CUDA_CHECK(dev_alloc(&d->d_summary, (size_t)12 * cap));
-  CTAG_CUDA_CHECK(dev_alloc(&d->d_markers, (size_t)ctag_detector::kMarkerCap * cap));
-  CTAG_CUDA_CHECK(dev_alloc(&d->d_packed, (size_t)ctag_detector::kMarkerCap * cap));
-  CTAG_CUDA_CHECK(cudaMallocHost(&d->h_summary, sizeof(int) * 12 * cap));
-  CTAG_CUDA_CHECK(cudaMallocHost(&d->h_packed, sizeof(ctag_marker) * ctag_detector::kMarkerCap * cap));
-  {
-    cudaDeviceProp prop;
-    CTAG_CUDA_CHECK(cudaGetDeviceProperties(&prop, d->device));
-    d->sms = prop.multiProcessorCount;
-    d->edge_warps = quad_edge_warps(d->sms);
-    d->exact_ctas = quad_exact_ctas(d->sms);
-    CTAG_CUDA_CHECK(cudaMalloc(&d->d_quad_scratch, quad_scratch_bytes_per_warp(g) * d->edge_warps));
-    CTAG_CUDA_CHECK(cudaMalloc(&d->d_traj, quad_traj_bytes_per_cta() * d->exact_ctas));
-    // components that reach four edges / their cluster points: the reference caps a frame at 1000 quads
-    // (isVisited[1000]), so 1024 four-edge components per frame is already past its envelope; overflow drops the
-    // component and flags the frame instead of writing out of bounds
-    d->fit_cap = cap * (d->legal_cap < 1024 ? d->legal_cap : 1024);
-    CTAG_CUDA_CHECK(cudaMalloc(&d->d_fit_results, quad_fitresult_bytes() * 80 * (size_t)d->fit_cap));
-    CTAG_CUDA_CHECK(dev_alloc(&d->d_exact_list, (size_t)4 * d->fit_cap));
-    const long long per_frame_pts = (long long)g.hw * g.hh < 262144 ? (long long)g.hw * g.hh : 262144;
-    d->pool_cap = (int)(per_frame_pts * cap < 0x7fffffff ? per_frame_pts * cap : 0x7fffffff);
-    CTAG_CUDA_CHECK(cudaMalloc(&d->d_fits, quad_fitrec_bytes() * d->fit_cap));
-    CTAG_CUDA_CHECK(dev_alloc(&d->d_lines, (size_t)16 * d->fit_cap));
-    CTAG_CUDA_CHECK(dev_alloc(&d->d_pool, (size_t)d->pool_cap));
-  }
-  d->cap_frames = cap;
+  s->spans = (g.nblocks + 1023) / 1024;
+  s->legal_cap = g.hw * g.hh / kAreaMin + 1;  // every legal component has >= 30 pixels
+  if (s->legal_cap > 65536) s->legal_cap = 65536;
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_gray, s->gray_fstride * cap));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_bin, s->bin_fstride * cap));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_labels, nb));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_st_area, nb));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_st_x0, nb));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_st_y0, nb));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_st_x1, nb));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_st_y1, nb));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_roots_tmp, nb));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_span_count, (size_t)s->spans * cap));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_legal, (size_t)s->legal_cap * 6 * cap));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_counters, (size_t)4 * cap));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_prefix, (size_t)cap + 1));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_qctl, 8));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_quad_status, (size_t)s->legal_cap * cap));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_quad_corners, (size_t)s->legal_cap * 8 * cap));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_quads, (size_t)kQuadCap * 8 * cap));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_quad_comp, (size_t)kQuadCap * cap));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_n_quads, (size_t)cap));
+  CTAG_CUDA_CHECK(slot_alloc_bytes(s, &s->d_geom, sizeof_quad_geom() * kQuadCap * cap));
+  CTAG_CUDA_CHECK(slot_alloc_bytes(s, &s->d_feats, sizeof_feature_rec() * kFeatCap * cap));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_fstate, (size_t)4 * cap));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_packed_count, 4));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_summary, (size_t)12 * cap));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_markers, (size_t)kMarkerCap * cap));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_packed, (size_t)kMarkerCap * cap));
+  CTAG_CUDA_CHECK(cudaMallocHost(&s->h_summary, sizeof(int) * 12 * cap));
+  CTAG_CUDA_CHECK(cudaMallocHost(&s->h_packed, sizeof(ctag_marker) * kMarkerCap * cap));
+  s->edge_warps = quad_edge_warps(d->sms);
+  s->exact_ctas = quad_exact_ctas(d->sms);
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_quad_scratch, quad_scratch_bytes_per_warp(g) * s->edge_warps));
+  CTAG_CUDA_CHECK(slot_alloc_bytes(s, &s->d_traj, quad_traj_bytes_per_cta() * s->exact_ctas));
+  // components that reach four edges / their cluster points: the reference caps a frame at 1000 quads
+  // (isVisited[1000]), so 1024 four-edge components per frame is already past its envelope; overflow drops the
+  // component and flags the frame instead of writing out of bounds
+  s->fit_cap = cap * (s->legal_cap < 1024 ? s->legal_cap : 1024);
+  CTAG_CUDA_CHECK(slot_alloc_bytes(s, &s->d_fit_results, quad_fitresult_bytes() * 80 * (size_t)s->fit_cap));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_exact_list, (size_t)4 * s->fit_cap));
+  const long long per_frame_pts = (long long)g.hw * g.hh < 262144 ? (long long)g.hw * g.hh : 262144;
+  s->pool_cap = (int)(per_frame_pts * cap < 0x7fffffff ? per_frame_pts * cap : 0x7fffffff);
+  CTAG_CUDA_CHECK(slot_alloc_bytes(s, &s->d_fits, quad_fitrec_bytes() * s->fit_cap));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_lines, (size_t)16 * s->fit_cap));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_pool, (size_t)s->pool_cap));
+  s->cap_frames = cap;
   return CTAG_OK;
 }
 
-static int ensure_stage(ctag_detector* d, size_t bytes) {
-  if (d->stage_bytes >= bytes) return CTAG_OK;
-  cudaFree(d->d_stage);
-  d->d_stage = nullptr;
-  d->stage_bytes = 0;
-  CTAG_CUDA_CHECK(cudaMalloc(&d->d_stage, bytes));
-  d->stage_bytes = bytes;
+static int ensure_stage(Slot* s, size_t bytes) {
+  if (s->stage_bytes >= bytes) return CTAG_OK;
+  cudaFree(s->d_stage);
+  s->d_stage = nullptr;
+  s->stage_bytes = 0;
+  CTAG_CUDA_CHECK(cudaMalloc(&s->d_stage, bytes));
+  s->stage_bytes = bytes;
+  return CTAG_OK;
+}
+
+// Enqueues the whole detect path for one batch on slot `s` (frames already on the device).
+static int enqueue_on_slot(ctag_detector* d, Slot* s, const void* frames_dev, int n, int w, int h, size_t pitch,
+                           size_t frame_stride, int channels, int corner_subpix, int subpix_dist) {
+  int rc = ensure_workspace(d, s, n, w, h);
+  if (rc != CTAG_OK) return rc;
+  s->n = n;
+  s->channels = channels;
+  s->subpix = corner_subpix;
+  s->launches = 0;
+  if (channels == 1) {
+    s->gray = static_cast<const uint8_t*>(frames_dev);
+    s->gray_pitch = pitch;
+    s->gray_fs = frame_stride;
+  } else {
+    s->gray = s->d_gray;
+    s->gray_pitch = s->geo.gpitch;
+    s->gray_fs = s->gray_fstride;
+  }
+  cudaStream_t st = s->stream;
+  CTAG_CUDA_CHECK(cudaEventRecord(s->ev[0], st));
+  rc = launch_front(frames_dev, n, s->geo, channels, pitch, frame_stride, s->d_gray, s->gray_fstride, s->d_bin,
+                    s->bin_fstride, st);
+  if (rc != CTAG_OK) return rc;
+  s->launches += 1;
+  CTAG_CUDA_CHECK(cudaEventRecord(s->ev[1], st));
+  rc = launch_ccl(s->d_bin, s->bin_fstride, n, s->geo, s->d_labels, s->d_st_area, s->d_st_x0, s->d_st_y0, s->d_st_x1,
+                  s->d_st_y1, s->d_roots_tmp, s->d_span_count, s->d_legal, s->legal_cap, s->d_counters, st, &s->launches);
+  if (rc != CTAG_OK) return rc;
+  CTAG_CUDA_CHECK(cudaEventRecord(s->ev[2], st));
+  rc = launch_quad(n, s->geo, s->d_bin, s->bin_fstride, s->d_labels, s->d_legal, s->legal_cap, s->d_counters, s->d_prefix,
+                   s->d_qctl, s->d_quad_scratch, s->edge_warps, s->d_fits, s->fit_cap, s->d_pool, s->pool_cap,
+                   d->d_pick_table, kPickTableMax, s->d_fit_results, s->d_exact_list, s->d_traj, s->exact_ctas, d->sms,
+                   s->d_lines, s->d_quad_status, s->d_quad_corners, kQuadCap, s->d_quads, s->d_quad_comp, s->d_n_quads, st,
+                   &s->launches);
+  if (rc != CTAG_OK) return rc;
+  CTAG_CUDA_CHECK(cudaEventRecord(s->ev[3], st));
+  rc = launch_features(n, s->geo, s->d_quads, s->d_n_quads, kQuadCap, s->d_geom, s->d_feats, kFeatCap, d->feature_size,
+                       s->d_fstate, s->gray, s->gray_pitch, s->gray_fs, corner_subpix, subpix_dist, st, &s->launches);
+  if (rc != CTAG_OK) return rc;
+  CTAG_CUDA_CHECK(cudaEventRecord(s->ev[4], st));
+  rc = launch_decode(n, s->d_feats, kFeatCap, s->d_fstate, d->d_state, d->rows, d->cols, d->feature_size, s->d_markers,
+                     kMarkerCap, s->d_counters, s->d_n_quads, kQuadCap, s->d_qctl + 4 /* QC_OVERFLOW */, s->d_packed,
+                     s->d_packed_count, s->d_summary, st, &s->launches);
+  if (rc != CTAG_OK) return rc;
+  CTAG_CUDA_CHECK(cudaEventRecord(s->ev[5], st));
+  CTAG_CUDA_CHECK(cudaMemcpyAsync(s->h_summary, s->d_summary, sizeof(int) * 12 * n, cudaMemcpyDeviceToHost, st));
+  s->busy = true;
+  return CTAG_OK;
+}
+
+static int collect_slot(ctag_detector* d, Slot* s, ctag_marker* out, int cap_per_frame, int* n_out, ctag_frame_info* info) {
+  s->busy = false;
+  CTAG_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+  for (int i = 0; i < CTAG_STAGE_COUNT; ++i) cudaEventElapsedTime(&d->stage_ms[i], s->ev[i], s->ev[i + 1]);
+  d->last_launches = s->launches;
+  int total = 0;
+  for (int f = 0; f < s->n; ++f) total += s->h_summary[12 * f + 10];
+  if (total > 0) {
+    CTAG_CUDA_CHECK(cudaMemcpyAsync(s->h_packed, s->d_packed, sizeof(ctag_marker) * total, cudaMemcpyDeviceToHost, s->stream));
+    CTAG_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+  }
+  for (int f = 0; f < s->n; ++f) {
+    const int* sm = s->h_summary + 12 * f;
+    if (n_out) n_out[f] = sm[6];
+    if (info) {
+      memset(&info[f], 0, sizeof(ctag_frame_info));
+      info[f].status = sm[0];
+      info[f].n_labels = sm[1];
+      info[f].n_legal = sm[2];
+      info[f].n_quads = sm[3];
+      info[f].n_features = sm[4];
+      info[f].n_groups = sm[5];
+      info[f].n_markers = sm[6];
+      info[f].flagged = sm[7];
+      info[f].stale_ids = sm[8];
+    }
+    if (out && cap_per_frame > 0) {
+      int ncopy = sm[10] < cap_per_frame ? sm[10] : cap_per_frame;
+      if (ncopy > 0) memcpy(out + (size_t)f * cap_per_frame, s->h_packed + sm[9], sizeof(ctag_marker) * ncopy);
+    }
+  }
+  return CTAG_OK;
+}
+
+static int check_args(ctag_detector* d, const void* frames, int n, int w, int h, int channels, int adaptive_thresh,
+                      int corner_subpix, int subpix_dist) {
+  if (!d || !frames || n <= 0 || w <= 0 || h <= 0) return CTAG_ERR_ARG;
+  if ((w & 1) || (h & 1)) return CTAG_ERR_ARG;  // exact 2x decimation needs even sizes (SURVEY B.1)
+  if (w / 2 > 4095 || h / 2 > 4095) return CTAG_ERR_UNSUPPORTED;  // packed 12-bit coordinates in the trace stack
+  if (channels != 1 && channels != 3) return CTAG_ERR_ARG;
+  if (adaptive_thresh != kWin) return CTAG_ERR_UNSUPPORTED;
+  if (corner_subpix && (subpix_dist < 0 || subpix_dist > 64)) return CTAG_ERR_ARG;
+  if (decode_smem_bytes(d->rows, d->cols) > 200 * 1024) return CTAG_ERR_UNSUPPORTED;
   return CTAG_OK;
 }
 
@@ -230,34 +320,32 @@ int ctag_create(ctag_detector** out, const int32_t* state, int rows, int cols, i
   *out = nullptr;
   for (int i = 0; i < rows * cols; ++i)
     if (!(state[i] >= 0 && state[i] <= 63)) return CTAG_ERR_DICTIONARY;  // check_dictionary, CylinderTag.cpp:56-65
-  int dev = 0;
-  int rc = select_device(cuda_device, &dev);
+  int dev = 0, sms = 0;
+  int rc = select_device(cuda_device, &dev, &sms);
   if (rc != CTAG_OK) return rc;
   CTAG_CUDA_CHECK(cudaSetDevice(dev));
   ctag_detector* d = new ctag_detector();
   d->device = dev;
+  d->sms = sms;
   d->state.assign(state, state + rows * cols);
   d->rows = rows;
   d->cols = cols;
   d->feature_size = feature_size;
-  if (cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaMalloc(&d->d_state, sizeof(int32_t) * rows * cols) != cudaSuccess ||
-      cudaMemcpy(d->d_state, state, sizeof(int32_t) * rows * cols, cudaMemcpyHostToDevice) != cudaSuccess) {
+  // initial subsets of cv::fitLine's 20 restarts for every point count up to kPickTableMax (fit_core.cuh)
+  std::vector<uint16_t> table((size_t)kPickTableMax * 200);
+  quad_build_pick_table(table.data(), kPickTableMax);
+  bool ok = cudaMalloc(&d->d_state, sizeof(int32_t) * rows * cols) == cudaSuccess &&
+            cudaMemcpy(d->d_state, state, sizeof(int32_t) * rows * cols, cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaMalloc(&d->d_pick_table, table.size() * sizeof(uint16_t)) == cudaSuccess &&
+            cudaMemcpy(d->d_pick_table, table.data(), table.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) == cudaSuccess;
+  for (Slot& s : d->slot) {
+    ok = ok && cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto& e : s.ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+  }
+  if (!ok) {
     set_last_error("detector setup", cudaGetLastError(), __FILE__, __LINE__);
     ctag_destroy(d);
     return CTAG_ERR_CUDA;
-  }
-  for (auto& e : d->ev) cudaEventCreate(&e);
-  {
-    // initial subsets of cv::fitLine's 20 restarts for every point count up to kPickTableMax (fit_core.cuh)
-    std::vector<uint16_t> table((size_t)ctag_detector::kPickTableMax * 200);
-    quad_build_pick_table(table.data(), ctag_detector::kPickTableMax);
-    if (cudaMalloc(&d->d_pick_table, table.size() * sizeof(uint16_t)) != cudaSuccess ||
-        cudaMemcpy(d->d_pick_table, table.data(), table.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess) {
-      set_last_error("pick table", cudaGetLastError(), __FILE__, __LINE__);
-      ctag_destroy(d);
-      return CTAG_ERR_CUDA;
-    }
   }
   *out = d;
   return CTAG_OK;
@@ -278,14 +366,16 @@ int ctag_create_from_file(ctag_detector** out, const char* marker_path, int cuda
 void ctag_destroy(ctag_detector* d) {
   if (!d) return;
   cudaSetDevice(d->device);
-  if (d->stream) cudaStreamSynchronize(d->stream);
-  free_workspace(d);
-  cudaFree(d->d_stage);
+  for (Slot& s : d->slot) {
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    free_workspace(&s);
+    cudaFree(s.d_stage);
+    for (auto& e : s.ev)
+      if (e) cudaEventDestroy(e);
+    if (s.stream) cudaStreamDestroy(s.stream);
+  }
   cudaFree(d->d_state);
   cudaFree(d->d_pick_table);
-  for (auto& e : d->ev)
-    if (e) cudaEventDestroy(e);
-  if (d->stream) cudaStreamDestroy(d->stream);
   delete d;
 }
 
@@ -304,126 +394,87 @@ int ctag_get_dictionary(const ctag_detector* d, int* rows, int* cols, int* featu
 int ctag_detect_batch_enqueue(ctag_detector* d, const void* frames_dev, int n, int w, int h, size_t pitch,
                               size_t frame_stride, int channels, int adaptive_thresh, int corner_subpix,
                               int subpix_dist) {
-  if (!d || !frames_dev || n <= 0 || w <= 0 || h <= 0) return CTAG_ERR_ARG;
-  if ((w & 1) || (h & 1)) return CTAG_ERR_ARG;  // exact 2x decimation needs even sizes (SURVEY B.1)
-  if (channels != 1 && channels != 3) return CTAG_ERR_ARG;
-  if (adaptive_thresh != kWin) return CTAG_ERR_UNSUPPORTED;
-  if (d->in_flight) return CTAG_ERR_ARG;
-  if (corner_subpix && (subpix_dist < 0 || subpix_dist > 64)) return CTAG_ERR_ARG;
-  if (decode_smem_bytes(d->rows, d->cols) > 200 * 1024) return CTAG_ERR_UNSUPPORTED;
+  int rc = check_args(d, frames_dev, n, w, h, channels, adaptive_thresh, corner_subpix, subpix_dist);
+  if (rc != CTAG_OK) return rc;
+  if (d->in_flight >= kSlots) return CTAG_ERR_ARG;  // collect first
   CTAG_CUDA_CHECK(cudaSetDevice(d->device));
   if (frame_stride == 0) frame_stride = pitch * (size_t)h;
-  int rc = ensure_workspace(d, n, w, h);
+  Slot* s = &d->slot[d->next_enqueue];
+  rc = enqueue_on_slot(d, s, frames_dev, n, w, h, pitch, frame_stride, channels, corner_subpix, subpix_dist);
   if (rc != CTAG_OK) return rc;
-  d->cur_n = n;
-  d->cur_channels = channels;
-  d->launches = 0;
-  if (channels == 1) {
-    d->cur_gray = static_cast<const uint8_t*>(frames_dev);
-    d->cur_gray_pitch = pitch;
-    d->cur_gray_fstride = frame_stride;
-  } else {
-    d->cur_gray = d->d_gray;
-    d->cur_gray_pitch = d->geo.gpitch;
-    d->cur_gray_fstride = d->gray_fstride;
-  }
-  CTAG_CUDA_CHECK(cudaEventRecord(d->ev[0], d->stream));
-  rc = launch_front(frames_dev, n, d->geo, channels, pitch, frame_stride, d->d_gray, d->gray_fstride, d->d_bin,
-                    d->bin_fstride, d->stream);
-  if (rc != CTAG_OK) return rc;
-  d->launches += 1;
-  CTAG_CUDA_CHECK(cudaEventRecord(d->ev[1], d->stream));
-  rc = launch_ccl(d->d_bin, d->bin_fstride, n, d->geo, d->d_labels, d->d_st_area, d->d_st_x0, d->d_st_y0, d->d_st_x1,
-                  d->d_st_y1, d->d_roots_tmp, d->d_span_count, d->d_legal, d->legal_cap, d->d_counters, d->stream,
-                  &d->launches);
-  if (rc != CTAG_OK) return rc;
-  CTAG_CUDA_CHECK(cudaEventRecord(d->ev[2], d->stream));
-  rc = launch_quad(n, d->geo, d->d_bin, d->bin_fstride, d->d_labels, d->d_legal, d->legal_cap, d->d_counters, d->d_prefix,
-                   d->d_work_counter, d->d_quad_scratch, d->edge_warps, d->d_fits, d->fit_cap, d->d_pool, d->pool_cap,
-                   d->d_pick_table, ctag_detector::kPickTableMax, d->d_fit_results, d->d_exact_list, d->d_traj,
-                   d->exact_ctas, d->sms, d->d_lines, d->d_quad_status, d->d_quad_corners, ctag_detector::kQuadCap,
-                   d->d_quads, d->d_quad_comp, d->d_n_quads, d->stream, &d->launches);
-  if (rc != CTAG_OK) return rc;
-  CTAG_CUDA_CHECK(cudaEventRecord(d->ev[3], d->stream));
-  rc = launch_features(n, d->geo, d->d_quads, d->d_n_quads, ctag_detector::kQuadCap, d->d_geom, d->d_feats,
-                       ctag_detector::kFeatCap, d->feature_size, d->d_fstate, d->cur_gray, d->cur_gray_pitch,
-                       d->cur_gray_fstride, corner_subpix, subpix_dist, d->stream, &d->launches);
-  if (rc != CTAG_OK) return rc;
-  CTAG_CUDA_CHECK(cudaEventRecord(d->ev[4], d->stream));
-  rc = launch_decode(n, d->d_feats, ctag_detector::kFeatCap, d->d_fstate, d->d_state, d->rows, d->cols, d->feature_size,
-                     d->d_markers, ctag_detector::kMarkerCap, d->d_counters, d->d_n_quads, ctag_detector::kQuadCap,
-                     d->d_work_counter + 4 /* QC_OVERFLOW */, d->d_packed, d->d_packed_count, d->d_summary, d->stream, &d->launches);
-  if (rc != CTAG_OK) return rc;
-  CTAG_CUDA_CHECK(cudaEventRecord(d->ev[5], d->stream));
-  CTAG_CUDA_CHECK(cudaMemcpyAsync(d->h_summary, d->d_summary, sizeof(int) * 12 * n, cudaMemcpyDeviceToHost, d->stream));
-  d->cur_subpix = corner_subpix;
-  d->in_flight = true;
+  d->next_enqueue = (d->next_enqueue + 1) % kSlots;
+  d->in_flight += 1;
   return CTAG_OK;
 }
 
 int ctag_detect_batch_collect(ctag_detector* d, ctag_marker* out, int cap_per_frame, int* n_out, ctag_frame_info* info) {
-  if (!d || !d->in_flight) return CTAG_ERR_ARG;
-  (void)out;
-  (void)cap_per_frame;
+  if (!d || d->in_flight <= 0) return CTAG_ERR_ARG;
   CTAG_CUDA_CHECK(cudaSetDevice(d->device));
-  d->in_flight = false;
-  CTAG_CUDA_CHECK(cudaStreamSynchronize(d->stream));
-  for (int sidx = 0; sidx < CTAG_STAGE_COUNT; ++sidx) cudaEventElapsedTime(&d->stage_ms[sidx], d->ev[sidx], d->ev[sidx + 1]);
-  int total = 0;
-  for (int f = 0; f < d->cur_n; ++f) total += d->h_summary[12 * f + 10];
-  if (total > 0) {
-    CTAG_CUDA_CHECK(cudaMemcpyAsync(d->h_packed, d->d_packed, sizeof(ctag_marker) * total, cudaMemcpyDeviceToHost, d->stream));
-    CTAG_CUDA_CHECK(cudaStreamSynchronize(d->stream));
-  }
-  for (int f = 0; f < d->cur_n; ++f) {
-    const int* sm = d->h_summary + 12 * f;
-    if (n_out) n_out[f] = sm[6];
-    if (info) {
-      memset(&info[f], 0, sizeof(ctag_frame_info));
-      info[f].status = sm[0];
-      info[f].n_labels = sm[1];
-      info[f].n_legal = sm[2];
-      info[f].n_quads = sm[3];
-      info[f].n_features = sm[4];
-      info[f].n_groups = sm[5];
-      info[f].n_markers = sm[6];
-      info[f].flagged = sm[7];
-      info[f].stale_ids = sm[8];
-    }
-    if (out && cap_per_frame > 0) {
-      int ncopy = sm[10] < cap_per_frame ? sm[10] : cap_per_frame;
-      if (ncopy > 0) memcpy(out + (size_t)f * cap_per_frame, d->h_packed + sm[9], sizeof(ctag_marker) * ncopy);
-    }
-  }
-  return CTAG_OK;
+  Slot* s = &d->slot[d->next_collect];
+  d->last = d->next_collect;
+  d->next_collect = (d->next_collect + 1) % kSlots;
+  d->in_flight -= 1;
+  return collect_slot(d, s, out, cap_per_frame, n_out, info);
 }
 
 int ctag_detect_batch(ctag_detector* d, const void* frames, int n, int w, int h, size_t pitch, size_t frame_stride,
                       int channels, int is_device, int adaptive_thresh, int corner_subpix, int subpix_dist,
                       ctag_marker* out, int cap_per_frame, int* n_out, ctag_frame_info* info) {
-  if (!d || !frames || n <= 0 || w <= 0 || h <= 0) return CTAG_ERR_ARG;
-  if (channels != 1 && channels != 3) return CTAG_ERR_ARG;
-  const void* src = frames;
-  if (frame_stride == 0) frame_stride = pitch * (size_t)h;
-  if (!is_device) {
-    CTAG_CUDA_CHECK(cudaSetDevice(d->device));
-    // host frames: copy into a 16B-pitched device staging buffer (2-D copy normalises any host pitch)
-    size_t dpitch = (size_t)round_up(w * channels, 16);
-    size_t dfs = dpitch * h;
-    int rc = ensure_stage(d, dfs * n);
-    if (rc != CTAG_OK) return rc;
-    if (pitch < (size_t)w * channels) return CTAG_ERR_ARG;
-    for (int f = 0; f < n; ++f)
-      CTAG_CUDA_CHECK(cudaMemcpy2DAsync(d->d_stage + dfs * f, dpitch, static_cast<const uint8_t*>(frames) + frame_stride * f,
-                                        pitch, (size_t)w * channels, h, cudaMemcpyHostToDevice, d->stream));
-    src = d->d_stage;
-    pitch = dpitch;
-    frame_stride = dfs;
-  }
-  int rc = ctag_detect_batch_enqueue(d, src, n, w, h, pitch, frame_stride, channels, adaptive_thresh, corner_subpix,
-                                     subpix_dist);
+  int rc = check_args(d, frames, n, w, h, channels, adaptive_thresh, corner_subpix, subpix_dist);
   if (rc != CTAG_OK) return rc;
-  return ctag_detect_batch_collect(d, out, cap_per_frame, n_out, info);
+  if (d->in_flight != 0) return CTAG_ERR_ARG;  // the synchronous call does not mix with pending asynchronous batches
+  if (frame_stride == 0) frame_stride = pitch * (size_t)h;
+  if (is_device) {
+    rc = ctag_detect_batch_enqueue(d, frames, n, w, h, pitch, frame_stride, channels, adaptive_thresh, corner_subpix,
+                                   subpix_dist);
+    if (rc != CTAG_OK) return rc;
+    return ctag_detect_batch_collect(d, out, cap_per_frame, n_out, info);
+  }
+  // Host frames: cut the batch into chunks and alternate the two slots, so that the H2D copy of chunk c+1 (its own
+  // stream) overlaps the kernels of chunk c.  The 2-D copy normalises any host pitch to a 16-byte multiple (TMA).
+  CTAG_CUDA_CHECK(cudaSetDevice(d->device));
+  if (pitch < (size_t)w * channels) return CTAG_ERR_ARG;
+  const size_t dpitch = (size_t)round_up(w * channels, 16);
+  const size_t dfs = dpitch * h;
+  const int chunk = n < 8 ? n : (n + 3) / 4;  // small batches stay whole (the debug getters then see all frames)
+  int done = 0, queued = 0;
+  int q_first[kSlots], q_count[kSlots];
+  while (done < n) {
+    while (queued < n && d->in_flight < kSlots) {
+      const int c = n - queued < chunk ? n - queued : chunk;
+      Slot* s = &d->slot[d->next_enqueue];
+      rc = ensure_stage(s, dfs * c);
+      if (rc != CTAG_OK) return rc;
+      // one 2-D copy per frame keeps frame_stride != pitch*h inputs correct
+      for (int f = 0; f < c; ++f)
+        CTAG_CUDA_CHECK(cudaMemcpy2DAsync(s->d_stage + dfs * f, dpitch,
+                                          static_cast<const uint8_t*>(frames) + frame_stride * (queued + f), pitch,
+                                          (size_t)w * channels, h, cudaMemcpyHostToDevice, s->stream));
+      rc = enqueue_on_slot(d, s, s->d_stage, c, w, h, dpitch, dfs, channels, corner_subpix, subpix_dist);
+      if (rc != CTAG_OK) return rc;
+      q_first[d->next_enqueue] = queued;
+      q_count[d->next_enqueue] = c;
+      d->next_enqueue = (d->next_enqueue + 1) % kSlots;
+      d->in_flight += 1;
+      queued += c;
+    }
+    const int si = d->next_collect;
+    Slot* s = &d->slot[si];
+    const int first = q_first[si], c = q_count[si];
+    d->last = si;
+    d->next_collect = (d->next_collect + 1) % kSlots;
+    d->in_flight -= 1;
+    rc = collect_slot(d, s, out ? out + (size_t)first * cap_per_frame : nullptr, cap_per_frame, n_out ? n_out + first : nullptr,
+                      info ? info + first : nullptr);
+    if (rc != CTAG_OK) return rc;
+    if (out)
+      for (int f = 0; f < c; ++f) {
+        const int nm = n_out ? n_out[first + f] : 0;
+        for (int k = 0; k < nm && k < cap_per_frame; ++k) out[(size_t)(first + f) * cap_per_frame + k].frame = first + f;
+      }
+    done += c;
+  }
+  return CTAG_OK;
 }
 
 int ctag_detect(ctag_detector* d, const uint8_t* gray, int w, int h, size_t pitch, int adaptive_thresh, int corner_subpix,
@@ -444,56 +495,68 @@ int ctag_stage_time_ms(const ctag_detector* d, float* ms_out) {
   return CTAG_OK;
 }
 
-int ctag_last_launch_count(const ctag_detector* d) { return d ? d->launches : 0; }
-void* ctag_stream(const ctag_detector* d) { return d ? (void*)d->stream : nullptr; }
+int ctag_last_launch_count(const ctag_detector* d) { return d ? d->last_launches : 0; }
+void* ctag_stream(const ctag_detector* d) { return d ? (void*)d->slot[0].stream : nullptr; }
+
+// The debug getters address the most recently collected batch (for a chunked host call: its last chunk, so tests that
+// use them pass batches of at most two frames or device frames).
+static Slot* last_slot(ctag_detector* d, int frame) {
+  if (!d || d->last < 0) return nullptr;
+  Slot* s = &d->slot[d->last];
+  return (frame >= 0 && frame < s->n) ? s : nullptr;
+}
 
 int ctag_debug_get_gray(ctag_detector* d, int frame, uint8_t* out, size_t out_pitch) {
-  if (!d || !out || frame < 0 || frame >= d->cur_n || !d->cur_gray) return CTAG_ERR_ARG;
+  Slot* s = last_slot(d, frame);
+  if (!s || !out || !s->gray) return CTAG_ERR_ARG;
   CTAG_CUDA_CHECK(cudaSetDevice(d->device));
-  CTAG_CUDA_CHECK(cudaMemcpy2D(out, out_pitch, d->cur_gray + d->cur_gray_fstride * frame, d->cur_gray_pitch, d->w, d->h,
-                               cudaMemcpyDeviceToHost));
+  CTAG_CUDA_CHECK(cudaMemcpy2D(out, out_pitch, s->gray + s->gray_fs * frame, s->gray_pitch, s->w, s->h, cudaMemcpyDeviceToHost));
   return CTAG_OK;
 }
 
 int ctag_debug_get_binary(ctag_detector* d, int frame, uint8_t* out, size_t out_pitch) {
-  if (!d || !out || frame < 0 || frame >= d->cur_n) return CTAG_ERR_ARG;
+  Slot* s = last_slot(d, frame);
+  if (!s || !out) return CTAG_ERR_ARG;
   CTAG_CUDA_CHECK(cudaSetDevice(d->device));
-  CTAG_CUDA_CHECK(cudaMemcpy2D(out, out_pitch, d->d_bin + d->bin_fstride * frame, d->geo.bpitch, d->geo.hw, d->geo.hh,
+  CTAG_CUDA_CHECK(cudaMemcpy2D(out, out_pitch, s->d_bin + s->bin_fstride * frame, s->geo.bpitch, s->geo.hw, s->geo.hh,
                                cudaMemcpyDeviceToHost));
   return CTAG_OK;
 }
 
 int ctag_debug_get_components(ctag_detector* d, int frame, int32_t* out, int cap, int* n_out) {
-  if (!d || !out || !n_out || frame < 0 || frame >= d->cur_n) return CTAG_ERR_ARG;
+  Slot* s = last_slot(d, frame);
+  if (!s || !out || !n_out) return CTAG_ERR_ARG;
   CTAG_CUDA_CHECK(cudaSetDevice(d->device));
   int c[4];
-  CTAG_CUDA_CHECK(cudaMemcpy(c, d->d_counters + 4 * frame, sizeof(c), cudaMemcpyDeviceToHost));
+  CTAG_CUDA_CHECK(cudaMemcpy(c, s->d_counters + 4 * frame, sizeof(c), cudaMemcpyDeviceToHost));
   int n = c[1] < cap ? c[1] : cap;
-  CTAG_CUDA_CHECK(cudaMemcpy(out, d->d_legal + (size_t)frame * d->legal_cap * 6, sizeof(int) * 6 * n, cudaMemcpyDeviceToHost));
+  CTAG_CUDA_CHECK(cudaMemcpy(out, s->d_legal + (size_t)frame * s->legal_cap * 6, sizeof(int) * 6 * n, cudaMemcpyDeviceToHost));
   *n_out = n;
   return CTAG_OK;
 }
+
 int ctag_debug_get_quads(ctag_detector* d, int frame, int32_t* comp_index, float* corners, int cap, int* n_out) {
-  if (!d || !comp_index || !corners || !n_out || frame < 0 || frame >= d->cur_n) return CTAG_ERR_ARG;
+  Slot* s = last_slot(d, frame);
+  if (!s || !comp_index || !corners || !n_out) return CTAG_ERR_ARG;
   CTAG_CUDA_CHECK(cudaSetDevice(d->device));
   int nq = 0;
-  CTAG_CUDA_CHECK(cudaMemcpy(&nq, d->d_n_quads + frame, sizeof(int), cudaMemcpyDeviceToHost));
-  if (nq > ctag_detector::kQuadCap) nq = ctag_detector::kQuadCap;
+  CTAG_CUDA_CHECK(cudaMemcpy(&nq, s->d_n_quads + frame, sizeof(int), cudaMemcpyDeviceToHost));
+  if (nq > kQuadCap) nq = kQuadCap;
   if (nq > cap) nq = cap;
-  CTAG_CUDA_CHECK(cudaMemcpy(comp_index, d->d_quad_comp + (size_t)frame * ctag_detector::kQuadCap, sizeof(int) * nq,
-                             cudaMemcpyDeviceToHost));
-  CTAG_CUDA_CHECK(cudaMemcpy(corners, d->d_quads + (size_t)frame * ctag_detector::kQuadCap * 8, sizeof(float) * 8 * nq,
-                             cudaMemcpyDeviceToHost));
+  CTAG_CUDA_CHECK(cudaMemcpy(comp_index, s->d_quad_comp + (size_t)frame * kQuadCap, sizeof(int) * nq, cudaMemcpyDeviceToHost));
+  CTAG_CUDA_CHECK(cudaMemcpy(corners, s->d_quads + (size_t)frame * kQuadCap * 8, sizeof(float) * 8 * nq, cudaMemcpyDeviceToHost));
   *n_out = nq;
   return CTAG_OK;
 }
+
 int ctag_debug_get_features(ctag_detector* d, int frame, float* corners, float* center, float* angle, int32_t* quad_pair,
                             int cap, int* n_out) {
-  if (!d || !n_out || frame < 0 || frame >= d->cur_n) return CTAG_ERR_ARG;
+  Slot* s = last_slot(d, frame);
+  if (!s || !n_out) return CTAG_ERR_ARG;
   CTAG_CUDA_CHECK(cudaSetDevice(d->device));
   int fs[4];
-  CTAG_CUDA_CHECK(cudaMemcpy(fs, d->d_fstate + 4 * frame, sizeof(fs), cudaMemcpyDeviceToHost));
-  int nf = fs[1] < ctag_detector::kFeatCap ? fs[1] : ctag_detector::kFeatCap;
+  CTAG_CUDA_CHECK(cudaMemcpy(fs, s->d_fstate + 4 * frame, sizeof(fs), cudaMemcpyDeviceToHost));
+  int nf = fs[1] < kFeatCap ? fs[1] : kFeatCap;
   if (nf > cap) nf = cap;
   struct Rec {
     float c[16];
@@ -503,7 +566,7 @@ int ctag_debug_get_features(ctag_detector* d, int frame, float* corners, float* 
   if (sizeof(Rec) != sizeof_feature_rec()) return CTAG_ERR_UNSUPPORTED;
   std::vector<Rec> recs(nf);
   if (nf)
-    CTAG_CUDA_CHECK(cudaMemcpy(recs.data(), static_cast<const uint8_t*>(d->d_feats) + sizeof(Rec) * ctag_detector::kFeatCap * frame,
+    CTAG_CUDA_CHECK(cudaMemcpy(recs.data(), static_cast<const uint8_t*>(s->d_feats) + sizeof(Rec) * kFeatCap * frame,
                                sizeof(Rec) * nf, cudaMemcpyDeviceToHost));
   for (int i = 0; i < nf; ++i) {
     if (corners) memcpy(corners + 16 * i, recs[i].c, sizeof(float) * 16);

@@ -213,6 +213,9 @@ CT_HD int welsch_restart_from_picks(PtFn pt, int count, const int* picked, int n
     // residuals, error, raw weights
     const float px0 = line[2], py0 = line[3], nx = line[1], ny = -line[0];
     double err = 0, sum_w = 0;
+    // unrolled so that the (independent) exp evaluations of neighbouring points overlap; the accumulations keep the
+    // library's order
+#pragma unroll 4
     for (int j = 0; j < count; ++j) {
       int p = pt(j);
       float x = (float)pt_x(p) - px0, y = (float)pt_y(p) - py0;
@@ -226,6 +229,7 @@ CT_HD int welsch_restart_from_picks(PtFn pt, int count, const int* picked, int n
     double x = 0, y = 0, x2 = 0, y2 = 0, xy = 0, wsum = 0;
     const bool norm = fabs(sum_w) > 1.1920928955078125e-07;
     const double inv = norm ? 1. / sum_w : 0.;
+#pragma unroll 4
     for (int j = 0; j < count; ++j) {
       int p = pt(j);
       float fx = (float)pt_x(p), fy = (float)pt_y(p);

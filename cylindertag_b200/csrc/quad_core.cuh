@@ -157,8 +157,14 @@ CT_HD uint32_t row_bits3(const uint32_t* vis, int wpr, int h, int y, int x) {
 
 // 8-neighbour occupancy of (x,y) in the reference's probing order N,NE,E,SE,S,SW,W,NW (corner_detector.h:84-85)
 CT_HD uint32_t nbr_mask(const uint32_t* vis, int wpr, int h, int x, int y) {
-  const uint32_t t0 = row_bits3(vis, wpr, h, y - 1, x), t1 = row_bits3(vis, wpr, h, y, x),
-                 t2 = row_bits3(vis, wpr, h, y + 1, x);
+  uint32_t t0, t1, t2;
+  if (wpr == 1) {  // boxes up to 32 px wide (most quads): one word per row, no straddling
+    const uint32_t r0 = y > 0 ? vis[y - 1] : 0u, r1 = vis[y], r2 = y + 1 < h ? vis[y + 1] : 0u;
+    if (x == 0) t0 = (r0 << 1) & 7u, t1 = (r1 << 1) & 7u, t2 = (r2 << 1) & 7u;
+    else t0 = (r0 >> (x - 1)) & 7u, t1 = (r1 >> (x - 1)) & 7u, t2 = (r2 >> (x - 1)) & 7u;
+  } else {
+    t0 = row_bits3(vis, wpr, h, y - 1, x), t1 = row_bits3(vis, wpr, h, y, x), t2 = row_bits3(vis, wpr, h, y + 1, x);
+  }
   return ((t0 >> 1) & 1u) | (((t0 >> 2) & 1u) << 1) | (((t1 >> 2) & 1u) << 2) | (((t2 >> 2) & 1u) << 3) |
          (((t2 >> 1) & 1u) << 4) | ((t2 & 1u) << 5) | ((t1 & 1u) << 6) | ((t0 & 1u) << 7);
 }

@@ -90,9 +90,12 @@ class Detector:
                                                     channels, int(adaptive_thresh), int(bool(corner_subpix)),
                                                     int(subpix_dist)), "ctag_detect_batch_enqueue")
         self._shape, self._n = (h, w), n
+        self._pending = getattr(self, "_pending", [])
+        self._pending.append(n)
 
     def collect(self, cap_per_frame=16):
-        n = self._n
+        """Results of the oldest enqueued batch (up to two batches may be in flight)."""
+        n = self._pending.pop(0) if getattr(self, "_pending", None) else self._n
         out = np.zeros((n, cap_per_frame), C.MARKER_DTYPE)
         cnt = np.zeros(n, np.int32)
         info = np.zeros(n, C.INFO_DTYPE)
