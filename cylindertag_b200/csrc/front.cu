@@ -38,11 +38,14 @@ struct Layout {
   static constexpr int h = (C == 3) ? 0 : BOX;
   static constexpr int p = (C == 3) ? H_BYTES : BOX + H_BYTES;
   static constexpr int small_ = (C == 3) ? 4 * BOX : BOX + H_BYTES + P_BYTES;
-  static constexpr int tmin = small_;             // CTY*CTX bytes
-  static constexpr int tmax = small_ + 192;       // CTY*CTX bytes
-  static constexpr int vthr = small_ + 384;       // OTY*OTX int16
-  static constexpr int mbar = small_ + 384 + 256; // 8 bytes
-  static constexpr int total = small_ + 384 + 256 + 16;
+  static constexpr int tmin = small_;               // CTY*CTX bytes
+  static constexpr int tmax = small_ + 192;         // CTY*CTX bytes
+  static constexpr int cmn = small_ + 384;          // CTY x 96 column minima
+  static constexpr int cmx = small_ + 384 + 960;    // CTY x 96 column maxima
+  static constexpr int vthr = small_ + 2304;        // OTY*OTX bytes
+  static constexpr int thr16 = small_ + 2304 + 128; // OTY x 5 x 16 threshold bytes (one per owned pixel column)
+  static constexpr int mbar = small_ + 2304 + 128 + 640;
+  static constexpr int total = small_ + 2304 + 128 + 640 + 16;
 };
 }  // namespace front
 
@@ -57,22 +60,34 @@ __device__ __forceinline__ uint32_t dp4a_uu(uint32_t a, uint32_t b, uint32_t c) 
   return d;
 }
 
-// cvtColor(BGR2GRAY): (3735*B + 19235*G + 9798*R + 16384) >> 15, coefficients split into hi/lo bytes for dp4a.
-__device__ __forceinline__ uint32_t gray_of(uint32_t bgrx) {
-  const uint32_t LO = 151u | (35u << 8) | (70u << 16);
-  const uint32_t HI = 14u | (75u << 8) | (38u << 16);
-  uint32_t lo = dp4a_uu(bgrx, LO, 16384u);
-  uint32_t hi = dp4a_uu(bgrx, HI, 0u);
-  return (lo + (hi << 8)) >> 15;
+// dp2a: d = c + a.u16[0] * b.u8[2h] + a.u16[1] * b.u8[2h+1]  (h = 0 for .lo, 1 for .hi)
+__device__ __forceinline__ uint32_t dp2a_lo_uu(uint32_t a16, uint32_t b8, uint32_t c) {
+  uint32_t d;
+  asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a16), "r"(b8), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t dp2a_hi_uu(uint32_t a16, uint32_t b8, uint32_t c) {
+  uint32_t d;
+  asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a16), "r"(b8), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int dp2a_lo_ss(uint32_t a16, uint32_t b8, int c) {
+  int d;
+  asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a16), "r"(b8), "r"(c));
+  return d;
 }
 
+// cvtColor(BGR2GRAY): (3735*B + 19235*G + 9798*R + 16384) >> 15.  With the coefficients doubled the result is byte 2
+// of (7470*B + 38470*G + 19596*R + 32768) < 2^24, and 16-bit coefficients fit dp2a: two IDP per pixel, no byte
+// extraction (the four pixels of a 12-byte group sit at byte offsets 0,3,6,9; each lands on one .lo and one .hi).
 __device__ __forceinline__ uint32_t gray4(uint32_t w0, uint32_t w1, uint32_t w2) {
-  uint32_t p0 = w0;
-  uint32_t p1 = __byte_perm(w0, w1, 0x0543);
-  uint32_t p2 = __byte_perm(w1, w2, 0x0432);
-  uint32_t p3 = w2 >> 8;
-  uint32_t g0 = gray_of(p0), g1 = gray_of(p1), g2 = gray_of(p2), g3 = gray_of(p3);
-  return g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+  const uint32_t cB = 7470u, cG = 38470u, cR = 19596u;
+  const uint32_t BG = cB | (cG << 16), R0 = cR, ZB = cB << 16, GR = cG | (cR << 16);
+  uint32_t g0 = dp2a_hi_uu(R0, w0, dp2a_lo_uu(BG, w0, 32768u));  // B,G,R = w0.b0 w0.b1 w0.b2
+  uint32_t g1 = dp2a_lo_uu(GR, w1, dp2a_hi_uu(ZB, w0, 32768u));  // w0.b3 w1.b0 w1.b1
+  uint32_t g2 = dp2a_lo_uu(R0, w2, dp2a_hi_uu(BG, w1, 32768u));  // w1.b2 w1.b3 w2.b0
+  uint32_t g3 = dp2a_hi_uu(GR, w2, dp2a_lo_uu(ZB, w2, 32768u));  // w2.b1 w2.b2 w2.b3
+  return __byte_perm(__byte_perm(g0, g1, 0x0062), __byte_perm(g2, g3, 0x0062), 0x5410);
 }
 
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
@@ -161,67 +176,99 @@ __global__ void __launch_bounds__(front::NT) front_kernel(const __grid_constant_
     }
   }
 
-  // ---- phase B: horizontal taps (-3,19,19,-3): H[row][j] from region columns 2j+5..2j+8 ---------------------
-  int16_t* H = reinterpret_cast<int16_t*>(smem + L::h);
+  // ---- phase B: horizontal taps (-3,19,19,-3) on two rows at a time: HT[rp][j] = (h[2rp][j], h[2rp+1][j]) as an
+  //      int16 pair, the layout the vertical dp2a wants.  h[row][j] uses region columns 2j+5..2j+8. -----------------
+  uint32_t* HT = reinterpret_cast<uint32_t*>(smem + L::h);
   {
     const uint32_t COEF = 0xFD1313FDu;  // (-3, 19, 19, -3) as signed bytes
-    for (int item = tid; item < RH * 23; item += NT) {
-      int row = item / 23, k = item - row * 23;
-      const uint8_t* src = g + row * RW + 8 * k;
-      uint32_t w1 = *reinterpret_cast<const uint32_t*>(src + 4);
-      uint2 w23 = *reinterpret_cast<const uint2*>(src + 8);
-      int h0 = dp4a_us(__byte_perm(w1, w23.x, 0x4321), COEF, 0);
-      int h1 = dp4a_us(__byte_perm(w1, w23.x, 0x6543), COEF, 0);
-      int h2 = dp4a_us(__byte_perm(w23.x, w23.y, 0x4321), COEF, 0);
-      int h3 = dp4a_us(__byte_perm(w23.x, w23.y, 0x6543), COEF, 0);
-      uint2 o;
-      o.x = (uint32_t)(h0 & 0xFFFF) | ((uint32_t)h1 << 16);
-      o.y = (uint32_t)(h2 & 0xFFFF) | ((uint32_t)h3 << 16);
-      *reinterpret_cast<uint2*>(H + row * HP + 4 * k) = o;
+    for (int item = tid; item < (RH / 2) * 23; item += NT) {
+      const int rp = item / 23, k = item - rp * 23;
+      const uint8_t* src = g + (2 * rp) * RW + 8 * k;
+      const uint32_t a1 = *reinterpret_cast<const uint32_t*>(src + 4);
+      const uint2 a23 = *reinterpret_cast<const uint2*>(src + 8);
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(src + RW + 4);
+      const uint2 b23 = *reinterpret_cast<const uint2*>(src + RW + 8);
+      const int h0 = dp4a_us(__byte_perm(a1, a23.x, 0x4321), COEF, 0), g0 = dp4a_us(__byte_perm(b1, b23.x, 0x4321), COEF, 0);
+      const int h1 = dp4a_us(__byte_perm(a1, a23.x, 0x6543), COEF, 0), g1 = dp4a_us(__byte_perm(b1, b23.x, 0x6543), COEF, 0);
+      const int h2 = dp4a_us(__byte_perm(a23.x, a23.y, 0x4321), COEF, 0), g2 = dp4a_us(__byte_perm(b23.x, b23.y, 0x4321), COEF, 0);
+      const int h3 = dp4a_us(__byte_perm(a23.x, a23.y, 0x6543), COEF, 0), g3 = dp4a_us(__byte_perm(b23.x, b23.y, 0x6543), COEF, 0);
+      uint4 o;
+      o.x = __byte_perm((uint32_t)h0, (uint32_t)g0, 0x5410);
+      o.y = __byte_perm((uint32_t)h1, (uint32_t)g1, 0x5410);
+      o.z = __byte_perm((uint32_t)h2, (uint32_t)g2, 0x5410);
+      o.w = __byte_perm((uint32_t)h3, (uint32_t)g3, 0x5410);
+      *reinterpret_cast<uint4*>(HT + rp * HP + 4 * k) = o;
     }
   }
   __syncthreads();
 
-  // ---- phase C: vertical taps + round-half-even + saturate: P[i][j] from H rows 2i..2i+3 --------------------
+  // ---- phase C: vertical taps + round-half-even + saturate: P[i][j] from row pairs i and i+1 ------------------------
   uint8_t* P = smem + L::p;
-  for (int item = tid; item < 50 * 45; item += NT) {
-    int i = item / 45, jp = item - i * 45;
-    const int16_t* hp = H + (2 * i) * HP + 2 * jp;
-    uint32_t r0 = *reinterpret_cast<const uint32_t*>(hp);
-    uint32_t r1 = *reinterpret_cast<const uint32_t*>(hp + HP);
-    uint32_t r2 = *reinterpret_cast<const uint32_t*>(hp + 2 * HP);
-    uint32_t r3 = *reinterpret_cast<const uint32_t*>(hp + 3 * HP);
-    int va = 19 * ((int)(int16_t)r1 + (int)(int16_t)r2) - 3 * ((int)(int16_t)r0 + (int)(int16_t)r3);
-    int vb = 19 * (((int)r1 >> 16) + ((int)r2 >> 16)) - 3 * (((int)r0 >> 16) + ((int)r3 >> 16));
-    va = (va + 511 + ((va >> 10) & 1)) >> 10;
-    vb = (vb + 511 + ((vb >> 10) & 1)) >> 10;
-    va = min(max(va, 0), 255);
-    vb = min(max(vb, 0), 255);
-    P[i * PP + POFF + 2 * jp] = (uint8_t)va;  // POFF is odd: two byte stores
-    P[i * PP + POFF + 2 * jp + 1] = (uint8_t)vb;
+  {
+    const uint32_t C01 = 0x000013FDu;  // (-3, 19) on bytes 0,1
+    const uint32_t C23 = 0x0000FD13u;  // (19, -3)
+    for (int item = tid; item < 50 * 23; item += NT) {
+      const int i = item / 23, k = item - i * 23;
+      const uint4 a = *reinterpret_cast<const uint4*>(HT + i * HP + 4 * k);
+      const uint4 b = *reinterpret_cast<const uint4*>(HT + (i + 1) * HP + 4 * k);
+      int v0 = dp2a_lo_ss(b.x, C23, dp2a_lo_ss(a.x, C01, 0));
+      int v1 = dp2a_lo_ss(b.y, C23, dp2a_lo_ss(a.y, C01, 0));
+      int v2 = dp2a_lo_ss(b.z, C23, dp2a_lo_ss(a.z, C01, 0));
+      int v3 = dp2a_lo_ss(b.w, C23, dp2a_lo_ss(a.w, C01, 0));
+      // v / 1024 rounded half to even (what cv::resize's float path does), then saturate_cast<uchar>
+      v0 = (v0 + 511 + ((v0 >> 10) & 1)) >> 10;
+      v1 = (v1 + 511 + ((v1 >> 10) & 1)) >> 10;
+      v2 = (v2 + 511 + ((v2 >> 10) & 1)) >> 10;
+      v3 = (v3 + 511 + ((v3 >> 10) & 1)) >> 10;
+      uint8_t* dst = P + i * PP + POFF + 4 * k;  // POFF is odd: byte stores
+      dst[0] = (uint8_t)min(max(v0, 0), 255);
+      dst[1] = (uint8_t)min(max(v1, 0), 255);
+      dst[2] = (uint8_t)min(max(v2, 0), 255);
+      dst[3] = (uint8_t)min(max(v3, 0), 255);
+    }
   }
   __syncthreads();
 
-  // ---- phase D: 5x5 tile min/max over valid pixels (corner_detector.cpp:42-53) ------------------------------
+  // ---- phase D: 5x5 tile min/max over valid pixels (corner_detector.cpp:42-53): column extrema, then 5 columns -------
   uint8_t* tmin = smem + L::tmin;
   uint8_t* tmax = smem + L::tmax;
-  if (tid < CTX * CTY) {
-    int ti = tid / CTX, tj = tid - ti * CTX;
+  uint8_t* cmn = smem + L::cmn;
+  uint8_t* cmx = smem + L::cmx;
+  const bool edge_cta = (cx == 0) || (cy == 0) || (OW * cx + OW + 5 > geo.hw) || (OH * cy + OH + 5 > geo.hh);
+  for (int item = tid; item < CTY * 90; item += NT) {
+    const int ti = item / 90, j = item - ti * 90;
+    const uint8_t* col = P + (5 * ti) * PP + POFF + j;
     int mn = 255, mx = 0;
+    if (!edge_cta) {
 #pragma unroll
-    for (int dy = 0; dy < 5; ++dy) {
-      int i = 5 * ti + dy;
-      int yh = OH * cy - 5 + i;
+      for (int dy = 0; dy < 5; ++dy) {
+        const int v = col[dy * PP];
+        mn = min(mn, v);
+        mx = max(mx, v);
+      }
+    } else {
+      const int xh = OW * cx - 5 + j;
 #pragma unroll
-      for (int dx = 0; dx < 5; ++dx) {
-        int j = 5 * tj + dx;
-        int xh = OW * cx - 5 + j;
+      for (int dy = 0; dy < 5; ++dy) {
+        const int yh = OH * cy - 5 + 5 * ti + dy;
         if (yh >= 0 && yh < geo.hh && xh >= 0 && xh < geo.hw) {
-          int v = P[i * PP + POFF + j];
+          const int v = col[dy * PP];
           mn = min(mn, v);
           mx = max(mx, v);
         }
       }
+    }
+    cmn[ti * 96 + j] = (uint8_t)mn;
+    cmx[ti * 96 + j] = (uint8_t)mx;
+  }
+  __syncthreads();
+  if (tid < CTX * CTY) {
+    const int ti = tid / CTX, tj = tid - ti * CTX;
+    int mn = 255, mx = 0;
+#pragma unroll
+    for (int dx = 0; dx < 5; ++dx) {
+      mn = min(mn, (int)cmn[ti * 96 + 5 * tj + dx]);
+      mx = max(mx, (int)cmx[ti * 96 + 5 * tj + dx]);
     }
     tmin[tid] = (uint8_t)mn;
     tmax[tid] = (uint8_t)mx;
@@ -229,7 +276,7 @@ __global__ void __launch_bounds__(front::NT) front_kernel(const __grid_constant_
   __syncthreads();
 
   // ---- phase E: 3x3 tile dilation -> integer threshold per owned tile (corner_detector.cpp:54-78) -----------
-  int16_t* vthr = reinterpret_cast<int16_t*>(smem + L::vthr);
+  uint8_t* vthr = smem + L::vthr;
   if (tid < OTX * OTY) {
     int oi = tid / OTX, oj = tid - oi * OTX;
     int ty = OTY * cy + oi, tx = OTX * cx + oj;
@@ -244,13 +291,20 @@ __global__ void __launch_bounds__(front::NT) front_kernel(const __grid_constant_
           mx = max(mx, (int)tmax[(oi + dy) * CTX + oj + dx]);
         }
       // dst = 255 iff src < min(0.3f, (max+min)/2) in float; src = lut255(v) is strictly increasing in v,
-      // so find the smallest v with lut255(v) >= thr and compare integers per pixel.
+      // so find the smallest v with lut255(v) >= thr and compare integers per pixel (t <= 77 because thr <= 0.3).
       float thr = fminf(0.3f, __fmul_rn(__fadd_rn(lut255(mx), lut255(mn)), 0.5f));
       t = min(max((int)(thr * 255.0f), 0), 255);
       while (t > 0 && !(lut255(t - 1) < thr)) --t;
       while (t < 256 && lut255(t) < thr) ++t;
     }
-    vthr[tid] = (int16_t)t;
+    vthr[tid] = (uint8_t)t;
+  }
+  __syncthreads();
+  // one threshold byte per owned pixel column, per tile row: lets phase F compare 4 pixels per instruction group
+  uint8_t* thr16 = smem + L::thr16;
+  for (int item = tid; item < OTY * OW; item += NT) {
+    const int oi = item / OW, jo = item - oi * OW;
+    thr16[item] = vthr[oi * OTX + jo / 5];
   }
   __syncthreads();
 
@@ -258,25 +312,26 @@ __global__ void __launch_bounds__(front::NT) front_kernel(const __grid_constant_
   {
     uint8_t* bin_f = bin_out + (size_t)fr * bin_fstride;
     for (int item = tid; item < OH * 5; item += NT) {
-      int i = item / 5, q = item - i * 5;
-      int yh = OH * cy + i, xh0 = OW * cx + 16 * q;
+      const int i = item / 5, q = item - i * 5;
+      const int yh = OH * cy + i, xh0 = OW * cx + 16 * q;
       if (yh >= geo.hh || xh0 >= geo.bpitch) continue;
-      uint4 v = *reinterpret_cast<const uint4*>(P + (i + 5) * PP + 16 + 16 * q);
-      uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      const uint4 v = *reinterpret_cast<const uint4*>(P + (i + 5) * PP + 16 + 16 * q);
+      const uint4 t = *reinterpret_cast<const uint4*>(thr16 + (i / 5) * OW + 16 * q);
+      const uint32_t vw[4] = {v.x, v.y, v.z, v.w}, tw[4] = {t.x, t.y, t.z, t.w};
       uint32_t o[4];
-      const int16_t* trow = vthr + (i / 5) * OTX;
 #pragma unroll
       for (int ww = 0; ww < 4; ++ww) {
-        uint32_t acc = 0;
+        // per-byte v < t for t <= 127: ((v | 0x80) - t) keeps bit 7 iff (v & 0x7f) >= t; v >= 128 is never below t
+        const uint32_t d = (vw[ww] | 0x80808080u) - tw[ww];
+        const uint32_t lt = ~(d | vw[ww]) & 0x80808080u;
+        o[ww] = (lt >> 7) * 255u;
+      }
+      if (xh0 + 16 > geo.hw) {  // right image edge inside this group: columns >= hw stay background
 #pragma unroll
-        for (int bb = 0; bb < 4; ++bb) {
-          int k = 4 * ww + bb;
-          int jo = 16 * q + k;
-          int val = (w[ww] >> (8 * bb)) & 255;
-          bool fg = (val < (int)trow[jo / 5]) && (xh0 + k < geo.hw);
-          acc |= (fg ? 255u : 0u) << (8 * bb);
-        }
-        o[ww] = acc;
+        for (int ww = 0; ww < 4; ++ww)
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb)
+            if (xh0 + 4 * ww + bb >= geo.hw) o[ww] &= ~(255u << (8 * bb));
       }
       *reinterpret_cast<uint4*>(bin_f + (size_t)yh * geo.bpitch + xh0) = make_uint4(o[0], o[1], o[2], o[3]);
     }
