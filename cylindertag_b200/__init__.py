@@ -7,6 +7,7 @@ needs the built library and a B200.
 from . import _capi
 from ._capi import CtagError
 from .detector import Detector
+from .api import CamInfo, CylinderTag, MarkerInfo, ModelInfo, PoseInfo
 
-__all__ = ["Detector", "CtagError", "_capi"]
+__all__ = ["CylinderTag", "Detector", "MarkerInfo", "ModelInfo", "CamInfo", "PoseInfo", "CtagError", "_capi"]
 __version__ = "0.1"

@@ -1,0 +1,212 @@
+"""Python mirror of the reference's `CylinderTag` class (header/CylinderTag.h:12-52) for the detect path.
+
+Same method names and argument meaning as the reference: construct from a `.marker` file or a state matrix, `detect`,
+`loadModel`, `loadCamera`, `estimatePose`, `drawAxis`.  `detect` runs entirely in the CUDA library (C ABI, include/ctag.h);
+`estimatePose` stays on the host as in the reference (CylinderTag.cpp:198-209, pose_estimation.cpp:50-143): OpenCV
+EPnP for the start, then a Levenberg-Marquardt refinement of the pinhole reprojection error on undistorted points
+(the reference uses Ceres; scipy's LM minimises the same 2-residual cost).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _capi as C
+from .detector import Detector
+
+
+@dataclass
+class MarkerInfo:  # header/corner_detector.h:16-22
+    markerID: int = -1
+    featurePos: list = field(default_factory=list)
+    feature_ID: list = field(default_factory=list)
+    feature_ID_left: list = field(default_factory=list)
+    feature_ID_right: list = field(default_factory=list)
+    cornerLists: list = field(default_factory=list)  # each [8][2] float32, full-res pixel coordinates
+    feature_center: list = field(default_factory=list)
+    edge_length: list = field(default_factory=list)
+    cr_left: list = field(default_factory=list)
+    cr_right: list = field(default_factory=list)
+
+
+@dataclass
+class CamInfo:  # header/pose_estimation.h:12-14
+    Intrinsic: np.ndarray = None
+    distCoeffs: np.ndarray = None
+
+
+@dataclass
+class ModelInfo:  # header/pose_estimation.h:16-20
+    MarkerID: int = -1
+    axis: np.ndarray = None
+    base: np.ndarray = None
+    corners: np.ndarray = None  # [8 * model_size, 3]
+
+
+@dataclass
+class PoseInfo:  # header/pose_estimation.h:22-25
+    markerID: int = -1  # INDEX into the model list, not the dictionary row (pose_estimation.cpp:59,69)
+    rvec: np.ndarray = None
+    tvec: np.ndarray = None
+
+
+def marker_from_record(rec) -> MarkerInfo:
+    n = int(rec["n_features"])
+    m = MarkerInfo(markerID=int(rec["marker_id"]))
+    m.feature_ID = [int(v) for v in rec["feature_id"][:n]]
+    m.feature_ID_left = [int(v) for v in rec["id_left"][:n]]
+    m.feature_ID_right = [int(v) for v in rec["id_right"][:n]]
+    m.featurePos = [int(v) for v in rec["feature_pos"][:n] if v >= 0]
+    m.cornerLists = [rec["corners"][k].copy() for k in range(n)]
+    m.feature_center = [tuple(rec["center"][k]) for k in range(n)]
+    m.edge_length = [float(v) for v in rec["edge_length"][:n]]
+    m.cr_left = [float(v) for v in rec["cr_left"][:n]]
+    m.cr_right = [float(v) for v in rec["cr_right"][:n]]
+    return m
+
+
+class CylinderTag:
+    def __init__(self, path_or_state, feature_size=None, device=-1):
+        """CylinderTag(path) loads a .marker file (CylinderTag.cpp:16-41); CylinderTag(state, feature_size) takes the
+        state matrix (CylinderTag.cpp:43-54; feature_size must be given, the reference leaves it unset, SURVEY C-3).
+        Errors surface as the reference's messages (it throws std::string)."""
+        try:
+            if isinstance(path_or_state, (str, bytes)) or hasattr(path_or_state, "__fspath__"):
+                self._det = Detector(marker_path=path_or_state, device=device)
+            else:
+                self._det = Detector(state=path_or_state, feature_size=feature_size, device=device)
+        except C.CtagError as e:
+            if e.code == C.ERR_FILE:
+                raise RuntimeError("load_from_file, could not open the file\n") from e
+            if e.code == C.ERR_DICTIONARY:
+                raise RuntimeError("check_dictionary, the number in state matrix must between 0 to 63\n") from e
+            raise
+
+    @property
+    def detector(self) -> Detector:
+        return self._det
+
+    # ---- Marker Detector (CylinderTag.cpp:67-128) ----
+    def detect(self, img, cornerList=None, adaptiveThresh=5, cornerSubPix=False, cornerSubPixDist=3):
+        """Returns the marker list; if `cornerList` (a list) is given it is assigned in place like the reference's
+        output argument: replaced on success, left untouched on the two early exits (which print the reference's
+        messages and return None)."""
+        img = np.asarray(img)
+        if img.ndim != 2 or img.dtype != np.uint8:
+            raise ValueError("detect expects an 8-bit single-channel image")
+        recs, status = self._det.detect(img, adaptiveThresh, cornerSubPix, cornerSubPixDist, cap=64)
+        if status == C.FRAME_NO_CORNER:
+            print("No corner detected!")
+            return None
+        if status == C.FRAME_NO_FEATURE:
+            print("No feature detected!")
+            return None
+        markers = [marker_from_record(r) for r in recs]
+        if cornerList is not None:
+            cornerList[:] = markers
+        return markers
+
+    # ---- loaders ----
+    def loadModel(self, path) -> list:
+        """CylinderTag.cpp:161-190."""
+        try:
+            toks = open(path).read().split()
+        except OSError as e:
+            raise RuntimeError("loadModel, could not open the model file\n") from e
+        it = iter(toks)
+        n, size = int(next(it)), int(next(it))
+        out = []
+        for _ in range(n):
+            m = ModelInfo(MarkerID=int(next(it)))
+            m.base = np.array([float(next(it)) for _ in range(3)], np.float32)
+            m.axis = np.array([float(next(it)) for _ in range(3)], np.float32)
+            m.corners = np.zeros((8 * size, 3), np.float32)
+            for _ in range(8 * size):
+                cid = int(next(it))
+                m.corners[cid] = [float(next(it)) for _ in range(3)]
+            out.append(m)
+        return out
+
+    def loadCamera(self, path) -> CamInfo:
+        """CylinderTag.cpp:192-196 (cv::FileStorage: cameraMatrix, distCoeffs, both dt: f)."""
+        import cv2
+        fs = cv2.FileStorage(str(path), cv2.FILE_STORAGE_READ)
+        cam = CamInfo(fs.getNode("cameraMatrix").mat(), fs.getNode("distCoeffs").mat())
+        fs.release()
+        return cam
+
+    # ---- Marker Localization (CylinderTag.cpp:198-209, pose_estimation.cpp:50-143) ----
+    def estimatePose(self, img, markers, reconstruct_model, camera, useDensePoseRefine=False) -> list:
+        poses = []
+        for mk in markers:
+            p = pnp_solver(mk, reconstruct_model, camera)
+            if p.markerID != -1:  # poses with markerID == -1 are erased (CylinderTag.cpp:206-208)
+                poses.append(p)
+        return poses
+
+    def drawAxis(self, img, markers, reconstruct_model, poses, camera, axisLength=5):
+        """CylinderTag.cpp:211-246 without the imshow window: returns the BGR overlay image."""
+        import cv2
+        out = cv2.cvtColor(np.asarray(img), cv2.COLOR_GRAY2BGR)
+        for i, pose in enumerate(poses):
+            if i >= len(markers):
+                break
+            model = reconstruct_model[pose.markerID]
+            pts3 = [model.corners[markers[i].featurePos[j] * 8 + k] for j in range(len(markers[i].cornerLists)) for k in range(8)]
+            base = model.base.astype(np.float64)
+            pts3 += [base, base + model.axis * axisLength, base + np.array([0.0372, 0.0372, 0.9986]) * axisLength,
+                     base + np.array([0.9980, -0.0520, -0.0353]) * axisLength]
+            ip, _ = cv2.projectPoints(np.array(pts3, np.float64), pose.rvec, pose.tvec, camera.Intrinsic.astype(np.float64),
+                                      camera.distCoeffs.astype(np.float64))
+            ip = ip.reshape(-1, 2)
+            for p in ip[:-5]:
+                cv2.circle(out, (int(p[0]), int(p[1])), 5, (255, 234, 32), -1)
+            o = (int(ip[-4][0]), int(ip[-4][1]))
+            for k, col in ((-3, (255, 0, 0)), (-2, (0, 255, 0)), (-1, (0, 0, 255))):
+                cv2.arrowedLine(out, o, (int(ip[k][0]), int(ip[k][1])), col, 10, cv2.LINE_AA, 0, 0.2)
+            cv2.circle(out, o, 8, (247, 235, 235), -1)
+        return out
+
+
+def select_pose_points(mk: MarkerInfo, model: ModelInfo):
+    """pose_estimation.cpp:72-95: which corners of which features enter the PnP problem."""
+    img_pts, obj_pts = [], []
+    n = len(mk.cornerLists)
+    for j in range(n):
+        bad = abs(mk.feature_ID_left[j] - mk.feature_ID_right[j]) > 1 or mk.feature_ID_right[j] == -1
+        if n > 3 and (j == 0 or j == len(mk.feature_ID_left) - 1) and bad:
+            continue
+        ks = [0, 1, 4, 5]
+        if abs(mk.feature_ID_left[j] - mk.feature_ID_right[j]) < 3 and mk.feature_ID_right[j] != -1:
+            ks += [2, 3, 6, 7]
+        for k in ks:
+            img_pts.append(mk.cornerLists[j][k])
+            obj_pts.append(model.corners[mk.featurePos[j] * 8 + k])
+    return np.array(img_pts, np.float32).reshape(-1, 2), np.array(obj_pts, np.float32).reshape(-1, 3)
+
+
+def pnp_solver(mk: MarkerInfo, models, camera: CamInfo) -> PoseInfo:
+    """PoseEstimator::PnPSolver + PoseBA (pose_estimation.cpp:50-128)."""
+    import cv2
+    from scipy.optimize import least_squares
+    idx = next((j for j, m in enumerate(models) if m.MarkerID == mk.markerID), -1)
+    if idx < 0:
+        return PoseInfo(-1)
+    img_pts, obj_pts = select_pose_points(mk, models[idx])
+    K = camera.Intrinsic.astype(np.float64)
+    D = camera.distCoeffs.astype(np.float64)
+    ok, rvec, tvec = cv2.solvePnP(obj_pts.astype(np.float64), img_pts.astype(np.float64), K, D, flags=cv2.SOLVEPNP_EPNP)
+    und = cv2.undistortPoints(img_pts.reshape(-1, 1, 2).astype(np.float64), K, D, P=K).reshape(-1, 2)
+    fx, fy, cx, cy = float(np.float32(K[0, 0])), float(np.float32(K[1, 1])), float(np.float32(K[0, 2])), float(np.float32(K[1, 2]))
+    X = obj_pts.astype(np.float64)
+
+    def resid(p):
+        R, _ = cv2.Rodrigues(p[:3])
+        Pc = X @ R.T + p[3:]
+        u = fx * Pc[:, 0] / Pc[:, 2] + cx
+        v = fy * Pc[:, 1] / Pc[:, 2] + cy
+        return np.concatenate([u - und[:, 0], v - und[:, 1]])
+
+    sol = least_squares(resid, np.concatenate([rvec.reshape(3), tvec.reshape(3)]), method="lm", xtol=1e-12, ftol=1e-15, gtol=1e-15)
+    return PoseInfo(idx, sol.x[:3].copy(), sol.x[3:].copy())

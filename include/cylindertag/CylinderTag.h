@@ -1,0 +1,208 @@
+// CylinderTag.h -- C++ host-side mirror of the reference's public class (header/CylinderTag.h:12-52) over the
+// B200 C ABI (include/ctag.h).  Header only; link against libctag_b200.so.
+//
+// It keeps the reference's method names, argument meaning and error behaviour for the detection path:
+//   CylinderTag(path) / CylinderTag(state)   CylinderTag.cpp:6-65   (throws std::string on file / dictionary errors)
+//   detect(img, markers, adaptiveThresh, cornerSubPix, cornerSubPixDist)   CylinderTag.cpp:67-128
+//       (assigns `markers` on success, leaves it untouched on the "No corner detected!" / "No feature detected!"
+//        early exits and prints the same messages)
+//   loadModel(path, models)                   CylinderTag.cpp:161-190
+//   loadCamera(path, camera)                  CylinderTag.cpp:192-196 (OpenCV YAML 1.0, cameraMatrix + distCoeffs)
+// The build image has no OpenCV C++ headers, so minimal stand-in types are defined here; define CTAG_WITH_OPENCV
+// before including to get cv::Mat / cv::Point2f based overloads instead.
+// estimatePose / drawAxis are host-side and outside the CUDA hot path; the Python mirror
+// (cylindertag_b200.CylinderTag) implements estimatePose, this header declares the data types they exchange.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../ctag.h"
+
+#ifdef CTAG_WITH_OPENCV
+#include <opencv2/core.hpp>
+#endif
+
+namespace ctag_api {
+
+#ifdef CTAG_WITH_OPENCV
+using Point2f = cv::Point2f;
+using Point3f = cv::Point3f;
+#else
+struct Point2f {
+  float x = 0, y = 0;
+};
+struct Point3f {
+  float x = 0, y = 0, z = 0;
+};
+#endif
+
+// 8-bit image view (what detect() needs from a cv::Mat): data, rows, cols, step, channels
+struct ImageView {
+  const uint8_t* data = nullptr;
+  int rows = 0, cols = 0;
+  size_t step = 0;
+  int channels = 1;
+};
+
+// row-major int matrix standing in for cv::Mat1i
+struct Mat1i {
+  int rows = 0, cols = 0;
+  std::vector<int32_t> data;
+};
+
+// header/corner_detector.h:16-22
+struct MarkerInfo {
+  int markerID = -1;
+  std::vector<int> featurePos, feature_ID, feature_ID_left, feature_ID_right;
+  std::vector<std::vector<Point2f>> cornerLists;
+  std::vector<Point2f> feature_center;
+  std::vector<float> edge_length, cr_left, cr_right;
+};
+
+// header/pose_estimation.h:12-25
+struct CamInfo {
+  float Intrinsic[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // row-major 3x3, dt: f
+  std::vector<float> distCoeffs;                      // 5x1, dt: f
+};
+struct ModelInfo {
+  int MarkerID = -1;
+  Point3f axis, base;
+  std::vector<Point3f> corners;
+};
+struct PoseInfo {
+  int markerID = -1;
+  double rvec[3] = {0, 0, 0}, tvec[3] = {0, 0, 0};
+};
+
+class CylinderTag {
+ public:
+  // Load state matrix of CylinderTag from file (CylinderTag.cpp:6-9,16-41)
+  explicit CylinderTag(const std::string& path, int cuda_device = -1) {
+    int rc = ctag_create_from_file(&det_, path.c_str(), cuda_device);
+    if (rc == CTAG_ERR_FILE) throw std::string("load_from_file, could not open the file\n");
+    if (rc == CTAG_ERR_DICTIONARY)
+      throw std::string("check_dictionary, the number in state matrix must between 0 to 63\nload_from_file, illegal marker info\n");
+    if (rc != CTAG_OK) throw std::string("CylinderTag, ") + ctag_strerror(rc) + ": " + ctag_last_error() + "\n";
+  }
+  // Manual input of the state matrix (CylinderTag.cpp:11-14,43-54).  The reference leaves featureSize unset here
+  // (SURVEY C-3); it has to be given.
+  CylinderTag(const Mat1i& set_state, int feature_size, int cuda_device = -1) {
+    int rc = ctag_create(&det_, set_state.data.data(), set_state.rows, set_state.cols, feature_size, cuda_device);
+    if (rc == CTAG_ERR_DICTIONARY)
+      throw std::string("check_dictionary, the number in state matrix must between 0 to 63\nload_from_set, illegal marker info\n");
+    if (rc != CTAG_OK) throw std::string("CylinderTag, ") + ctag_strerror(rc) + ": " + ctag_last_error() + "\n";
+  }
+  ~CylinderTag() { ctag_destroy(det_); }
+  CylinderTag(const CylinderTag&) = delete;
+  CylinderTag& operator=(const CylinderTag&) = delete;
+
+  // Marker Detector (CylinderTag.cpp:67-128). `img` is 8-bit single channel.
+  void detect(const ImageView& img, std::vector<MarkerInfo>& cornerList, int adaptiveThresh = 5, const bool cornerSubPix = false,
+              int cornerSubPixDist = 3) {
+    std::vector<ctag_marker> buf(kCap);
+    int n = 0, status = 0;
+    int rc = ctag_detect(det_, img.data, img.cols, img.rows, img.step, adaptiveThresh, cornerSubPix ? 1 : 0, cornerSubPixDist,
+                         buf.data(), kCap, &n, &status);
+    if (rc != CTAG_OK) throw std::string("detect, ") + ctag_strerror(rc) + ": " + ctag_last_error() + "\n";
+    if (status == CTAG_FRAME_NO_CORNER) {
+      std::cout << "No corner detected!" << std::endl;  // CylinderTag.cpp:88; output untouched
+      return;
+    }
+    if (status == CTAG_FRAME_NO_FEATURE) {
+      std::cout << "No feature detected!" << std::endl;  // CylinderTag.cpp:94; output untouched
+      return;
+    }
+    std::vector<MarkerInfo> out;
+    for (int m = 0; m < n && m < kCap; ++m) out.push_back(convert(buf[m]));
+    cornerList = out;  // markers_info = markers (CylinderTag.cpp:128)
+  }
+
+#ifdef CTAG_WITH_OPENCV
+  void detect(const cv::Mat& img, std::vector<MarkerInfo>& cornerList, int adaptiveThresh = 5, const bool cornerSubPix = false,
+              int cornerSubPixDist = 3) {
+    detect(ImageView{img.data, img.rows, img.cols, img.step, img.channels()}, cornerList, adaptiveThresh, cornerSubPix,
+           cornerSubPixDist);
+  }
+#endif
+
+  // Load reconstructed model (CylinderTag.cpp:161-190)
+  void loadModel(const std::string& path, std::vector<ModelInfo>& reconstruct_model) {
+    std::ifstream in(path);
+    if (!in.is_open()) throw std::string("loadModel, could not open the model file\n");
+    int model_num = 0, model_size = 0;
+    in >> model_num >> model_size;
+    reconstruct_model.assign(model_num, ModelInfo());
+    for (int i = 0; i < model_num; ++i) {
+      ModelInfo& m = reconstruct_model[i];
+      in >> m.MarkerID >> m.base.x >> m.base.y >> m.base.z >> m.axis.x >> m.axis.y >> m.axis.z;
+      m.corners.assign((size_t)model_size * 8, Point3f());
+      for (int j = 0; j < 8 * model_size; ++j) {
+        int id = 0;
+        Point3f p;
+        in >> id >> p.x >> p.y >> p.z;
+        if (id >= 0 && id < 8 * model_size) m.corners[id] = p;
+      }
+    }
+  }
+
+  // Load camera intrinsic (CylinderTag.cpp:192-196): OpenCV YAML 1.0 with cameraMatrix (3x3) and distCoeffs (5x1)
+  void loadCamera(const std::string& path, CamInfo& camera) {
+    std::ifstream in(path);
+    std::stringstream ss;
+    ss << in.rdbuf();
+    const std::string txt = ss.str();
+    std::vector<float> k = yaml_matrix(txt, "cameraMatrix"), dcf = yaml_matrix(txt, "distCoeffs");
+    for (size_t i = 0; i < 9 && i < k.size(); ++i) camera.Intrinsic[i] = k[i];
+    camera.distCoeffs = dcf;
+  }
+
+  ctag_detector* handle() { return det_; }
+
+ private:
+  static constexpr int kCap = 64;
+  ctag_detector* det_ = nullptr;
+
+  static MarkerInfo convert(const ctag_marker& c) {
+    MarkerInfo m;
+    m.markerID = c.marker_id;
+    for (int k = 0; k < c.n_features; ++k) {
+      m.feature_ID.push_back(c.feature_id[k]);
+      m.feature_ID_left.push_back(c.id_left[k]);
+      m.feature_ID_right.push_back(c.id_right[k]);
+      std::vector<Point2f> cl(8);
+      for (int q = 0; q < 8; ++q) cl[q].x = c.corners[k][q][0], cl[q].y = c.corners[k][q][1];
+      m.cornerLists.push_back(cl);
+      Point2f ce;
+      ce.x = c.center[k][0], ce.y = c.center[k][1];
+      m.feature_center.push_back(ce);
+      m.edge_length.push_back(c.edge_length[k]);
+      m.cr_left.push_back(c.cr_left[k]);
+      m.cr_right.push_back(c.cr_right[k]);
+    }
+    for (int k = 0; k < CTAG_MAX_FEATURES && c.feature_pos[k] >= 0 && (int)m.featurePos.size() < c.n_features; ++k)
+      m.featurePos.push_back(c.feature_pos[k]);
+    return m;
+  }
+
+  static std::vector<float> yaml_matrix(const std::string& txt, const std::string& key) {
+    std::vector<float> out;
+    size_t p = txt.find(key);
+    if (p == std::string::npos) return out;
+    size_t a = txt.find('[', p), b = txt.find(']', a);
+    if (a == std::string::npos || b == std::string::npos) return out;
+    std::string body = txt.substr(a + 1, b - a - 1);
+    for (char& ch : body)
+      if (ch == ',' || ch == '\n') ch = ' ';
+    std::stringstream ss(body);
+    double v;
+    while (ss >> v) out.push_back((float)v);  // dt: f
+    return out;
+  }
+};
+
+}  // namespace ctag_api

@@ -1,0 +1,24 @@
+"""The C++ mirror class (include/cylindertag/CylinderTag.h) compiles against the C ABI and keeps the reference's
+error convention (throw std::string).  Without a GPU the constructor reports the missing device loudly."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cxx_header_compiles_links_and_reports_errors(tmp_path):
+    from cylindertag_b200 import _capi
+    _capi.load()
+    exe = tmp_path / "cxx_test"
+    libdir = os.path.join(ROOT, "cylindertag_b200", "lib")
+    subprocess.run(["g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cxx", "test_cxx_header.cpp"),
+                    "-o", str(exe), "-L", libdir, "-lctag_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    data = os.path.join(ROOT, "tests", "golden", "data")
+    out = subprocess.run([str(exe), os.path.join(data, "CTag_2f12c.marker"), os.path.join(data, "CTag_2f12c.model"),
+                          os.path.join(data, "cameraParams.yml")], capture_output=True, text=True, check=True).stdout
+    assert "missing: load_from_file, could not open the file" in out
+    import torch
+    if torch.cuda.is_available():
+        assert "created=1 models=6" in out and "fx=4328.5" in out and "ndist=5" in out
+    else:
+        assert "no usable sm_100 CUDA device" in out and "created=0" in out
