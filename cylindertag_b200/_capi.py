@@ -67,6 +67,7 @@ SIGNATURES = {
     "ctag_detect_batch": (_I, [_P, _P, _I, _I, _I, _SZ, _SZ, _I, _I, _I, _I, _I, _P, _I, _P, _P]),
     "ctag_detect_batch_enqueue": (_I, [_P, _P, _I, _I, _I, _SZ, _SZ, _I, _I, _I, _I]),
     "ctag_detect_batch_collect": (_I, [_P, _P, _I, _P, _P]),
+    "ctag_max_in_flight": (_I, []),
     "ctag_stage_time_ms": (_I, [_P, ctypes.POINTER(ctypes.c_float)]),
     "ctag_last_launch_count": (_I, [_P]),
     "ctag_stream": (_P, [_P]),

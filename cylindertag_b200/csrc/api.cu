@@ -1,8 +1,9 @@
 // C ABI (include/ctag.h) over the sm_100a detection kernels: detector handle, workspaces, batch pipeline.
 //
-// A detector owns kSlots independent workspaces ("slots"), each with its own CUDA stream, so that two batches can be
-// in flight: the latency-bound sparse kernels of batch i overlap the bandwidth-bound dense kernels of batch i+1
-// (ctag_detect_batch_enqueue may be called twice before ctag_detect_batch_collect; results come back in FIFO order).
+// A detector owns kSlots independent workspaces ("slots"), each with its own CUDA stream, so that several batches can
+// be in flight: the latency-bound sparse kernels of batch i overlap the bandwidth-bound dense kernels of batch i+1
+// (ctag_detect_batch_enqueue may be called up to ctag_max_in_flight() times before ctag_detect_batch_collect; results
+// come back in FIFO order).
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -42,7 +43,7 @@ static FrameGeom make_geom(int w, int h) {
   return g;
 }
 
-constexpr int kSlots = 2;
+constexpr int kSlots = 4;
 constexpr int kQuadCap = CTAG_MAX_FRAME_QUADS;
 constexpr int kFeatCap = CTAG_MAX_FRAME_FEATURES;
 constexpr int kMarkerCap = CTAG_MAX_FRAME_FEATURES / 2;
@@ -496,6 +497,7 @@ int ctag_stage_time_ms(const ctag_detector* d, float* ms_out) {
 }
 
 int ctag_last_launch_count(const ctag_detector* d) { return d ? d->last_launches : 0; }
+int ctag_max_in_flight(void) { return kSlots; }
 void* ctag_stream(const ctag_detector* d) { return d ? (void*)d->slot[0].stream : nullptr; }
 
 // The debug getters address the most recently collected batch (for a chunked host call: its last chunk, so tests that

@@ -111,6 +111,9 @@ class Detector:
     def launch_count(self):
         return int(self._lib.ctag_last_launch_count(self._h))
 
+    def max_in_flight(self):
+        return int(self._lib.ctag_max_in_flight())
+
     def stream(self):
         return self._lib.ctag_stream(self._h)
 

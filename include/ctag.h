@@ -125,11 +125,14 @@ CTAG_API int ctag_detect_batch(ctag_detector* det, const void* frames, int n, in
                       int channels, int is_device, int adaptive_thresh, int corner_subpix, int subpix_dist,
                       ctag_marker* out, int cap_per_frame, int* n_out, ctag_frame_info* info);
 
-/* Asynchronous pair for device-resident throughput runs: enqueue the whole detect path for a batch on the detector's
- * stream, then collect.  Between the two calls the host is free (e.g. to upload the next batch). */
+/* Asynchronous pair for device-resident throughput runs: enqueue the whole detect path for a batch, then collect.
+ * Up to ctag_max_in_flight() batches may be enqueued before the first collect (each has its own workspace and CUDA
+ * stream, so the latency-bound sparse kernels of one batch overlap the dense kernels of the next); collect returns
+ * them in FIFO order.  Between the calls the host is free (e.g. to upload the next batch). */
 CTAG_API int ctag_detect_batch_enqueue(ctag_detector* det, const void* frames_dev, int n, int w, int h, size_t pitch,
                               size_t frame_stride, int channels, int adaptive_thresh, int corner_subpix, int subpix_dist);
 CTAG_API int ctag_detect_batch_collect(ctag_detector* det, ctag_marker* out, int cap_per_frame, int* n_out, ctag_frame_info* info);
+CTAG_API int ctag_max_in_flight(void);
 
 /* ---- instrumentation ------------------------------------------------------------------------ */
 
