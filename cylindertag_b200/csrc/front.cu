@@ -5,10 +5,14 @@
 //   a2  u8 -> f32 * 1/255           CylinderTag.cpp:80      (never materialised: applied to tile extrema only)
 //   a3  adaptiveThreshold           corner_detector.cpp:28-79 (5x5 tile min/max, 3x3 tile dilation, threshold)
 //
-// One CTA produces a 80x40 half-resolution patch (16x8 threshold tiles).  It needs the 18x10 surrounding tiles,
-// i.e. a 90x50 half-res patch, i.e. a 192x102 full-res region which is staged in shared memory by TMA
-// (cp.async.bulk.tensor.3d, zero fill outside the image; replicate borders are patched afterwards).
-// The half-res gray image, the float image and the tile extrema never touch HBM.
+// One tile = a 80x40 half-resolution patch (16x8 threshold tiles).  It needs the 18x10 surrounding tiles, i.e. a 90x50
+// half-res patch, i.e. a 192x102 full-res region which TMA stages in shared memory (cp.async.bulk.tensor.3d, zero fill
+// outside the image; replicate borders are patched afterwards).  The half-res gray image, the float image and the
+// tile extrema never touch HBM.
+//
+// Persistent CTAs (as many as fit per SM) walk the tile list with a stride; the TMA load of a CTA's NEXT tile is issued
+// as soon as the staging buffer of the current one is free (after the gray conversion for BGR input, at the top of the
+// iteration for gray input, which double-buffers), so the load latency hides behind the stencil phases.
 //
 // HBM traffic per frame (N = w*h): BGR input 3N read + N gray write + N/4 binary write; gray input N + N/4.
 #include "common.cuh"
@@ -17,34 +21,34 @@
 namespace ctag {
 
 namespace front {
-constexpr int OW = 80, OH = 40;      // owned half-res pixels per CTA
-constexpr int OTX = 16, OTY = 8;     // owned tiles
-constexpr int CTX = 18, CTY = 10;    // computed tiles (owned + 1 ring)
-constexpr int RW = 192, RH = 102;    // full-res region (pixels) staged per CTA
-constexpr int HP = 92;               // pitch of the horizontal-pass buffer (int16 elements)
+constexpr int OW = 80, OH = 40;      // owned half-res pixels per tile
+constexpr int OTX = 16, OTY = 8;     // owned threshold tiles
+constexpr int CTX = 18, CTY = 10;    // computed threshold tiles (owned + 1 ring)
+constexpr int RW = 192, RH = 102;    // full-res region (pixels) staged per tile
+constexpr int HP = 92;               // pitch of the horizontal-pass buffer (row-pair words)
 constexpr int PP = 112;              // pitch of the half-res patch (bytes)
 constexpr int POFF = 11;             // column shift of the half-res patch so that owned pixels start 16B aligned
 constexpr int NT = 256;
 constexpr int BOX = RW * RH;         // bytes of one TMA box
-constexpr int H_BYTES = ((RH * HP * 2 + 127) / 128) * 128;
+constexpr int H_BYTES = (((RH / 2) * HP * 4 + 127) / 128) * 128;
 constexpr int P_BYTES = ((50 * PP + 127) / 128) * 128;
 
 template <int C>
 struct Layout {
-  // C==3: [bgr 3 boxes | g | small]; H and P alias the bgr boxes once the gray conversion is done.
-  // C==1: [g | H | P | small]
+  // C==3: [bgr 3 boxes | g | HT | P | small]        (bgr is free for the next tile's TMA once g is built)
+  // C==1: [g0 | g1 | HT | P | small]                (gray tiles double-buffered)
   static constexpr int bgr = 0;
-  static constexpr int g = (C == 3) ? 3 * BOX : 0;
-  static constexpr int h = (C == 3) ? 0 : BOX;
-  static constexpr int p = (C == 3) ? H_BYTES : BOX + H_BYTES;
-  static constexpr int small_ = (C == 3) ? 4 * BOX : BOX + H_BYTES + P_BYTES;
+  static constexpr int g = (C == 3) ? 3 * BOX : 0;   // C==1: g0 at 0, g1 at BOX
+  static constexpr int h = (C == 3) ? 4 * BOX : 2 * BOX;
+  static constexpr int p = h + H_BYTES;
+  static constexpr int small_ = p + P_BYTES;
   static constexpr int tmin = small_;               // CTY*CTX bytes
   static constexpr int tmax = small_ + 192;         // CTY*CTX bytes
   static constexpr int cmn = small_ + 384;          // CTY x 96 column minima
   static constexpr int cmx = small_ + 384 + 960;    // CTY x 96 column maxima
   static constexpr int vthr = small_ + 2304;        // OTY*OTX bytes
-  static constexpr int thr16 = small_ + 2304 + 128; // OTY x 5 x 16 threshold bytes (one per owned pixel column)
-  static constexpr int mbar = small_ + 2304 + 128 + 640;
+  static constexpr int thr16 = small_ + 2304 + 128; // OTY x OW threshold bytes (one per owned pixel column)
+  static constexpr int mbar = small_ + 2304 + 128 + 640;  // 2 x 8 bytes
   static constexpr int total = small_ + 2304 + 128 + 640 + 16;
 };
 }  // namespace front
@@ -54,12 +58,6 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {
   asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
 }
-__device__ __forceinline__ uint32_t dp4a_uu(uint32_t a, uint32_t b, uint32_t c) {
-  uint32_t d;
-  asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-  return d;
-}
-
 // dp2a: d = c + a.u16[0] * b.u8[2h] + a.u16[1] * b.u8[2h+1]  (h = 0 for .lo, 1 for .hi)
 __device__ __forceinline__ uint32_t dp2a_lo_uu(uint32_t a16, uint32_t b8, uint32_t c) {
   uint32_t d;
@@ -104,237 +102,286 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
 // float image value of a u8 sample: Mat::convertTo(CV_32F, 1.0/255) = float(v) * float(1.0/255)  
 __device__ __forceinline__ float lut255(int v) { return __fmul_rn((float)v, (float)(1.0 / 255)); }
 
+struct TileGrid {
+  int tiles_x, tiles_y, tiles_per_frame, ntiles;
+};
+
 template <int C>
-__global__ void __launch_bounds__(front::NT) front_kernel(const __grid_constant__ CUtensorMap tmap, FrameGeom geo,
+__device__ __forceinline__ void issue_tile_load(const CUtensorMap* tmap, uint32_t mbar, uint32_t dst, const TileGrid& tg,
+                                                int tile) {
+  using namespace front;
+  const int fr = tile / tg.tiles_per_frame, rem = tile - fr * tg.tiles_per_frame;
+  const int cy = rem / tg.tiles_x, cx = rem - cy * tg.tiles_x;
+  const int x0r = 2 * OW * cx - 16, y0r = 2 * OH * cy - 11;
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(C * BOX) : "memory");
+#pragma unroll
+  for (int b = 0; b < C; ++b) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        :
+        : "r"(dst + b * BOX), "l"(tmap), "r"(mbar), "r"(C * x0r + RW * b), "r"(y0r), "r"(fr)
+        : "memory");
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(front::NT) front_kernel(const __grid_constant__ CUtensorMap tmap, FrameGeom geo, TileGrid tg,
                                                           uint8_t* __restrict__ gray_out, size_t gray_fstride,
                                                           uint8_t* __restrict__ bin_out, size_t bin_fstride) {
   using namespace front;
   using L = Layout<C>;
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
-  const int cx = blockIdx.x, cy = blockIdx.y, fr = blockIdx.z;
-  const int x0r = 2 * OW * cx - 16;  // full-res x of region column 0
-  const int y0r = 2 * OH * cy - 11;  // full-res y of region row 0
-  uint8_t* g = smem + L::g;
-  const uint32_t mbar = smem_u32(smem + L::mbar);
-
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncthreads();
-  if (tid == 0) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(C * BOX) : "memory");
-#pragma unroll
-    for (int b = 0; b < C; ++b) {
-      uint32_t dst = smem_u32(smem + (C == 3 ? L::bgr + b * BOX : L::g));
-      asm volatile(
-          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-          :
-          : "r"(dst), "l"(&tmap), "r"(mbar), "r"(C * x0r + RW * b), "r"(y0r), "r"(fr)
-          : "memory");
-    }
-  }
-  mbar_wait(mbar, 0);
-
-  // ---- phase A: BGR -> gray (whole region) + store of the owned gray pixels --------------------------------
-  if (C == 3) {
-    uint8_t* gray_f = gray_out + (size_t)fr * gray_fstride;
-    for (int item = tid; item < RH * 12; item += NT) {
-      int row = item / 12, gq = item - row * 12;
-      const uint4* src = reinterpret_cast<const uint4*>(smem + L::bgr + (gq >> 2) * BOX + row * RW + (gq & 3) * 48);
-      uint4 a = src[0], b = src[1], c = src[2];
-      uint4 o;
-      o.x = gray4(a.x, a.y, a.z);
-      o.y = gray4(a.w, b.x, b.y);
-      o.z = gray4(b.z, b.w, c.x);
-      o.w = gray4(c.y, c.z, c.w);
-      *reinterpret_cast<uint4*>(g + row * RW + gq * 16) = o;
-      int y = y0r + row, x = x0r + gq * 16;
-      if (row >= 11 && row < 11 + 2 * OH && gq >= 1 && gq <= 10 && y < geo.h && x < geo.w)
-        *reinterpret_cast<uint4*>(gray_f + (size_t)y * geo.gpitch + x) = o;
-    }
-    __syncthreads();
-  }
-
-  // ---- replicate-border patch (TMA zero-fills outside the image; INTER_CUBIC uses BORDER_REPLICATE) ---------
-  {
-    const int rW = geo.w - x0r, rH = geo.h - y0r;
-    const bool left = (cx == 0), right = (rW < RW), top = (cy == 0), bottom = (rH < RH);
-    if (left | right | top | bottom) {
-      if (left)
-        for (int r = tid; r < RH; r += NT) g[r * RW + 15] = g[r * RW + 16];
-      if (right)
-        for (int r = tid; r < RH; r += NT) g[r * RW + rW] = g[r * RW + rW - 1];
-      __syncthreads();
-      if (top)
-        for (int c = tid; c < RW; c += NT) g[10 * RW + c] = g[11 * RW + c];
-      if (bottom)
-        for (int c = tid; c < RW; c += NT) g[rH * RW + c] = g[(rH - 1) * RW + c];
-      __syncthreads();
-    }
-  }
-
-  // ---- phase B: horizontal taps (-3,19,19,-3) on two rows at a time: HT[rp][j] = (h[2rp][j], h[2rp+1][j]) as an
-  //      int16 pair, the layout the vertical dp2a wants.  h[row][j] uses region columns 2j+5..2j+8. -----------------
+  const uint32_t mbar0 = smem_u32(smem + L::mbar);
   uint32_t* HT = reinterpret_cast<uint32_t*>(smem + L::h);
-  {
-    const uint32_t COEF = 0xFD1313FDu;  // (-3, 19, 19, -3) as signed bytes
-    for (int item = tid; item < (RH / 2) * 23; item += NT) {
-      const int rp = item / 23, k = item - rp * 23;
-      const uint8_t* src = g + (2 * rp) * RW + 8 * k;
-      const uint32_t a1 = *reinterpret_cast<const uint32_t*>(src + 4);
-      const uint2 a23 = *reinterpret_cast<const uint2*>(src + 8);
-      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(src + RW + 4);
-      const uint2 b23 = *reinterpret_cast<const uint2*>(src + RW + 8);
-      const int h0 = dp4a_us(__byte_perm(a1, a23.x, 0x4321), COEF, 0), g0 = dp4a_us(__byte_perm(b1, b23.x, 0x4321), COEF, 0);
-      const int h1 = dp4a_us(__byte_perm(a1, a23.x, 0x6543), COEF, 0), g1 = dp4a_us(__byte_perm(b1, b23.x, 0x6543), COEF, 0);
-      const int h2 = dp4a_us(__byte_perm(a23.x, a23.y, 0x4321), COEF, 0), g2 = dp4a_us(__byte_perm(b23.x, b23.y, 0x4321), COEF, 0);
-      const int h3 = dp4a_us(__byte_perm(a23.x, a23.y, 0x6543), COEF, 0), g3 = dp4a_us(__byte_perm(b23.x, b23.y, 0x6543), COEF, 0);
-      uint4 o;
-      o.x = __byte_perm((uint32_t)h0, (uint32_t)g0, 0x5410);
-      o.y = __byte_perm((uint32_t)h1, (uint32_t)g1, 0x5410);
-      o.z = __byte_perm((uint32_t)h2, (uint32_t)g2, 0x5410);
-      o.w = __byte_perm((uint32_t)h3, (uint32_t)g3, 0x5410);
-      *reinterpret_cast<uint4*>(HT + rp * HP + 4 * k) = o;
-    }
-  }
-  __syncthreads();
-
-  // ---- phase C: vertical taps + round-half-even + saturate: P[i][j] from row pairs i and i+1 ------------------------
   uint8_t* P = smem + L::p;
-  {
-    const uint32_t C01 = 0x000013FDu;  // (-3, 19) on bytes 0,1
-    const uint32_t C23 = 0x0000FD13u;  // (19, -3)
-    for (int item = tid; item < 50 * 23; item += NT) {
-      const int i = item / 23, k = item - i * 23;
-      const uint4 a = *reinterpret_cast<const uint4*>(HT + i * HP + 4 * k);
-      const uint4 b = *reinterpret_cast<const uint4*>(HT + (i + 1) * HP + 4 * k);
-      int v0 = dp2a_lo_ss(b.x, C23, dp2a_lo_ss(a.x, C01, 0));
-      int v1 = dp2a_lo_ss(b.y, C23, dp2a_lo_ss(a.y, C01, 0));
-      int v2 = dp2a_lo_ss(b.z, C23, dp2a_lo_ss(a.z, C01, 0));
-      int v3 = dp2a_lo_ss(b.w, C23, dp2a_lo_ss(a.w, C01, 0));
-      // v / 1024 rounded half to even (what cv::resize's float path does), then saturate_cast<uchar>
-      v0 = (v0 + 511 + ((v0 >> 10) & 1)) >> 10;
-      v1 = (v1 + 511 + ((v1 >> 10) & 1)) >> 10;
-      v2 = (v2 + 511 + ((v2 >> 10) & 1)) >> 10;
-      v3 = (v3 + 511 + ((v3 >> 10) & 1)) >> 10;
-      uint8_t* dst = P + i * PP + POFF + 4 * k;  // POFF is odd: byte stores
-      dst[0] = (uint8_t)min(max(v0, 0), 255);
-      dst[1] = (uint8_t)min(max(v1, 0), 255);
-      dst[2] = (uint8_t)min(max(v2, 0), 255);
-      dst[3] = (uint8_t)min(max(v3, 0), 255);
-    }
-  }
-  __syncthreads();
-
-  // ---- phase D: 5x5 tile min/max over valid pixels (corner_detector.cpp:42-53): column extrema, then 5 columns -------
   uint8_t* tmin = smem + L::tmin;
   uint8_t* tmax = smem + L::tmax;
   uint8_t* cmn = smem + L::cmn;
   uint8_t* cmx = smem + L::cmx;
-  const bool edge_cta = (cx == 0) || (cy == 0) || (OW * cx + OW + 5 > geo.hw) || (OH * cy + OH + 5 > geo.hh);
-  for (int item = tid; item < CTY * 90; item += NT) {
-    const int ti = item / 90, j = item - ti * 90;
-    const uint8_t* col = P + (5 * ti) * PP + POFF + j;
-    int mn = 255, mx = 0;
-    if (!edge_cta) {
-#pragma unroll
-      for (int dy = 0; dy < 5; ++dy) {
-        const int v = col[dy * PP];
-        mn = min(mn, v);
-        mx = max(mx, v);
+  uint8_t* vthr = smem + L::vthr;
+  uint8_t* thr16 = smem + L::thr16;
+
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar0));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar0 + 8));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  int tile = blockIdx.x;
+  if (tid == 0 && tile < tg.ntiles) issue_tile_load<C>(&tmap, mbar0, smem_u32(smem + (C == 3 ? L::bgr : L::g)), tg, tile);
+
+  // C==3: one staging buffer + one barrier, parity flips per tile.  C==1: buffers/barriers alternate, parity flips
+  // every second tile.
+  for (int it = 0; tile < tg.ntiles; tile += gridDim.x, ++it) {
+    const int fr = tile / tg.tiles_per_frame, rem = tile - fr * tg.tiles_per_frame;
+    const int cy = rem / tg.tiles_x, cx = rem - cy * tg.tiles_x;
+    const int x0r = 2 * OW * cx - 16;  // full-res x of region column 0
+    const int y0r = 2 * OH * cy - 11;  // full-res y of region row 0
+    const int buf = (C == 1) ? (it & 1) : 0;
+    uint8_t* g = smem + L::g + (C == 1 ? buf * BOX : 0);
+    const int next = tile + gridDim.x;
+    if (C == 1) {
+      // prefetch the next tile into the other gray buffer (its last reader, phase B of the previous tile, is behind
+      // at least one barrier for every thread)
+      if (tid == 0 && next < tg.ntiles) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue_tile_load<C>(&tmap, mbar0 + 8 * (buf ^ 1), smem_u32(smem + L::g + (buf ^ 1) * BOX), tg, next);
       }
+      mbar_wait(mbar0 + 8 * buf, (it >> 1) & 1);
     } else {
-      const int xh = OW * cx - 5 + j;
-#pragma unroll
-      for (int dy = 0; dy < 5; ++dy) {
-        const int yh = OH * cy - 5 + 5 * ti + dy;
-        if (yh >= 0 && yh < geo.hh && xh >= 0 && xh < geo.hw) {
-          const int v = col[dy * PP];
-          mn = min(mn, v);
-          mx = max(mx, v);
+      mbar_wait(mbar0, it & 1);
+    }
+
+    // ---- phase A: BGR -> gray (whole region) + store of the owned gray pixels --------------------------------
+    if (C == 3) {
+      if (tid < 252) {
+        const int gq = tid % 12;  // 16-pixel group of the row
+        int row = tid / 12;       // rows row, row+21, ...
+        const uint8_t* src = smem + L::bgr + (gq >> 2) * BOX + (gq & 3) * 48 + row * RW;
+        uint8_t* dst = g + gq * 16 + row * RW;
+        const int x = x0r + gq * 16;
+        const bool own_col = gq >= 1 && gq <= 10 && x < geo.w;
+        uint8_t* gp = gray_out + (size_t)fr * gray_fstride + (ptrdiff_t)(y0r + row) * geo.gpitch + x;
+        for (; row < RH; row += 21, src += 21 * RW, dst += 21 * RW, gp += (size_t)21 * geo.gpitch) {
+          const uint4 a = reinterpret_cast<const uint4*>(src)[0], b = reinterpret_cast<const uint4*>(src)[1],
+                      c = reinterpret_cast<const uint4*>(src)[2];
+          uint4 o;
+          o.x = gray4(a.x, a.y, a.z);
+          o.y = gray4(a.w, b.x, b.y);
+          o.z = gray4(b.z, b.w, c.x);
+          o.w = gray4(c.y, c.z, c.w);
+          *reinterpret_cast<uint4*>(dst) = o;
+          if (own_col && row >= 11 && row < 11 + 2 * OH && y0r + row < geo.h) *reinterpret_cast<uint4*>(gp) = o;
         }
       }
+      __syncthreads();
+      // the BGR staging buffer is free: start loading this CTA's next tile behind the stencil phases
+      if (tid == 0 && next < tg.ntiles) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue_tile_load<C>(&tmap, mbar0, smem_u32(smem + L::bgr), tg, next);
+      }
     }
-    cmn[ti * 96 + j] = (uint8_t)mn;
-    cmx[ti * 96 + j] = (uint8_t)mx;
-  }
-  __syncthreads();
-  if (tid < CTX * CTY) {
-    const int ti = tid / CTX, tj = tid - ti * CTX;
-    int mn = 255, mx = 0;
-#pragma unroll
-    for (int dx = 0; dx < 5; ++dx) {
-      mn = min(mn, (int)cmn[ti * 96 + 5 * tj + dx]);
-      mx = max(mx, (int)cmx[ti * 96 + 5 * tj + dx]);
-    }
-    tmin[tid] = (uint8_t)mn;
-    tmax[tid] = (uint8_t)mx;
-  }
-  __syncthreads();
 
-  // ---- phase E: 3x3 tile dilation -> integer threshold per owned tile (corner_detector.cpp:54-78) -----------
-  uint8_t* vthr = smem + L::vthr;
-  if (tid < OTX * OTY) {
-    int oi = tid / OTX, oj = tid - oi * OTX;
-    int ty = OTY * cy + oi, tx = OTX * cx + oj;
-    int t = 0;  // border ring / outside: threshold 0 -> background (SURVEY C-1)
-    if (tx >= 1 && tx <= geo.cn - 2 && ty >= 1 && ty <= geo.rn - 2) {
+    // ---- replicate-border patch (TMA zero-fills outside the image; INTER_CUBIC uses BORDER_REPLICATE) ---------
+    {
+      const int rW = geo.w - x0r, rH = geo.h - y0r;
+      const bool left = (cx == 0), right = (rW < RW), top = (cy == 0), bottom = (rH < RH);
+      if (left | right | top | bottom) {
+        if (left)
+          for (int r = tid; r < RH; r += NT) g[r * RW + 15] = g[r * RW + 16];
+        if (right)
+          for (int r = tid; r < RH; r += NT) g[r * RW + rW] = g[r * RW + rW - 1];
+        __syncthreads();
+        if (top)
+          for (int c = tid; c < RW; c += NT) g[10 * RW + c] = g[11 * RW + c];
+        if (bottom)
+          for (int c = tid; c < RW; c += NT) g[rH * RW + c] = g[(rH - 1) * RW + c];
+        __syncthreads();
+      }
+    }
+
+    // ---- phase B: horizontal taps (-3,19,19,-3) on two rows at a time: HT[rp][j] = (h[2rp][j], h[2rp+1][j]) as an
+    //      int16 pair, the layout the vertical dp2a wants.  h[row][j] uses region columns 2j+5..2j+8. ---------------
+    if (tid < 253) {
+      const uint32_t COEF = 0xFD1313FDu;  // (-3, 19, 19, -3) as signed bytes
+      const int k = tid % 23;
+      int rp = tid / 23;  // row pairs rp, rp+11, ...
+      const uint8_t* src = g + (2 * rp) * RW + 8 * k;
+      uint32_t* dst = HT + rp * HP + 4 * k;
+      for (; rp < RH / 2; rp += 11, src += 22 * RW, dst += 11 * HP) {
+        const uint32_t a1 = *reinterpret_cast<const uint32_t*>(src + 4);
+        const uint2 a23 = *reinterpret_cast<const uint2*>(src + 8);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(src + RW + 4);
+        const uint2 b23 = *reinterpret_cast<const uint2*>(src + RW + 8);
+        const int h0 = dp4a_us(__byte_perm(a1, a23.x, 0x4321), COEF, 0), g0 = dp4a_us(__byte_perm(b1, b23.x, 0x4321), COEF, 0);
+        const int h1 = dp4a_us(__byte_perm(a1, a23.x, 0x6543), COEF, 0), g1 = dp4a_us(__byte_perm(b1, b23.x, 0x6543), COEF, 0);
+        const int h2 = dp4a_us(__byte_perm(a23.x, a23.y, 0x4321), COEF, 0), g2 = dp4a_us(__byte_perm(b23.x, b23.y, 0x4321), COEF, 0);
+        const int h3 = dp4a_us(__byte_perm(a23.x, a23.y, 0x6543), COEF, 0), g3 = dp4a_us(__byte_perm(b23.x, b23.y, 0x6543), COEF, 0);
+        uint4 o;
+        o.x = __byte_perm((uint32_t)h0, (uint32_t)g0, 0x5410);
+        o.y = __byte_perm((uint32_t)h1, (uint32_t)g1, 0x5410);
+        o.z = __byte_perm((uint32_t)h2, (uint32_t)g2, 0x5410);
+        o.w = __byte_perm((uint32_t)h3, (uint32_t)g3, 0x5410);
+        *reinterpret_cast<uint4*>(dst) = o;
+      }
+    }
+    __syncthreads();
+
+    // ---- phase C: vertical taps + round-half-even + saturate: P[i][j] from row pairs i and i+1 ----------------------
+    if (tid < 253) {
+      const uint32_t C01 = 0x000013FDu;  // (-3, 19) on bytes 0,1
+      const uint32_t C23 = 0x0000FD13u;  // (19, -3)
+      const int k = tid % 23;
+      int i = tid / 23;  // half-res rows i, i+11, ...
+      const uint32_t* src = HT + i * HP + 4 * k;
+      uint8_t* dst = P + i * PP + POFF + 4 * k;  // POFF is odd: byte stores
+      for (; i < 50; i += 11, src += 11 * HP, dst += 11 * PP) {
+        const uint4 a = *reinterpret_cast<const uint4*>(src);
+        const uint4 b = *reinterpret_cast<const uint4*>(src + HP);
+        int v0 = dp2a_lo_ss(b.x, C23, dp2a_lo_ss(a.x, C01, 0));
+        int v1 = dp2a_lo_ss(b.y, C23, dp2a_lo_ss(a.y, C01, 0));
+        int v2 = dp2a_lo_ss(b.z, C23, dp2a_lo_ss(a.z, C01, 0));
+        int v3 = dp2a_lo_ss(b.w, C23, dp2a_lo_ss(a.w, C01, 0));
+        // v / 1024 rounded half to even (what cv::resize's float path does), then saturate_cast<uchar>
+        v0 = (v0 + 511 + ((v0 >> 10) & 1)) >> 10;
+        v1 = (v1 + 511 + ((v1 >> 10) & 1)) >> 10;
+        v2 = (v2 + 511 + ((v2 >> 10) & 1)) >> 10;
+        v3 = (v3 + 511 + ((v3 >> 10) & 1)) >> 10;
+        dst[0] = (uint8_t)min(max(v0, 0), 255);
+        dst[1] = (uint8_t)min(max(v1, 0), 255);
+        dst[2] = (uint8_t)min(max(v2, 0), 255);
+        dst[3] = (uint8_t)min(max(v3, 0), 255);
+      }
+    }
+    __syncthreads();
+
+    // ---- phase D: 5x5 tile min/max over valid pixels (corner_detector.cpp:42-53): column extrema, then 5 columns -----
+    const bool edge_cta = (cx == 0) || (cy == 0) || (OW * cx + OW + 5 > geo.hw) || (OH * cy + OH + 5 > geo.hh);
+    if (tid < 180) {
+      const int j = tid % 90;
+      const int xh = OW * cx - 5 + j;
+      for (int ti = tid / 90; ti < CTY; ti += 2) {
+        const uint8_t* col = P + (5 * ti) * PP + POFF + j;
+        int mn = 255, mx = 0;
+        if (!edge_cta) {
+#pragma unroll
+          for (int dy = 0; dy < 5; ++dy) {
+            const int v = col[dy * PP];
+            mn = min(mn, v);
+            mx = max(mx, v);
+          }
+        } else {
+#pragma unroll
+          for (int dy = 0; dy < 5; ++dy) {
+            const int yh = OH * cy - 5 + 5 * ti + dy;
+            if (yh >= 0 && yh < geo.hh && xh >= 0 && xh < geo.hw) {
+              const int v = col[dy * PP];
+              mn = min(mn, v);
+              mx = max(mx, v);
+            }
+          }
+        }
+        cmn[ti * 96 + j] = (uint8_t)mn;
+        cmx[ti * 96 + j] = (uint8_t)mx;
+      }
+    }
+    __syncthreads();
+    if (tid < CTX * CTY) {
+      const int ti = tid / CTX, tj = tid - ti * CTX;
       int mn = 255, mx = 0;
 #pragma unroll
-      for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          mn = min(mn, (int)tmin[(oi + dy) * CTX + oj + dx]);
-          mx = max(mx, (int)tmax[(oi + dy) * CTX + oj + dx]);
-        }
-      // dst = 255 iff src < min(0.3f, (max+min)/2) in float; src = lut255(v) is strictly increasing in v,
-      // so find the smallest v with lut255(v) >= thr and compare integers per pixel (t <= 77 because thr <= 0.3).
-      float thr = fminf(0.3f, __fmul_rn(__fadd_rn(lut255(mx), lut255(mn)), 0.5f));
-      t = min(max((int)(thr * 255.0f), 0), 255);
-      while (t > 0 && !(lut255(t - 1) < thr)) --t;
-      while (t < 256 && lut255(t) < thr) ++t;
+      for (int dx = 0; dx < 5; ++dx) {
+        mn = min(mn, (int)cmn[ti * 96 + 5 * tj + dx]);
+        mx = max(mx, (int)cmx[ti * 96 + 5 * tj + dx]);
+      }
+      tmin[tid] = (uint8_t)mn;
+      tmax[tid] = (uint8_t)mx;
     }
-    vthr[tid] = (uint8_t)t;
-  }
-  __syncthreads();
-  // one threshold byte per owned pixel column, per tile row: lets phase F compare 4 pixels per instruction group
-  uint8_t* thr16 = smem + L::thr16;
-  for (int item = tid; item < OTY * OW; item += NT) {
-    const int oi = item / OW, jo = item - oi * OW;
-    thr16[item] = vthr[oi * OTX + jo / 5];
-  }
-  __syncthreads();
+    __syncthreads();
 
-  // ---- phase F: threshold the owned 80x40 pixels, 16 per thread, 128-bit stores -----------------------------
-  {
-    uint8_t* bin_f = bin_out + (size_t)fr * bin_fstride;
-    for (int item = tid; item < OH * 5; item += NT) {
-      const int i = item / 5, q = item - i * 5;
-      const int yh = OH * cy + i, xh0 = OW * cx + 16 * q;
-      if (yh >= geo.hh || xh0 >= geo.bpitch) continue;
-      const uint4 v = *reinterpret_cast<const uint4*>(P + (i + 5) * PP + 16 + 16 * q);
-      const uint4 t = *reinterpret_cast<const uint4*>(thr16 + (i / 5) * OW + 16 * q);
-      const uint32_t vw[4] = {v.x, v.y, v.z, v.w}, tw[4] = {t.x, t.y, t.z, t.w};
-      uint32_t o[4];
+    // ---- phase E: 3x3 tile dilation -> integer threshold per owned tile (corner_detector.cpp:54-78) -----------
+    if (tid < OTX * OTY) {
+      const int oi = tid / OTX, oj = tid - oi * OTX;
+      const int ty = OTY * cy + oi, tx = OTX * cx + oj;
+      int t = 0;  // border ring / outside: threshold 0 -> background (SURVEY C-1)
+      if (tx >= 1 && tx <= geo.cn - 2 && ty >= 1 && ty <= geo.rn - 2) {
+        int mn = 255, mx = 0;
 #pragma unroll
-      for (int ww = 0; ww < 4; ++ww) {
-        // per-byte v < t for t <= 127: ((v | 0x80) - t) keeps bit 7 iff (v & 0x7f) >= t; v >= 128 is never below t
-        const uint32_t d = (vw[ww] | 0x80808080u) - tw[ww];
-        const uint32_t lt = ~(d | vw[ww]) & 0x80808080u;
-        o[ww] = (lt >> 7) * 255u;
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            mn = min(mn, (int)tmin[(oi + dy) * CTX + oj + dx]);
+            mx = max(mx, (int)tmax[(oi + dy) * CTX + oj + dx]);
+          }
+        // dst = 255 iff src < min(0.3f, (max+min)/2) in float; src = lut255(v) is strictly increasing in v, so find
+        // the smallest v with lut255(v) >= thr and compare integers per pixel (t <= 77 because thr <= 0.3).
+        const float thr = fminf(0.3f, __fmul_rn(__fadd_rn(lut255(mx), lut255(mn)), 0.5f));
+        t = min(max((int)(thr * 255.0f), 0), 255);
+        while (t > 0 && !(lut255(t - 1) < thr)) --t;
+        while (t < 256 && lut255(t) < thr) ++t;
       }
-      if (xh0 + 16 > geo.hw) {  // right image edge inside this group: columns >= hw stay background
-#pragma unroll
-        for (int ww = 0; ww < 4; ++ww)
-#pragma unroll
-          for (int bb = 0; bb < 4; ++bb)
-            if (xh0 + 4 * ww + bb >= geo.hw) o[ww] &= ~(255u << (8 * bb));
-      }
-      *reinterpret_cast<uint4*>(bin_f + (size_t)yh * geo.bpitch + xh0) = make_uint4(o[0], o[1], o[2], o[3]);
+      vthr[tid] = (uint8_t)t;
     }
+    __syncthreads();
+    // one threshold byte per owned pixel column and tile row: lets phase F compare 4 pixels per instruction group
+    if (tid < OW) {
+      const int tj = tid / 5;
+#pragma unroll
+      for (int oi = 0; oi < OTY; ++oi) thr16[oi * OW + tid] = vthr[oi * OTX + tj];
+    }
+    __syncthreads();
+
+    // ---- phase F: threshold the owned 80x40 pixels, 16 per thread, 128-bit stores -----------------------------
+    if (tid < OH * 5) {
+      const int i = tid / 5, q = tid - i * 5;
+      const int yh = OH * cy + i, xh0 = OW * cx + 16 * q;
+      if (yh < geo.hh && xh0 < geo.bpitch) {
+        const uint4 v = *reinterpret_cast<const uint4*>(P + (i + 5) * PP + 16 + 16 * q);
+        const uint4 t = *reinterpret_cast<const uint4*>(thr16 + (i / 5) * OW + 16 * q);
+        const uint32_t vw[4] = {v.x, v.y, v.z, v.w}, tw[4] = {t.x, t.y, t.z, t.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int ww = 0; ww < 4; ++ww) {
+          // per-byte v < t for t <= 127: ((v | 0x80) - t) keeps bit 7 iff (v & 0x7f) >= t; v >= 128 is never below t
+          const uint32_t d = (vw[ww] | 0x80808080u) - tw[ww];
+          const uint32_t lt = ~(d | vw[ww]) & 0x80808080u;
+          o[ww] = (lt >> 7) * 255u;
+        }
+        if (xh0 + 16 > geo.hw) {  // right image edge inside this group: columns >= hw stay background
+#pragma unroll
+          for (int ww = 0; ww < 4; ++ww)
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb)
+              if (xh0 + 4 * ww + bb >= geo.hw) o[ww] &= ~(255u << (8 * bb));
+        }
+        *reinterpret_cast<uint4*>(bin_out + (size_t)fr * bin_fstride + (size_t)yh * geo.bpitch + xh0) =
+            make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    // no barrier needed here: the next iteration touches g/bgr (free since phase B / phase A) and reaches HT, P and
+    // the small arrays only after further barriers
   }
 }
 
@@ -359,6 +406,28 @@ int front_smem_bytes(int channels) {
   return channels == 3 ? front::Layout<3>::total : front::Layout<1>::total;
 }
 
+template <int C>
+static int launch_front_t(const CUtensorMap& tmap, int n, const FrameGeom& geo, uint8_t* gray_out, size_t gray_fstride,
+                          uint8_t* bin_out, size_t bin_fstride, cudaStream_t stream) {
+  using namespace front;
+  CTAG_CUDA_CHECK(cudaFuncSetAttribute(front_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Layout<C>::total));
+  int dev = 0, sms = 0, per_sm = 0;
+  CTAG_CUDA_CHECK(cudaGetDevice(&dev));
+  CTAG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CTAG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, front_kernel<C>, NT, Layout<C>::total));
+  if (per_sm < 1) per_sm = 1;
+  TileGrid tg;
+  tg.tiles_x = (geo.hw + OW - 1) / OW;
+  tg.tiles_y = (geo.hh + OH - 1) / OH;
+  tg.tiles_per_frame = tg.tiles_x * tg.tiles_y;
+  tg.ntiles = tg.tiles_per_frame * n;
+  int grid = sms * per_sm;  // persistent: one wave of resident CTAs
+  if (grid > tg.ntiles) grid = tg.ntiles;
+  front_kernel<C><<<grid, NT, Layout<C>::total, stream>>>(tmap, geo, tg, gray_out, gray_fstride, bin_out, bin_fstride);
+  CTAG_CUDA_CHECK(cudaGetLastError());
+  return CTAG_OK;
+}
+
 int launch_front(const void* frames_dev, int n, const FrameGeom& geo, int channels, size_t pitch, size_t frame_stride,
                  uint8_t* gray_out, size_t gray_fstride, uint8_t* bin_out, size_t bin_fstride, cudaStream_t stream) {
   using namespace front;
@@ -380,16 +449,8 @@ int launch_front(const void* frames_dev, int n, const FrameGeom& geo, int channe
     set_last_error_text("cuTensorMapEncodeTiled failed");
     return CTAG_ERR_CUDA;
   }
-  dim3 grid((geo.hw + OW - 1) / OW, (geo.hh + OH - 1) / OH, n);
-  if (channels == 3) {
-    CTAG_CUDA_CHECK(cudaFuncSetAttribute(front_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Layout<3>::total));
-    front_kernel<3><<<grid, NT, Layout<3>::total, stream>>>(tmap, geo, gray_out, gray_fstride, bin_out, bin_fstride);
-  } else {
-    CTAG_CUDA_CHECK(cudaFuncSetAttribute(front_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Layout<1>::total));
-    front_kernel<1><<<grid, NT, Layout<1>::total, stream>>>(tmap, geo, gray_out, gray_fstride, bin_out, bin_fstride);
-  }
-  CTAG_CUDA_CHECK(cudaGetLastError());
-  return CTAG_OK;
+  return channels == 3 ? launch_front_t<3>(tmap, n, geo, gray_out, gray_fstride, bin_out, bin_fstride, stream)
+                       : launch_front_t<1>(tmap, n, geo, gray_out, gray_fstride, bin_out, bin_fstride, stream);
 }
 
 }  // namespace ctag
