@@ -63,81 +63,133 @@ __device__ __forceinline__ void uf_unite(int* L, int a, int b) {
   }
 }
 
-__global__ void __launch_bounds__(1024) ccl_local_kernel(const uint8_t* __restrict__ bin, size_t bin_fstride, FrameGeom g,
-                                                         int* __restrict__ labels, int* __restrict__ st_area,
-                                                         int* __restrict__ st_x0, int* __restrict__ st_y0,
-                                                         int* __restrict__ st_x1, int* __restrict__ st_y1) {
+// 256 threads per 32x32-block tile; thread t owns the four horizontally adjacent blocks (4*(t&7) .. +3, t>>3) so that the
+// binary image is read with 8-byte loads and empty tiles (the common case) write their labels with 16-byte stores.
+__global__ void __launch_bounds__(256) ccl_local_kernel(const uint8_t* __restrict__ bin, size_t bin_fstride, FrameGeom g,
+                                                        int* __restrict__ labels, int* __restrict__ st_area,
+                                                        int* __restrict__ st_x0, int* __restrict__ st_y0,
+                                                        int* __restrict__ st_x1, int* __restrict__ st_y1) {
   __shared__ int L[1024];
   __shared__ uint8_t pat[1024];
   __shared__ int sA[1024], sX0[1024], sY0[1024], sX1[1024], sY1[1024];
-  const int t = threadIdx.x, tx = t & 31, ty = t >> 5;
-  const int bx = blockIdx.x * 32 + tx, by = blockIdx.y * 32 + ty, fr = blockIdx.z;
-  const bool inside = bx < g.bw && by < g.bh;
-  int p = 0;
-  if (inside) p = block_pattern(bin + (size_t)fr * bin_fstride, g, bx, by);
-  pat[t] = (uint8_t)p;
-  L[t] = p ? t : -1;
-  sA[t] = 0;
-  sX0[t] = 0x7fffffff;
-  sY0[t] = 0x7fffffff;
-  sX1[t] = -1;
-  sY1[t] = -1;
-  __syncthreads();
-  if (p) {
-    if (ty > 0) {
-      int q = pat[t - 32];
-      if ((p & 3) && (q & 12)) uf_unite(L, t, t - 32);
-      if (tx > 0 && (p & 1) && (pat[t - 33] & 8)) uf_unite(L, t, t - 33);
-      if (tx < 31 && (p & 2) && (pat[t - 31] & 4)) uf_unite(L, t, t - 31);
-    }
-    if (tx > 0 && (p & 5) && (pat[t - 1] & 10)) uf_unite(L, t, t - 1);
-  }
-  __syncthreads();
-  int r = -1;
-  if (p) r = uf_find(L, t);
-  __syncthreads();
-  if (p) L[t] = r;
-  // partial stats per local root, aggregated per warp (one warp = one row of 32 blocks) before touching smem atomics
-  {
-    unsigned active = __ballot_sync(0xffffffffu, p != 0);
-    if (p) {
-      unsigned grp = __match_any_sync(active, r);
-      int x = 2 * bx, y = 2 * by;
-      int xmin = (p & 5) ? x : x + 1, xmax = (p & 10) ? x + 1 : x;
-      int ymin = (p & 3) ? y : y + 1, ymax = (p & 12) ? y + 1 : y;
-      int a = __reduce_add_sync(grp, __popc(p));
-      xmin = __reduce_min_sync(grp, xmin);
-      ymin = __reduce_min_sync(grp, ymin);
-      xmax = __reduce_max_sync(grp, xmax);
-      ymax = __reduce_max_sync(grp, ymax);
-      if ((int)(__ffs(grp) - 1) == tx) {
-        atomicAdd(&sA[r], a);
-        atomicMin(&sX0[r], xmin);
-        atomicMin(&sY0[r], ymin);
-        atomicMax(&sX1[r], xmax);
-        atomicMax(&sY1[r], ymax);
-      }
+  const int t = threadIdx.x, tq = t & 7, ty = t >> 3;
+  const int bx0 = blockIdx.x * 32 + 4 * tq, by = blockIdx.y * 32 + ty, fr = blockIdx.z;
+  const size_t base = (size_t)fr * g.nblocks;
+  int p4[4] = {0, 0, 0, 0};
+  if (by < g.bh && bx0 < g.bw) {
+    // 8 pixels of two rows; bpitch is a multiple of 16 and columns >= hw inside the pitch are zero (front kernel)
+    const uint8_t* r0 = bin + (size_t)fr * bin_fstride + (size_t)(2 * by) * g.bpitch + 2 * bx0;
+    const uint2 a = *reinterpret_cast<const uint2*>(r0);
+    uint2 b = make_uint2(0u, 0u);
+    if (2 * by + 1 < g.hh) b = *reinterpret_cast<const uint2*>(r0 + g.bpitch);
+    const uint32_t aw[2] = {a.x, a.y}, bw_[2] = {b.x, b.y};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t va = aw[k >> 1] >> (16 * (k & 1)), vb = bw_[k >> 1] >> (16 * (k & 1));
+      p4[k] = ((va & 0xFF) ? 1 : 0) | ((va & 0xFF00) ? 2 : 0) | ((vb & 0xFF) ? 4 : 0) | ((vb & 0xFF00) ? 8 : 0);
+      if (bx0 + k >= g.bw) p4[k] = 0;
     }
   }
-  __syncthreads();
-  if (inside) {
-    size_t base = (size_t)fr * g.nblocks;
-    int gi = by * g.bw + bx;
-    int e = -1;
-    if (p) {
-      int gr = (blockIdx.y * 32 + (r >> 5)) * g.bw + blockIdx.x * 32 + (r & 31);
-      if (r == t) {
-        e = gi;
-        st_area[base + gi] = sA[t];
-        st_x0[base + gi] = sX0[t];
-        st_y0[base + gi] = sY0[t];
-        st_x1[base + gi] = sX1[t];
-        st_y1[base + gi] = sY1[t];
+  // empty tile: only the background labels have to be written
+  if (!__syncthreads_or(p4[0] | p4[1] | p4[2] | p4[3])) {
+    if (by < g.bh && bx0 < g.bw) {
+      int* dst = labels + base + (size_t)by * g.bw + bx0;
+      if (bx0 + 3 < g.bw && ((base + (size_t)by * g.bw + bx0) & 3) == 0) {
+        *reinterpret_cast<int4*>(dst) = make_int4(-1, -1, -1, -1);
       } else {
-        e = kTag | gr;
+        for (int k = 0; k < 4 && bx0 + k < g.bw; ++k) dst[k] = -1;
       }
     }
-    labels[base + gi] = e;
+    return;
+  }
+  const int l0 = ty * 32 + 4 * tq;  // tile-local index of the first owned block
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    pat[l0 + k] = (uint8_t)p4[k];
+    L[l0 + k] = p4[k] ? l0 + k : -1;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int p = p4[k], l = l0 + k, tx = 4 * tq + k;
+    if (p) {
+      if (ty > 0) {
+        int q = pat[l - 32];
+        if ((p & 3) && (q & 12)) uf_unite(L, l, l - 32);
+        if (tx > 0 && (p & 1) && (pat[l - 33] & 8)) uf_unite(L, l, l - 33);
+        if (tx < 31 && (p & 2) && (pat[l - 31] & 4)) uf_unite(L, l, l - 31);
+      }
+      if (tx > 0 && (p & 5) && (pat[l - 1] & 10)) uf_unite(L, l, l - 1);
+    }
+  }
+  __syncthreads();
+  int r4[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) r4[k] = p4[k] ? uf_find(L, l0 + k) : -1;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int l = l0 + k;
+    if (p4[k]) {
+      L[l] = r4[k];
+      if (r4[k] == l) {  // stats live at the tile-local roots only
+        sA[l] = 0;
+        sX0[l] = 0x7fffffff;
+        sY0[l] = 0x7fffffff;
+        sX1[l] = -1;
+        sY1[l] = -1;
+      }
+    }
+  }
+  __syncthreads();
+  // partial stats per local root: merge the thread's own blocks that share a root, then smem atomics
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int p = p4[k];
+    if (!p) continue;
+    const int r = r4[k];
+    bool first = true;
+    for (int q = 0; q < k; ++q) first &= !(p4[q] && r4[q] == r);
+    if (!first) continue;
+    int a = 0, xmin = 0x7fffffff, ymin = 0x7fffffff, xmax = -1, ymax = -1;
+    for (int q = k; q < 4; ++q) {
+      const int pq = p4[q];
+      if (!pq || r4[q] != r) continue;
+      const int x = 2 * (bx0 + q), y = 2 * by;
+      a += __popc(pq);
+      xmin = min(xmin, (pq & 5) ? x : x + 1);
+      xmax = max(xmax, (pq & 10) ? x + 1 : x);
+      ymin = min(ymin, (pq & 3) ? y : y + 1);
+      ymax = max(ymax, (pq & 12) ? y + 1 : y);
+    }
+    atomicAdd(&sA[r], a);
+    atomicMin(&sX0[r], xmin);
+    atomicMin(&sY0[r], ymin);
+    atomicMax(&sX1[r], xmax);
+    atomicMax(&sY1[r], ymax);
+  }
+  __syncthreads();
+  if (by < g.bh) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int bx = bx0 + k;
+      if (bx >= g.bw) continue;
+      const int gi = by * g.bw + bx, l = l0 + k, r = r4[k];
+      int e = -1;
+      if (p4[k]) {
+        if (r == l) {
+          e = gi;
+          st_area[base + gi] = sA[l];
+          st_x0[base + gi] = sX0[l];
+          st_y0[base + gi] = sY0[l];
+          st_x1[base + gi] = sX1[l];
+          st_y1[base + gi] = sY1[l];
+        } else {
+          e = kTag | ((blockIdx.y * 32 + (r >> 5)) * g.bw + blockIdx.x * 32 + (r & 31));
+        }
+      }
+      labels[base + gi] = e;
+    }
   }
 }
 
@@ -334,7 +386,7 @@ int launch_ccl(const uint8_t* bin, size_t bin_fstride, int n, const FrameGeom& g
                int* st_y0, int* st_x1, int* st_y1, int* roots_tmp, int* span_count, int* legal, int legal_cap,
                int* counters, cudaStream_t stream, int* launches) {
   dim3 tiles((g.bw + 31) / 32, (g.bh + 31) / 32, n);
-  ccl_local_kernel<<<tiles, 1024, 0, stream>>>(bin, bin_fstride, g, labels, st_area, st_x0, st_y0, st_x1, st_y1);
+  ccl_local_kernel<<<tiles, 256, 0, stream>>>(bin, bin_fstride, g, labels, st_area, st_x0, st_y0, st_x1, st_y1);
   ccl_merge_kernel<<<tiles, 64, 0, stream>>>(bin, bin_fstride, g, labels);
   int spans = (g.nblocks + 1023) / 1024;
   ccl_final_kernel<<<dim3(spans, n), 1024, 0, stream>>>(g, labels, st_area, st_x0, st_y0, st_x1, st_y1, roots_tmp,
