@@ -251,23 +251,35 @@ __global__ void __launch_bounds__(64) ccl_merge_kernel(const uint8_t* __restrict
   }
 }
 
-// One thread per block.  roots_tmp[span*1024 + k] = k-th global root (ascending) of the span; span_count[span].
-__global__ void __launch_bounds__(1024) ccl_final_kernel(FrameGeom g, int* __restrict__ labels, int* __restrict__ st_area,
-                                                         int* __restrict__ st_x0, int* __restrict__ st_y0,
-                                                         int* __restrict__ st_x1, int* __restrict__ st_y1,
-                                                         int* __restrict__ roots_tmp, int* __restrict__ span_count,
-                                                         int spans_per_frame) {
-  __shared__ int warp_cnt[32];
+// Four consecutive blocks per thread (16-byte label loads; background runs are skipped at once).
+// roots_tmp[span*1024 + k] = k-th global root (ascending) of the 1024-block span; span_count[span].
+__global__ void __launch_bounds__(256) ccl_final_kernel(FrameGeom g, int* __restrict__ labels, int* __restrict__ st_area,
+                                                        int* __restrict__ st_x0, int* __restrict__ st_y0,
+                                                        int* __restrict__ st_x1, int* __restrict__ st_y1,
+                                                        int* __restrict__ roots_tmp, int* __restrict__ span_count,
+                                                        int spans_per_frame) {
+  __shared__ int warp_cnt[8];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const int fr = blockIdx.y;
   const size_t base = (size_t)fr * g.nblocks;
   int* lab = labels + base;
-  const int i = blockIdx.x * 1024 + t;
-  bool is_root = false;
-  if (i < g.nblocks) {
-    int e = lab[i];
-    if (e >= 0) {
-      int r = gfind(lab, i);
+  const int i0 = blockIdx.x * 1024 + 4 * t;
+  int e4[4] = {-1, -1, -1, -1};
+  if (i0 + 3 < g.nblocks && ((base + i0) & 3) == 0) {
+    const int4 v = *reinterpret_cast<const int4*>(lab + i0);
+    e4[0] = v.x, e4[1] = v.y, e4[2] = v.z, e4[3] = v.w;
+  } else {
+    for (int k = 0; k < 4; ++k)
+      if (i0 + k < g.nblocks) e4[k] = lab[i0 + k];
+  }
+  int nroot = 0;
+  unsigned rootmask = 0;
+  if ((e4[0] & e4[1] & e4[2] & e4[3]) >= 0) {  // at least one foreground block (labels are >= 0, background is -1)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int e = e4[k], i = i0 + k;
+      if (e < 0) continue;
+      const int r = gfind(lab, i);
       if (e & kTag) {
         lab[i] = r;
       } else if (r != i) {
@@ -279,28 +291,33 @@ __global__ void __launch_bounds__(1024) ccl_final_kernel(FrameGeom g, int* __res
         atomicMax(&st_y1[base + r], st_y1[base + i]);
         lab[i] = r;
       } else {
-        is_root = true;
+        rootmask |= 1u << k;
+        ++nroot;
       }
     }
   }
-  unsigned bal = __ballot_sync(0xffffffffu, is_root);
-  if (lane == 0) warp_cnt[wid] = __popc(bal);
-  __syncthreads();
-  if (wid == 0) {
-    int v = warp_cnt[lane];
-    int inc = v;
+  // exclusive prefix of the per-thread root counts over the CTA (warp shuffle scan + 8 warp totals)
+  int inc = nroot;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int n = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += n;
-    }
-    warp_cnt[lane] = inc - v;  // exclusive
-    if (lane == 31) span_count[fr * spans_per_frame + blockIdx.x] = inc;
+  for (int o = 1; o < 32; o <<= 1) {
+    int n = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += n;
   }
+  if (lane == 31) warp_cnt[wid] = inc;
   __syncthreads();
-  if (is_root) {
-    int pos = warp_cnt[wid] + __popc(bal & ((1u << lane) - 1));
-    roots_tmp[base + (size_t)blockIdx.x * 1024 + pos] = i;
+  int woff = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    const int c = warp_cnt[w];
+    if (w < wid) woff += c;
+    total += c;
+  }
+  if (t == 0) span_count[fr * spans_per_frame + blockIdx.x] = total;
+  if (nroot) {
+    int pos = woff + inc - nroot;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (rootmask & (1u << k)) roots_tmp[base + (size_t)blockIdx.x * 1024 + pos++] = i0 + k;
   }
 }
 
@@ -389,7 +406,7 @@ int launch_ccl(const uint8_t* bin, size_t bin_fstride, int n, const FrameGeom& g
   ccl_local_kernel<<<tiles, 256, 0, stream>>>(bin, bin_fstride, g, labels, st_area, st_x0, st_y0, st_x1, st_y1);
   ccl_merge_kernel<<<tiles, 64, 0, stream>>>(bin, bin_fstride, g, labels);
   int spans = (g.nblocks + 1023) / 1024;
-  ccl_final_kernel<<<dim3(spans, n), 1024, 0, stream>>>(g, labels, st_area, st_x0, st_y0, st_x1, st_y1, roots_tmp,
+  ccl_final_kernel<<<dim3(spans, n), 256, 0, stream>>>(g, labels, st_area, st_x0, st_y0, st_x1, st_y1, roots_tmp,
                                                         span_count, spans);
   ccl_list_kernel<<<n, 1024, 0, stream>>>(g, st_area, st_x0, st_y0, st_x1, st_y1, roots_tmp, span_count, spans, legal,
                                           legal_cap, counters);
