@@ -164,6 +164,8 @@ inline void welsch_pick_table(uint16_t* table, int max_count) {
   }
 }
 
+constexpr int kWelschCache = 128;  // raw weights kept per thread up to this cluster size
+
 // One restart from its (sorted) initial subset; `visit(i, err, line)` is called for every iterate (at most 30).
 template <typename PtFn, typename Visitor>
 CT_HD int welsch_restart_from_picks(PtFn pt, int count, const int* picked, int np, Visitor& visit);
@@ -197,6 +199,7 @@ CT_HD int welsch_restart_from_picks(PtFn pt, int count, const int* picked, int n
     line_from_moments(x, y, x2, y2, xy, w, line);
   }
   const float c = 1 / 2.9846f;
+  float wcache[kWelschCache];
   int nvis = 0;
   for (int i = 0; i < 30; ++i) {
     if (i > 0) {
@@ -210,9 +213,11 @@ CT_HD int welsch_restart_from_picks(PtFn pt, int count, const int* picked, int n
         if (d < 0.01f) break;
       }
     }
-    // residuals, error, raw weights
+    // residuals, error, raw weights.  For clusters of up to kWelschCache points the raw weights are kept (thread-local
+    // array) so that the refit pass does not have to evaluate exp again; larger clusters recompute them.
     const float px0 = line[2], py0 = line[3], nx = line[1], ny = -line[0];
     double err = 0, sum_w = 0;
+    const bool cached = count <= kWelschCache;
     // unrolled so that the (independent) exp evaluations of neighbouring points overlap; the accumulations keep the
     // library's order
 #pragma unroll 4
@@ -221,11 +226,13 @@ CT_HD int welsch_restart_from_picks(PtFn pt, int count, const int* picked, int n
       float x = (float)pt_x(p) - px0, y = (float)pt_y(p) - py0;
       float r = (float)fabs(nx * x + ny * y);
       err += r;
-      sum_w += welsch_exp(-r * r * c * c);
+      float wr = welsch_exp(-r * r * c * c);
+      if (cached) wcache[j] = wr;
+      sum_w += wr;
     }
     visit(nvis, err, line);
     ++nvis;
-    // normalised weights + refit (second pass recomputes the residuals instead of storing them)
+    // normalised weights + refit
     double x = 0, y = 0, x2 = 0, y2 = 0, xy = 0, wsum = 0;
     const bool norm = fabs(sum_w) > 1.1920928955078125e-07;
     const double inv = norm ? 1. / sum_w : 0.;
@@ -233,9 +240,15 @@ CT_HD int welsch_restart_from_picks(PtFn pt, int count, const int* picked, int n
     for (int j = 0; j < count; ++j) {
       int p = pt(j);
       float fx = (float)pt_x(p), fy = (float)pt_y(p);
-      float xx = fx - px0, yy = fy - py0;
-      float r = (float)fabs(nx * xx + ny * yy);
-      float w = norm ? (float)(welsch_exp(-r * r * c * c) * inv) : 1.f;
+      float wr;
+      if (cached) {
+        wr = wcache[j];
+      } else {
+        float xx = fx - px0, yy = fy - py0;
+        float r = (float)fabs(nx * xx + ny * yy);
+        wr = welsch_exp(-r * r * c * c);
+      }
+      float w = norm ? (float)(wr * inv) : 1.f;
       x += w * fx;
       y += w * fy;
       x2 += w * fx * fx;
