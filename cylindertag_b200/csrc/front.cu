@@ -25,9 +25,10 @@ constexpr int OW = 80, OH = 40;      // owned half-res pixels per tile
 constexpr int OTX = 16, OTY = 8;     // owned threshold tiles
 constexpr int CTX = 18, CTY = 10;    // computed threshold tiles (owned + 1 ring)
 constexpr int RW = 192, RH = 102;    // full-res region (pixels) staged per tile
-constexpr int HP = 92;               // pitch of the horizontal-pass buffer (row-pair words)
+constexpr int HP = 96;               // pitch of the horizontal-pass buffer (row-pair words), 24 quads of columns
 constexpr int PP = 112;              // pitch of the half-res patch (bytes)
-constexpr int POFF = 11;             // column shift of the half-res patch so that owned pixels start 16B aligned
+constexpr int POFF = 11;             // patch column of half-res column j (x = 80cx - 5 + j); owned pixels start at 16
+constexpr int HOFF = 3;              // the stencil passes run on j' = j + HOFF so that their 4-column groups are aligned
 constexpr int NT = 256;
 constexpr int BOX = RW * RH;         // bytes of one TMA box
 constexpr int H_BYTES = (((RH / 2) * HP * 4 + 127) / 128) * 128;
@@ -72,6 +73,13 @@ __device__ __forceinline__ uint32_t dp2a_hi_uu(uint32_t a16, uint32_t b8, uint32
 __device__ __forceinline__ int dp2a_lo_ss(uint32_t a16, uint32_t b8, int c) {
   int d;
   asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a16), "r"(b8), "r"(c));
+  return d;
+}
+
+// d = (c << 16) | (sat_u8(a) << 8) | sat_u8(b)
+__device__ __forceinline__ uint32_t pack_sat_u8(int a, int b, uint32_t c) {
+  uint32_t d;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
 }
 
@@ -222,57 +230,61 @@ __global__ void __launch_bounds__(front::NT) front_kernel(const __grid_constant_
       }
     }
 
-    // ---- phase B: horizontal taps (-3,19,19,-3) on two rows at a time: HT[rp][j] = (h[2rp][j], h[2rp+1][j]) as an
-    //      int16 pair, the layout the vertical dp2a wants.  h[row][j] uses region columns 2j+5..2j+8. ---------------
-    if (tid < 253) {
+    // ---- phase B: horizontal taps (-3,19,19,-3) on two rows at a time: HT[rp][j'] = (h[2rp][j'], h[2rp+1][j']) as an
+    //      int16 pair, the layout the vertical dp2a wants.  j' = j + 3 (x = 80cx - 8 + j'), so h[row][j'] uses region
+    //      columns 2j'-1..2j'+2 and every group of four j' starts on an 8-byte boundary of the gray row; columns
+    //      j' = 0..2 and 93..95 are never used (their taps may touch a neighbouring row: harmless). ------------------
+    {
       const uint32_t COEF = 0xFD1313FDu;  // (-3, 19, 19, -3) as signed bytes
-      const int k = tid % 23;
-      int rp = tid / 23;  // row pairs rp, rp+11, ...
-      const uint8_t* src = g + (2 * rp) * RW + 8 * k;
-      uint32_t* dst = HT + rp * HP + 4 * k;
-      for (; rp < RH / 2; rp += 11, src += 22 * RW, dst += 11 * HP) {
-        const uint32_t a1 = *reinterpret_cast<const uint32_t*>(src + 4);
-        const uint2 a23 = *reinterpret_cast<const uint2*>(src + 8);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(src + RW + 4);
-        const uint2 b23 = *reinterpret_cast<const uint2*>(src + RW + 8);
-        const int h0 = dp4a_us(__byte_perm(a1, a23.x, 0x4321), COEF, 0), g0 = dp4a_us(__byte_perm(b1, b23.x, 0x4321), COEF, 0);
-        const int h1 = dp4a_us(__byte_perm(a1, a23.x, 0x6543), COEF, 0), g1 = dp4a_us(__byte_perm(b1, b23.x, 0x6543), COEF, 0);
-        const int h2 = dp4a_us(__byte_perm(a23.x, a23.y, 0x4321), COEF, 0), g2 = dp4a_us(__byte_perm(b23.x, b23.y, 0x4321), COEF, 0);
-        const int h3 = dp4a_us(__byte_perm(a23.x, a23.y, 0x6543), COEF, 0), g3 = dp4a_us(__byte_perm(b23.x, b23.y, 0x6543), COEF, 0);
-        uint4 o;
-        o.x = __byte_perm((uint32_t)h0, (uint32_t)g0, 0x5410);
-        o.y = __byte_perm((uint32_t)h1, (uint32_t)g1, 0x5410);
-        o.z = __byte_perm((uint32_t)h2, (uint32_t)g2, 0x5410);
-        o.w = __byte_perm((uint32_t)h3, (uint32_t)g3, 0x5410);
-        *reinterpret_cast<uint4*>(dst) = o;
+      const int k = tid % 24;
+      int rp = tid / 24;  // row pairs rp, rp+10, ... (240 threads), the remaining pairs by the last 16 threads below
+      if (tid < 240) {
+        const uint8_t* src = g + (2 * rp) * RW + 8 * k;
+        uint32_t* dst = HT + rp * HP + 4 * k;
+        for (; rp < RH / 2; rp += 10, src += 20 * RW, dst += 10 * HP) {
+          // k == 0 only feeds the unused column j' = 0: do not read in front of the row (and of the buffer)
+          const uint32_t a0 = k ? *reinterpret_cast<const uint32_t*>(src - 4) : 0u, a3 = *reinterpret_cast<const uint32_t*>(src + 8);
+          const uint2 a12 = *reinterpret_cast<const uint2*>(src);
+          const uint32_t b0 = k ? *reinterpret_cast<const uint32_t*>(src + RW - 4) : 0u, b3 = *reinterpret_cast<const uint32_t*>(src + RW + 8);
+          const uint2 b12 = *reinterpret_cast<const uint2*>(src + RW);
+          const int h0 = dp4a_us(__byte_perm(a0, a12.x, 0x6543), COEF, 0), g0 = dp4a_us(__byte_perm(b0, b12.x, 0x6543), COEF, 0);
+          const int h1 = dp4a_us(__byte_perm(a12.x, a12.y, 0x4321), COEF, 0), g1 = dp4a_us(__byte_perm(b12.x, b12.y, 0x4321), COEF, 0);
+          const int h2 = dp4a_us(__byte_perm(a12.x, a12.y, 0x6543), COEF, 0), g2 = dp4a_us(__byte_perm(b12.x, b12.y, 0x6543), COEF, 0);
+          const int h3 = dp4a_us(__byte_perm(a12.y, a3, 0x4321), COEF, 0), g3 = dp4a_us(__byte_perm(b12.y, b3, 0x4321), COEF, 0);
+          uint4 o;
+          o.x = __byte_perm((uint32_t)h0, (uint32_t)g0, 0x5410);
+          o.y = __byte_perm((uint32_t)h1, (uint32_t)g1, 0x5410);
+          o.z = __byte_perm((uint32_t)h2, (uint32_t)g2, 0x5410);
+          o.w = __byte_perm((uint32_t)h3, (uint32_t)g3, 0x5410);
+          *reinterpret_cast<uint4*>(dst) = o;
+        }
       }
     }
     __syncthreads();
 
-    // ---- phase C: vertical taps + round-half-even + saturate: P[i][j] from row pairs i and i+1 ----------------------
-    if (tid < 253) {
+    // ---- phase C: vertical taps + round-half-even + saturate: P[i][8 + j'] from row pairs i and i+1 -----------------
+    {
       const uint32_t C01 = 0x000013FDu;  // (-3, 19) on bytes 0,1
       const uint32_t C23 = 0x0000FD13u;  // (19, -3)
-      const int k = tid % 23;
-      int i = tid / 23;  // half-res rows i, i+11, ...
-      const uint32_t* src = HT + i * HP + 4 * k;
-      uint8_t* dst = P + i * PP + POFF + 4 * k;  // POFF is odd: byte stores
-      for (; i < 50; i += 11, src += 11 * HP, dst += 11 * PP) {
-        const uint4 a = *reinterpret_cast<const uint4*>(src);
-        const uint4 b = *reinterpret_cast<const uint4*>(src + HP);
-        int v0 = dp2a_lo_ss(b.x, C23, dp2a_lo_ss(a.x, C01, 0));
-        int v1 = dp2a_lo_ss(b.y, C23, dp2a_lo_ss(a.y, C01, 0));
-        int v2 = dp2a_lo_ss(b.z, C23, dp2a_lo_ss(a.z, C01, 0));
-        int v3 = dp2a_lo_ss(b.w, C23, dp2a_lo_ss(a.w, C01, 0));
-        // v / 1024 rounded half to even (what cv::resize's float path does), then saturate_cast<uchar>
-        v0 = (v0 + 511 + ((v0 >> 10) & 1)) >> 10;
-        v1 = (v1 + 511 + ((v1 >> 10) & 1)) >> 10;
-        v2 = (v2 + 511 + ((v2 >> 10) & 1)) >> 10;
-        v3 = (v3 + 511 + ((v3 >> 10) & 1)) >> 10;
-        dst[0] = (uint8_t)min(max(v0, 0), 255);
-        dst[1] = (uint8_t)min(max(v1, 0), 255);
-        dst[2] = (uint8_t)min(max(v2, 0), 255);
-        dst[3] = (uint8_t)min(max(v3, 0), 255);
+      const int k = tid % 24;
+      int i = tid / 24;  // half-res rows i, i+10, ...
+      if (tid < 240) {
+        const uint32_t* src = HT + i * HP + 4 * k;
+        uint8_t* dst = P + i * PP + (POFF - HOFF) + 4 * k;  // 4-byte aligned
+        for (; i < 50; i += 10, src += 10 * HP, dst += 10 * PP) {
+          const uint4 a = *reinterpret_cast<const uint4*>(src);
+          const uint4 b = *reinterpret_cast<const uint4*>(src + HP);
+          int v0 = dp2a_lo_ss(b.x, C23, dp2a_lo_ss(a.x, C01, 0));
+          int v1 = dp2a_lo_ss(b.y, C23, dp2a_lo_ss(a.y, C01, 0));
+          int v2 = dp2a_lo_ss(b.z, C23, dp2a_lo_ss(a.z, C01, 0));
+          int v3 = dp2a_lo_ss(b.w, C23, dp2a_lo_ss(a.w, C01, 0));
+          // v / 1024 rounded half to even (what cv::resize's float path does), then saturate_cast<uchar>
+          v0 = (v0 + 511 + ((v0 >> 10) & 1)) >> 10;
+          v1 = (v1 + 511 + ((v1 >> 10) & 1)) >> 10;
+          v2 = (v2 + 511 + ((v2 >> 10) & 1)) >> 10;
+          v3 = (v3 + 511 + ((v3 >> 10) & 1)) >> 10;
+          *reinterpret_cast<uint32_t*>(dst) = pack_sat_u8(v1, v0, pack_sat_u8(v3, v2, 0u));
+        }
       }
     }
     __syncthreads();
