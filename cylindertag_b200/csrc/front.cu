@@ -29,7 +29,7 @@ constexpr int HP = 96;               // pitch of the horizontal-pass buffer (row
 constexpr int PP = 112;              // pitch of the half-res patch (bytes)
 constexpr int POFF = 11;             // patch column of half-res column j (x = 80cx - 5 + j); owned pixels start at 16
 constexpr int HOFF = 3;              // the stencil passes run on j' = j + HOFF so that their 4-column groups are aligned
-constexpr int NT = 256;
+constexpr int NT = 384;              // 12 warps per CTA, two CTAs per SM (shared memory bound)
 constexpr int BOX = RW * RH;         // bytes of one TMA box
 constexpr int H_BYTES = (((RH / 2) * HP * 4 + 127) / 128) * 128;
 constexpr int P_BYTES = ((50 * PP + 127) / 128) * 128;
@@ -184,15 +184,19 @@ __global__ void __launch_bounds__(front::NT) front_kernel(const __grid_constant_
 
     // ---- phase A: BGR -> gray (whole region) + store of the owned gray pixels --------------------------------
     if (C == 3) {
-      if (tid < 252) {
-        const int gq = tid % 12;  // 16-pixel group of the row
-        int row = tid / 12;       // rows row, row+21, ...
+      {
+        // thread -> (16-pixel group gq, row).  Eight consecutive lanes take the four groups of one staging box on two
+        // consecutive rows: their 16-byte slots (3*(gq&3) + 4*row) mod 8 are all different, so the 128-bit loads from
+        // the box and the 128-bit store into the gray tile are free of bank conflicts.
+        const int rest = tid >> 3;
+        const int gq = (rest % 3) * 4 + (tid & 3);
+        int row = 2 * (rest / 3) + ((tid >> 2) & 1);  // rows row, row+32, ...
         const uint8_t* src = smem + L::bgr + (gq >> 2) * BOX + (gq & 3) * 48 + row * RW;
         uint8_t* dst = g + gq * 16 + row * RW;
         const int x = x0r + gq * 16;
         const bool own_col = gq >= 1 && gq <= 10 && x < geo.w;
         uint8_t* gp = gray_out + (size_t)fr * gray_fstride + (ptrdiff_t)(y0r + row) * geo.gpitch + x;
-        for (; row < RH; row += 21, src += 21 * RW, dst += 21 * RW, gp += (size_t)21 * geo.gpitch) {
+        for (; row < RH; row += NT / 12, src += (NT / 12) * RW, dst += (NT / 12) * RW, gp += (size_t)(NT / 12) * geo.gpitch) {
           const uint4 a = reinterpret_cast<const uint4*>(src)[0], b = reinterpret_cast<const uint4*>(src)[1],
                       c = reinterpret_cast<const uint4*>(src)[2];
           uint4 o;
@@ -237,11 +241,11 @@ __global__ void __launch_bounds__(front::NT) front_kernel(const __grid_constant_
     {
       const uint32_t COEF = 0xFD1313FDu;  // (-3, 19, 19, -3) as signed bytes
       const int k = tid % 24;
-      int rp = tid / 24;  // row pairs rp, rp+10, ... (240 threads), the remaining pairs by the last 16 threads below
-      if (tid < 240) {
+      int rp = tid / 24;  // row pairs rp, rp+16, ...
+      {
         const uint8_t* src = g + (2 * rp) * RW + 8 * k;
         uint32_t* dst = HT + rp * HP + 4 * k;
-        for (; rp < RH / 2; rp += 10, src += 20 * RW, dst += 10 * HP) {
+        for (; rp < RH / 2; rp += NT / 24, src += 2 * (NT / 24) * RW, dst += (NT / 24) * HP) {
           // k == 0 only feeds the unused column j' = 0: do not read in front of the row (and of the buffer)
           const uint32_t a0 = k ? *reinterpret_cast<const uint32_t*>(src - 4) : 0u, a3 = *reinterpret_cast<const uint32_t*>(src + 8);
           const uint2 a12 = *reinterpret_cast<const uint2*>(src);
@@ -267,11 +271,11 @@ __global__ void __launch_bounds__(front::NT) front_kernel(const __grid_constant_
       const uint32_t C01 = 0x000013FDu;  // (-3, 19) on bytes 0,1
       const uint32_t C23 = 0x0000FD13u;  // (19, -3)
       const int k = tid % 24;
-      int i = tid / 24;  // half-res rows i, i+10, ...
-      if (tid < 240) {
+      int i = tid / 24;  // half-res rows i, i+16, ...
+      {
         const uint32_t* src = HT + i * HP + 4 * k;
         uint8_t* dst = P + i * PP + (POFF - HOFF) + 4 * k;  // 4-byte aligned
-        for (; i < 50; i += 10, src += 10 * HP, dst += 10 * PP) {
+        for (; i < 50; i += NT / 24, src += (NT / 24) * HP, dst += (NT / 24) * PP) {
           const uint4 a = *reinterpret_cast<const uint4*>(src);
           const uint4 b = *reinterpret_cast<const uint4*>(src + HP);
           int v0 = dp2a_lo_ss(b.x, C23, dp2a_lo_ss(a.x, C01, 0));
@@ -291,10 +295,10 @@ __global__ void __launch_bounds__(front::NT) front_kernel(const __grid_constant_
 
     // ---- phase D: 5x5 tile min/max over valid pixels (corner_detector.cpp:42-53): column extrema, then 5 columns -----
     const bool edge_cta = (cx == 0) || (cy == 0) || (OW * cx + OW + 5 > geo.hw) || (OH * cy + OH + 5 > geo.hh);
-    if (tid < 180) {
+    if (tid < 360) {
       const int j = tid % 90;
       const int xh = OW * cx - 5 + j;
-      for (int ti = tid / 90; ti < CTY; ti += 2) {
+      for (int ti = tid / 90; ti < CTY; ti += 4) {
         const uint8_t* col = P + (5 * ti) * PP + POFF + j;
         int mn = 255, mx = 0;
         if (!edge_cta) {
