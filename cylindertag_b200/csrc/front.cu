@@ -147,7 +147,6 @@ __global__ void __launch_bounds__(front::NT) front_kernel(const __grid_constant_
   uint8_t* tmax = smem + L::tmax;
   uint8_t* cmn = smem + L::cmn;
   uint8_t* cmx = smem + L::cmx;
-  uint8_t* vthr = smem + L::vthr;
   uint8_t* thr16 = smem + L::thr16;
 
   if (tid == 0) {
@@ -295,32 +294,37 @@ __global__ void __launch_bounds__(front::NT) front_kernel(const __grid_constant_
 
     // ---- phase D: 5x5 tile min/max over valid pixels (corner_detector.cpp:42-53): column extrema, then 5 columns -----
     const bool edge_cta = (cx == 0) || (cy == 0) || (OW * cx + OW + 5 > geo.hw) || (OH * cy + OH + 5 > geo.hh);
-    if (tid < 360) {
-      const int j = tid % 90;
-      const int xh = OW * cx - 5 + j;
-      for (int ti = tid / 90; ti < CTY; ti += 4) {
-        const uint8_t* col = P + (5 * ti) * PP + POFF + j;
-        int mn = 255, mx = 0;
-        if (!edge_cta) {
+    {
+      // one thread per (tile row, aligned word of 4 patch columns): 5 word loads, byte-wise min/max in registers.
+      // Patch columns 8..103 (words 2..25) cover j = -3..92; the tile pass only reads j = 0..89.
+      const int wq = tid % 24;  // word index - 2
+      const uint8_t* colw = P + 8 + 4 * wq;
+      for (int ti = tid / 24; ti < CTY; ti += NT / 24) {
+        uint32_t mn = 0xFFFFFFFFu, mx = 0u;
 #pragma unroll
-          for (int dy = 0; dy < 5; ++dy) {
-            const int v = col[dy * PP];
-            mn = min(mn, v);
-            mx = max(mx, v);
-          }
-        } else {
+        for (int dy = 0; dy < 5; ++dy) {
+          const int i = 5 * ti + dy;
+          uint32_t v = *reinterpret_cast<const uint32_t*>(colw + i * PP);
+          if (edge_cta) {
+            // pixels outside the image do not take part (corner_detector.cpp:44 clips the window)
+            const int yh = OH * cy - 5 + i;
+            uint32_t keep = 0u;
+            if (yh >= 0 && yh < geo.hh) {
 #pragma unroll
-          for (int dy = 0; dy < 5; ++dy) {
-            const int yh = OH * cy - 5 + 5 * ti + dy;
-            if (yh >= 0 && yh < geo.hh && xh >= 0 && xh < geo.hw) {
-              const int v = col[dy * PP];
-              mn = min(mn, v);
-              mx = max(mx, v);
+              for (int b = 0; b < 4; ++b) {
+                const int xh = OW * cx - 8 + 4 * wq + b;
+                if (xh >= 0 && xh < geo.hw) keep |= 0xFFu << (8 * b);
+              }
             }
+            mn = __vminu4(mn, v | ~keep);
+            mx = __vmaxu4(mx, v & keep);
+          } else {
+            mn = __vminu4(mn, v);
+            mx = __vmaxu4(mx, v);
           }
         }
-        cmn[ti * 96 + j] = (uint8_t)mn;
-        cmx[ti * 96 + j] = (uint8_t)mx;
+        *reinterpret_cast<uint32_t*>(cmn + ti * 96 + 4 * wq) = mn;  // cmn/cmx column index = j + 3
+        *reinterpret_cast<uint32_t*>(cmx + ti * 96 + 4 * wq) = mx;
       }
     }
     __syncthreads();
@@ -329,8 +333,8 @@ __global__ void __launch_bounds__(front::NT) front_kernel(const __grid_constant_
       int mn = 255, mx = 0;
 #pragma unroll
       for (int dx = 0; dx < 5; ++dx) {
-        mn = min(mn, (int)cmn[ti * 96 + 5 * tj + dx]);
-        mx = max(mx, (int)cmx[ti * 96 + 5 * tj + dx]);
+        mn = min(mn, (int)cmn[ti * 96 + HOFF + 5 * tj + dx]);
+        mx = max(mx, (int)cmx[ti * 96 + HOFF + 5 * tj + dx]);
       }
       tmin[tid] = (uint8_t)mn;
       tmax[tid] = (uint8_t)mx;
@@ -358,14 +362,10 @@ __global__ void __launch_bounds__(front::NT) front_kernel(const __grid_constant_
         while (t > 0 && !(lut255(t - 1) < thr)) --t;
         while (t < 256 && lut255(t) < thr) ++t;
       }
-      vthr[tid] = (uint8_t)t;
-    }
-    __syncthreads();
-    // one threshold byte per owned pixel column and tile row: lets phase F compare 4 pixels per instruction group
-    if (tid < OW) {
-      const int tj = tid / 5;
+      // one threshold byte per owned pixel column of this tile: lets phase F compare 4 pixels per instruction group
+      uint8_t* dst = thr16 + oi * OW + 5 * oj;
 #pragma unroll
-      for (int oi = 0; oi < OTY; ++oi) thr16[oi * OW + tid] = vthr[oi * OTX + tj];
+      for (int q = 0; q < 5; ++q) dst[q] = (uint8_t)t;
     }
     __syncthreads();
 
