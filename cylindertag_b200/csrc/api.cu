@@ -59,6 +59,8 @@ struct Slot {
   size_t stage_bytes = 0;
   std::vector<void*> owned;  // device allocations of the workspace (freed together)
   uint8_t *d_gray = nullptr, *d_bin = nullptr, *d_quad_scratch = nullptr;
+  uint8_t *d_half = nullptr, *d_tiles = nullptr;  // generic-window front end only (allocated on first use)
+  size_t tiles_bytes = 0;
   size_t gray_fstride = 0, bin_fstride = 0;
   int *d_labels = nullptr, *d_st_area = nullptr, *d_st_x0 = nullptr, *d_st_y0 = nullptr, *d_st_x1 = nullptr,
       *d_st_y1 = nullptr, *d_roots_tmp = nullptr, *d_span_count = nullptr, *d_legal = nullptr, *d_counters = nullptr;
@@ -123,6 +125,8 @@ static void free_workspace(Slot* s) {
   // d_stage is managed separately (ensure_stage): it may hold the batch that is about to be processed
   for (void* p : s->owned) cudaFree(p);
   s->owned.clear();
+  s->d_half = s->d_tiles = nullptr;
+  s->tiles_bytes = 0;
   cudaFreeHost(s->h_summary);
   cudaFreeHost(s->h_packed);
   s->h_summary = nullptr;
@@ -220,9 +224,17 @@ static int ensure_stage(Slot* s, size_t bytes) {
 
 // Enqueues the whole detect path for one batch on slot `s` (frames already on the device).
 static int enqueue_on_slot(ctag_detector* d, Slot* s, const void* frames_dev, int n, int w, int h, size_t pitch,
-                           size_t frame_stride, int channels, int corner_subpix, int subpix_dist) {
+                           size_t frame_stride, int channels, int window, int corner_subpix, int subpix_dist) {
   int rc = ensure_workspace(d, s, n, w, h);
   if (rc != CTAG_OK) return rc;
+  if (window != kWin) {
+    if (!s->d_half) CTAG_CUDA_CHECK(slot_alloc(s, &s->d_half, s->bin_fstride * s->cap_frames));
+    const size_t need = 2 * (size_t)s->cap_frames * ((s->geo.hw + window - 1) / window) * ((s->geo.hh + window - 1) / window);
+    if (s->tiles_bytes < need) {
+      CTAG_CUDA_CHECK(slot_alloc(s, &s->d_tiles, need));  // the previous (smaller) buffer stays owned until the workspace is freed
+      s->tiles_bytes = need;
+    }
+  }
   s->n = n;
   s->channels = channels;
   s->subpix = corner_subpix;
@@ -238,10 +250,15 @@ static int enqueue_on_slot(ctag_detector* d, Slot* s, const void* frames_dev, in
   }
   cudaStream_t st = s->stream;
   CTAG_CUDA_CHECK(cudaEventRecord(s->ev[0], st));
-  rc = launch_front(frames_dev, n, s->geo, channels, pitch, frame_stride, s->d_gray, s->gray_fstride, s->d_bin,
-                    s->bin_fstride, st);
+  if (window == kWin) {
+    rc = launch_front(frames_dev, n, s->geo, channels, pitch, frame_stride, s->d_gray, s->gray_fstride, s->d_bin,
+                      s->bin_fstride, st);
+    s->launches += 1;
+  } else {
+    rc = launch_front_generic(frames_dev, n, s->geo, channels, pitch, frame_stride, window, s->d_gray, s->gray_fstride,
+                              s->d_half, s->d_tiles, s->d_bin, s->bin_fstride, st, &s->launches);
+  }
   if (rc != CTAG_OK) return rc;
-  s->launches += 1;
   CTAG_CUDA_CHECK(cudaEventRecord(s->ev[1], st));
   rc = launch_ccl(s->d_bin, s->bin_fstride, n, s->geo, s->d_labels, s->d_st_area, s->d_st_x0, s->d_st_y0, s->d_st_x1,
                   s->d_st_y1, s->d_roots_tmp, s->d_span_count, s->d_legal, s->legal_cap, s->d_counters, st, &s->launches);
@@ -308,7 +325,7 @@ static int check_args(ctag_detector* d, const void* frames, int n, int w, int h,
   if ((w & 1) || (h & 1)) return CTAG_ERR_ARG;  // exact 2x decimation needs even sizes
   if (w / 2 > 4095 || h / 2 > 4095) return CTAG_ERR_UNSUPPORTED;  // packed 12-bit coordinates in the trace stack
   if (channels != 1 && channels != 3) return CTAG_ERR_ARG;
-  if (adaptive_thresh != kWin) return CTAG_ERR_UNSUPPORTED;
+  if (adaptive_thresh < 1) return CTAG_ERR_ARG;
   if (corner_subpix && (subpix_dist < 0 || subpix_dist > 64)) return CTAG_ERR_ARG;
   if (decode_smem_bytes(d->rows, d->cols) > 200 * 1024) return CTAG_ERR_UNSUPPORTED;
   return CTAG_OK;
@@ -401,7 +418,7 @@ int ctag_detect_batch_enqueue(ctag_detector* d, const void* frames_dev, int n, i
   CTAG_CUDA_CHECK(cudaSetDevice(d->device));
   if (frame_stride == 0) frame_stride = pitch * (size_t)h;
   Slot* s = &d->slot[d->next_enqueue];
-  rc = enqueue_on_slot(d, s, frames_dev, n, w, h, pitch, frame_stride, channels, corner_subpix, subpix_dist);
+  rc = enqueue_on_slot(d, s, frames_dev, n, w, h, pitch, frame_stride, channels, adaptive_thresh, corner_subpix, subpix_dist);
   if (rc != CTAG_OK) return rc;
   d->next_enqueue = (d->next_enqueue + 1) % kSlots;
   d->in_flight += 1;
@@ -451,7 +468,7 @@ int ctag_detect_batch(ctag_detector* d, const void* frames, int n, int w, int h,
         CTAG_CUDA_CHECK(cudaMemcpy2DAsync(s->d_stage + dfs * f, dpitch,
                                           static_cast<const uint8_t*>(frames) + frame_stride * (queued + f), pitch,
                                           (size_t)w * channels, h, cudaMemcpyHostToDevice, s->stream));
-      rc = enqueue_on_slot(d, s, s->d_stage, c, w, h, dpitch, dfs, channels, corner_subpix, subpix_dist);
+      rc = enqueue_on_slot(d, s, s->d_stage, c, w, h, dpitch, dfs, channels, adaptive_thresh, corner_subpix, subpix_dist);
       if (rc != CTAG_OK) return rc;
       q_first[d->next_enqueue] = queued;
       q_count[d->next_enqueue] = c;

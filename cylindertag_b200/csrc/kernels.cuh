@@ -9,6 +9,12 @@ int launch_front(const void* frames_dev, int n, const FrameGeom& geo, int channe
                  uint8_t* gray_out, size_t gray_fstride, uint8_t* bin_out, size_t bin_fstride, cudaStream_t stream);
 int front_smem_bytes(int channels);
 
+// front_generic.cu: the same stages for an adaptiveThresh window other than 5 (three plain kernels, half-res image in HBM).
+// tile_buf needs 2 * n * ceil(hw/window) * ceil(hh/window) bytes, half_buf the size of the binary image.
+int launch_front_generic(const void* frames_dev, int n, const FrameGeom& g, int channels, size_t pitch, size_t frame_stride,
+                         int window, uint8_t* gray_out, size_t gray_fstride, uint8_t* half_buf, uint8_t* tile_buf,
+                         uint8_t* bin_out, size_t bin_fstride, cudaStream_t stream, int* launches);
+
 // K2/K3 (ccl.cu): block-based union-find labelling, stats, ordered legal-component list.
 // legal[frame][k] = {root, area, x0, y0, x1, y1}; counters[frame] = {n_components, n_legal, overflow, 0}.
 int launch_ccl(const uint8_t* bin, size_t bin_fstride, int n, const FrameGeom& g, int* labels, int* st_area, int* st_x0,

@@ -45,7 +45,7 @@ enum {
   CTAG_ERR_DICTIONARY = -3,  /* replaces `throw "... must between 0 to 63"` (CylinderTag.cpp:56-65) */
   CTAG_ERR_CUDA = -4,        /* CUDA runtime/driver failure; see ctag_last_error() */
   CTAG_ERR_NO_DEVICE = -5,   /* no usable sm_100 device: there is NO CPU fallback */
-  CTAG_ERR_UNSUPPORTED = -6, /* configuration outside the implemented envelope */
+  CTAG_ERR_UNSUPPORTED = -6, /* configuration outside the implemented envelope (half-res side > 4095, dictionary > 200 KB) */
   CTAG_ERR_CAPACITY = -7,    /* an internal device list overflowed its capacity */
   CTAG_ERR_ALIGNMENT = -8    /* device input not 16-byte aligned / pitch not a multiple of 16 */
 };

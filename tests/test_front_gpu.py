@@ -47,7 +47,23 @@ def test_bgr_gray_and_binary_bit_exact(detector, shape):
         assert np.array_equal(detector.debug_binary(f), oracle_binary(gray)), (shape, f)
 
 
-def test_unsupported_window_is_loud(detector, test_gray):
+@pytest.mark.parametrize("win", [3, 4, 7, 11])
+def test_generic_threshold_window(detector, test_gray, win):
+    """adaptiveThresh other than 5 goes through the unfused kernels; same bit-exact bar."""
+    rng = np.random.default_rng(win)
+    frames = np.stack([test_gray[:400, :640], np.clip(rng.normal(70, 45, (400, 640)), 0, 255).astype(np.uint8)])
+    detector.detect_batch(frames, win, False, 3)
+    for f in range(2):
+        half = o.half_resize(frames[f])
+        assert np.array_equal(detector.debug_binary(f), o.adaptive_threshold(o.convert_to_float(half), win)), (win, f)
+    bgr = rng.integers(0, 256, (1, 202, 326, 3), dtype=np.uint8)
+    detector.detect_batch(bgr, win, False, 3)
+    gray = o.bgr2gray(bgr[0])
+    assert np.array_equal(detector.debug_gray(0), gray)
+    assert np.array_equal(detector.debug_binary(0), o.adaptive_threshold(o.convert_to_float(o.half_resize(gray)), win))
+
+
+def test_bad_window_is_loud(detector, test_gray):
     from cylindertag_b200 import CtagError
     with pytest.raises(CtagError):
-        detector.detect_batch(test_gray[None, :64, :64], 7, False, 3)
+        detector.detect_batch(test_gray[None, :64, :64], 0, False, 3)
