@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--markers", type=int, default=6)
     ap.add_argument("--distinct", type=int, default=0, help="distinct rendered frames in the ring (0: 16 at 4K, 32 at 1080p)")
+    ap.add_argument("--channels", type=int, default=3, choices=[1, 3], help="3 = BGR frames (caller's cvtColor fused in), 1 = gray frames (detect's own contract)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -183,11 +184,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = (f"{a.res} ({w}x{h}) BGR synthetic frames, {a.markers} rendered 2f12c markers each, batch {a.batch} "
-                f"(ring of {a.distinct} distinct frames, batch input {a.batch * w * h * 3 / 1e6:.0f} MB vs 126 MB L2), "
-                f"detect(adaptiveThresh=5, cornerSubPix=true, dist=5) incl. the caller's BGR2GRAY")
+    cname = "BGR" if a.channels == 3 else "gray"
+    workload = (f"{a.res} ({w}x{h}) {cname} synthetic frames, {a.markers} rendered 2f12c markers each, batch {a.batch} "
+                f"(ring of {a.distinct} distinct frames, batch input {a.batch * w * h * a.channels / 1e6:.0f} MB vs 126 MB L2), "
+                f"detect(adaptiveThresh=5, cornerSubPix=true, dist=5)" + (" incl. the caller's BGR2GRAY" if a.channels == 3 else ""))
     config = {"workload": workload, "resolution": a.res, "batch": a.batch, "markers_per_frame": a.markers,
-              "channels": 3, "l2_policy": "inputs larger than L2", "frames_per_step_per_gpu": a.batch}
+              "channels": a.channels, "l2_policy": "inputs larger than L2", "frames_per_step_per_gpu": a.batch}
 
     if a.impl == "reference":
         if rank != 0:
@@ -232,16 +234,20 @@ def main():
     state, fs = load_dictionary()
     seeds = [2000 + rank * a.distinct + i for i in range(a.distinct)]
     distinct = render_frames(seeds, w, h, a.markers, min(8, max(1, (os.cpu_count() or 8) // max(world, 1))))
-    host = torch.empty((a.batch, h, w, 3), dtype=torch.uint8).pin_memory()
+    ch = a.channels
+    if ch == 1:
+        import cv2
+        distinct = [cv2.cvtColor(f, cv2.COLOR_BGR2GRAY) for f in distinct]
+    host = torch.empty((a.batch, h, w, 3) if ch == 3 else (a.batch, h, w), dtype=torch.uint8).pin_memory()
     for i in range(a.batch):
         host[i] = torch.from_numpy(distinct[i % a.distinct])
     frames = host.to(dev, non_blocking=False)
-    pitch, fstride = w * 3, w * h * 3
+    pitch, fstride = w * ch, w * h * ch
     det = Detector(state=state, feature_size=fs, device=local)
     cap = 16
 
     def step_device():
-        det.enqueue_device(frames.data_ptr(), a.batch, w, h, pitch, fstride, 3, 5, True, 5)
+        det.enqueue_device(frames.data_ptr(), a.batch, w, h, pitch, fstride, ch, 5, True, 5)
         return det.collect(cap)
 
     def barrier():
@@ -250,7 +256,7 @@ def main():
         torch.cuda.synchronize()
 
     def enqueue():
-        det.enqueue_device(frames.data_ptr(), a.batch, w, h, pitch, fstride, 3, 5, True, 5)
+        det.enqueue_device(frames.data_ptr(), a.batch, w, h, pitch, fstride, ch, 5, True, 5)
 
     for _ in range(a.warmup):
         markers, counts, info = step_device()
@@ -325,7 +331,7 @@ def main():
         parity = "skipped"
         try:
             from oracle import ctag_oracle as o
-            dump = o.detect(o.bgr2gray(distinct[0]), state, fs, 5, True, 5)
+            dump = o.detect(o.bgr2gray(distinct[0]) if ch == 3 else distinct[0], state, fs, 5, True, 5)
             got = markers[0][:int(counts[0])]
             ok = len(dump.markers) == int(counts[0]) and all(
                 int(g["marker_id"]) == m.markerID and list(g["feature_pos"][:len(m.featurePos)]) == m.featurePos and
@@ -336,7 +342,7 @@ def main():
             parity = f"error: {exc}"
         peak, peak_src = hbm_peak()
         front_ms = stage_acc["front"]
-        alg_bytes = 4.25 * w * h * a.batch
+        alg_bytes = (4.25 if ch == 3 else 1.25) * w * h * a.batch
         achieved = alg_bytes / (front_ms / 1000.0) / 1e9
         traffic = None
         try:
@@ -346,7 +352,7 @@ def main():
         line = {"metric": "detect_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8/int32 dense, f32/f64 sparse", "data": "synthetic", "config": config,
-                "roofline": {"bound": "hbm", "kernel": "front_kernel<3> (gray + cubic decimation + adaptive threshold)",
+                "roofline": {"bound": "hbm", "kernel": f"front_kernel<{ch}> (" + ("gray + " if ch == 3 else "") + "cubic decimation + adaptive threshold)",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                              "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                              "kernel_ms_per_launch": front_ms},
