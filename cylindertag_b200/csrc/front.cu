@@ -29,19 +29,21 @@ constexpr int HP = 96;               // pitch of the horizontal-pass buffer (row
 constexpr int PP = 112;              // pitch of the half-res patch (bytes)
 constexpr int POFF = 11;             // patch column of half-res column j (x = 80cx - 5 + j); owned pixels start at 16
 constexpr int HOFF = 3;              // the stencil passes run on j' = j + HOFF so that their 4-column groups are aligned
-constexpr int NT = 384;              // 12 warps per CTA, two CTAs per SM (shared memory bound)
+constexpr int NT = 384;              // 12 warps per CTA, three CTAs per SM (shared memory bound)
 constexpr int BOX = RW * RH;         // bytes of one TMA box
 constexpr int H_BYTES = (((RH / 2) * HP * 4 + 127) / 128) * 128;
 constexpr int P_BYTES = ((50 * PP + 127) / 128) * 128;
 
 template <int C>
 struct Layout {
-  // C==3: [bgr 3 boxes | g | HT | P | small]        (bgr is free for the next tile's TMA once g is built)
-  // C==1: [g0 | g1 | HT | P | small]                (gray tiles double-buffered)
+  // C==3: [bgr 3 boxes | P | small]   gray tile aliases box 0 (built through registers once every thread has read its
+  //                                   BGR bytes), HT aliases box 1: 67.5 KB per CTA, three CTAs per SM
+  // C==1: [g0 | g1 | HT | P | small]  (gray tiles double-buffered)
   static constexpr int bgr = 0;
-  static constexpr int g = (C == 3) ? 3 * BOX : 0;   // C==1: g0 at 0, g1 at BOX
-  static constexpr int h = (C == 3) ? 4 * BOX : 2 * BOX;
-  static constexpr int p = h + H_BYTES;
+  static constexpr int g = 0;                        // C==1: g0 at 0, g1 at BOX
+  static constexpr int h = (C == 3) ? BOX : 2 * BOX;
+  static constexpr int after_h = (C == 3) ? 3 * BOX : h + H_BYTES;
+  static constexpr int p = after_h;
   static constexpr int small_ = p + P_BYTES;
   static constexpr int tmin = small_;               // CTY*CTX bytes
   static constexpr int tmax = small_ + 192;         // CTY*CTX bytes
@@ -133,7 +135,7 @@ __device__ __forceinline__ void issue_tile_load(const CUtensorMap* tmap, uint32_
 }
 
 template <int C>
-__global__ void __launch_bounds__(front::NT) front_kernel(const __grid_constant__ CUtensorMap tmap, FrameGeom geo, TileGrid tg,
+__global__ void __launch_bounds__(front::NT, 3) front_kernel(const __grid_constant__ CUtensorMap tmap, FrameGeom geo, TileGrid tg,
                                                           uint8_t* __restrict__ gray_out, size_t gray_fstride,
                                                           uint8_t* __restrict__ bin_out, size_t bin_fstride) {
   using namespace front;
@@ -189,30 +191,34 @@ __global__ void __launch_bounds__(front::NT) front_kernel(const __grid_constant_
         // the box and the 128-bit store into the gray tile are free of bank conflicts.
         const int rest = tid >> 3;
         const int gq = (rest % 3) * 4 + (tid & 3);
-        int row = 2 * (rest / 3) + ((tid >> 2) & 1);  // rows row, row+32, ...
+        const int row = 2 * (rest / 3) + ((tid >> 2) & 1);  // rows row, row+32, row+64, row+96
         const uint8_t* src = smem + L::bgr + (gq >> 2) * BOX + (gq & 3) * 48 + row * RW;
         uint8_t* dst = g + gq * 16 + row * RW;
         const int x = x0r + gq * 16;
         const bool own_col = gq >= 1 && gq <= 10 && x < geo.w;
         uint8_t* gp = gray_out + (size_t)fr * gray_fstride + (ptrdiff_t)(y0r + row) * geo.gpitch + x;
-        for (; row < RH; row += NT / 12, src += (NT / 12) * RW, dst += (NT / 12) * RW, gp += (size_t)(NT / 12) * geo.gpitch) {
-          const uint4 a = reinterpret_cast<const uint4*>(src)[0], b = reinterpret_cast<const uint4*>(src)[1],
-                      c = reinterpret_cast<const uint4*>(src)[2];
-          uint4 o;
-          o.x = gray4(a.x, a.y, a.z);
-          o.y = gray4(a.w, b.x, b.y);
-          o.z = gray4(b.z, b.w, c.x);
-          o.w = gray4(c.y, c.z, c.w);
-          *reinterpret_cast<uint4*>(dst) = o;
-          if (own_col && row >= 11 && row < 11 + 2 * OH && y0r + row < geo.h) *reinterpret_cast<uint4*>(gp) = o;
+        constexpr int RS = NT / 12;  // row step
+        uint4 o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = row + u * RS;
+          if (r < RH) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(src + u * RS * RW);
+            const uint4 a = s4[0], b = s4[1], c = s4[2];
+            o[u].x = gray4(a.x, a.y, a.z);
+            o[u].y = gray4(a.w, b.x, b.y);
+            o[u].z = gray4(b.z, b.w, c.x);
+            o[u].w = gray4(c.y, c.z, c.w);
+            if (own_col && r >= 11 && r < 11 + 2 * OH && y0r + r < geo.h)
+              *reinterpret_cast<uint4*>(gp + (size_t)(u * RS) * geo.gpitch) = o[u];
+          }
         }
+        __syncthreads();  // every BGR byte has been read: the gray tile may overwrite box 0
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (row + u * RS < RH) *reinterpret_cast<uint4*>(dst + u * RS * RW) = o[u];
       }
       __syncthreads();
-      // the BGR staging buffer is free: start loading this CTA's next tile behind the stencil phases
-      if (tid == 0 && next < tg.ntiles) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue_tile_load<C>(&tmap, mbar0, smem_u32(smem + L::bgr), tg, next);
-      }
     }
 
     // ---- replicate-border patch (TMA zero-fills outside the image; INTER_CUBIC uses BORDER_REPLICATE) ---------
@@ -291,6 +297,14 @@ __global__ void __launch_bounds__(front::NT) front_kernel(const __grid_constant_
       }
     }
     __syncthreads();
+    if (C == 3) {
+      // the gray tile (box 0) and HT (box 1) are dead: load this CTA's next tile behind phases D-F; the other CTAs of
+      // the SM cover what remains of the latency
+      if (tid == 0 && next < tg.ntiles) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue_tile_load<C>(&tmap, mbar0, smem_u32(smem + L::bgr), tg, next);
+      }
+    }
 
     // ---- phase D: 5x5 tile min/max over valid pixels (corner_detector.cpp:42-53): column extrema, then 5 columns -----
     const bool edge_cta = (cx == 0) || (cy == 0) || (OW * cx + OW + 5 > geo.hw) || (OH * cy + OH + 5 > geo.hh);
