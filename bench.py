@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--distinct", type=int, default=0, help="distinct rendered frames in the ring (0: 16 at 4K, 32 at 1080p)")
     ap.add_argument("--channels", type=int, default=3, choices=[1, 3], help="3 = BGR frames (caller's cvtColor fused in), 1 = gray frames (detect's own contract)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--timeline", default="", help="write the stage timeline of the timed batches (ms, per batch) to this file")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
@@ -271,6 +272,7 @@ def main():
     sampler = ClockSampler(local)
     launches = 0
     n_markers = 0
+    timeline = []
     barrier()
     sampler.start()
     ev0.record(stream)  # both detector streams are idle here, so the event is stamped immediately
@@ -283,12 +285,19 @@ def main():
             enqueue()
             queued += 1
         markers, counts, info = det.collect(cap)
+        if a.timeline:
+            timeline.append(det.stage_timeline_ms())
         launches += det.launch_count()
         n_markers += int(counts.sum())
     ev1.record(stream)  # every collect synchronised its stream: stamped now, after the last batch finished
     barrier()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
+    if a.timeline and rank == 0:
+        with open(a.timeline, "w") as f:
+            f.write("# batch: start of front, ccl, quad, feature, decode, end (ms since detector creation)\n")
+            for i, row in enumerate(timeline):
+                f.write(f"{i} " + " ".join(f"{v:.3f}" for v in row) + "\n")
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -69,6 +69,7 @@ SIGNATURES = {
     "ctag_detect_batch_collect": (_I, [_P, _P, _I, _P, _P]),
     "ctag_max_in_flight": (_I, []),
     "ctag_stage_time_ms": (_I, [_P, ctypes.POINTER(ctypes.c_float)]),
+    "ctag_stage_timeline_ms": (_I, [_P, ctypes.POINTER(ctypes.c_float)]),
     "ctag_last_launch_count": (_I, [_P]),
     "ctag_stream": (_P, [_P]),
     "ctag_debug_get_gray": (_I, [_P, _I, _P, _SZ]),

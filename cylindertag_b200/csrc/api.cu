@@ -93,6 +93,8 @@ struct ctag_detector {
   int32_t* d_state = nullptr;
   uint16_t* d_pick_table = nullptr;  // cv::fitLine restart subsets per point count (fit_core.cuh)
   Slot slot[kSlots];
+  cudaEvent_t epoch = nullptr;  // recorded once at creation: origin of ctag_stage_timeline_ms
+  float stage_stamp_ms[CTAG_STAGE_COUNT + 1] = {};
   int next_enqueue = 0, next_collect = 0, in_flight = 0;
   int last = -1;  // slot of the most recently collected batch (debug getters, stage times)
   float stage_ms[CTAG_STAGE_COUNT] = {0, 0, 0, 0, 0};
@@ -289,6 +291,7 @@ static int collect_slot(ctag_detector* d, Slot* s, ctag_marker* out, int cap_per
   s->busy = false;
   CTAG_CUDA_CHECK(cudaStreamSynchronize(s->stream));
   for (int i = 0; i < CTAG_STAGE_COUNT; ++i) cudaEventElapsedTime(&d->stage_ms[i], s->ev[i], s->ev[i + 1]);
+  for (int i = 0; i <= CTAG_STAGE_COUNT; ++i) cudaEventElapsedTime(&d->stage_stamp_ms[i], d->epoch, s->ev[i]);
   d->last_launches = s->launches;
   int total = 0;
   for (int f = 0; f < s->n; ++f) total += s->h_summary[12 * f + 10];
@@ -356,6 +359,8 @@ int ctag_create(ctag_detector** out, const int32_t* state, int rows, int cols, i
             cudaMemcpy(d->d_state, state, sizeof(int32_t) * rows * cols, cudaMemcpyHostToDevice) == cudaSuccess &&
             cudaMalloc(&d->d_pick_table, table.size() * sizeof(uint16_t)) == cudaSuccess &&
             cudaMemcpy(d->d_pick_table, table.data(), table.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) == cudaSuccess;
+  ok = ok && cudaEventCreate(&d->epoch) == cudaSuccess && cudaEventRecord(d->epoch, 0) == cudaSuccess &&
+       cudaEventSynchronize(d->epoch) == cudaSuccess;
   for (Slot& s : d->slot) {
     ok = ok && cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
     for (auto& e : s.ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
@@ -392,6 +397,7 @@ void ctag_destroy(ctag_detector* d) {
       if (e) cudaEventDestroy(e);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
+  if (d->epoch) cudaEventDestroy(d->epoch);
   cudaFree(d->d_state);
   cudaFree(d->d_pick_table);
   delete d;
@@ -510,6 +516,12 @@ int ctag_detect(ctag_detector* d, const uint8_t* gray, int w, int h, size_t pitc
 int ctag_stage_time_ms(const ctag_detector* d, float* ms_out) {
   if (!d || !ms_out) return CTAG_ERR_ARG;
   for (int i = 0; i < CTAG_STAGE_COUNT; ++i) ms_out[i] = d->stage_ms[i];
+  return CTAG_OK;
+}
+
+int ctag_stage_timeline_ms(const ctag_detector* d, float* ms_out) {
+  if (!d || !ms_out) return CTAG_ERR_ARG;
+  for (int i = 0; i <= CTAG_STAGE_COUNT; ++i) ms_out[i] = d->stage_stamp_ms[i];
   return CTAG_OK;
 }
 

@@ -114,14 +114,27 @@ __device__ __forceinline__ float lut255(int v) { return __fmul_rn((float)v, (flo
 
 struct TileGrid {
   int tiles_x, tiles_y, tiles_per_frame, ntiles;
+  uint32_t m_frame, m_row;  // floor(2^32 / tiles_per_frame), floor(2^32 / tiles_x)
 };
+
+// tile -> (frame, tile row, tile column) without integer division: the multiply-high quotient with the floored
+// reciprocal is at most one too small for any 32-bit dividend, one compare fixes it.
+__device__ __forceinline__ void tile_coords(const TileGrid& tg, int tile, int& fr, int& cy, int& cx) {
+  uint32_t q = __umulhi((uint32_t)tile, tg.m_frame);
+  uint32_t rem = (uint32_t)tile - q * (uint32_t)tg.tiles_per_frame;
+  if (rem >= (uint32_t)tg.tiles_per_frame) { ++q; rem -= (uint32_t)tg.tiles_per_frame; }
+  uint32_t r = __umulhi(rem, tg.m_row);
+  uint32_t c = rem - r * (uint32_t)tg.tiles_x;
+  if (c >= (uint32_t)tg.tiles_x) { ++r; c -= (uint32_t)tg.tiles_x; }
+  fr = (int)q; cy = (int)r; cx = (int)c;
+}
 
 template <int C>
 __device__ __forceinline__ void issue_tile_load(const CUtensorMap* tmap, uint32_t mbar, uint32_t dst, const TileGrid& tg,
                                                 int tile) {
   using namespace front;
-  const int fr = tile / tg.tiles_per_frame, rem = tile - fr * tg.tiles_per_frame;
-  const int cy = rem / tg.tiles_x, cx = rem - cy * tg.tiles_x;
+  int fr, cy, cx;
+  tile_coords(tg, tile, fr, cy, cx);
   const int x0r = 2 * OW * cx - 16, y0r = 2 * OH * cy - 11;
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(C * BOX) : "memory");
 #pragma unroll
@@ -164,8 +177,8 @@ __global__ void __launch_bounds__(front::NT, 3) front_kernel(const __grid_consta
   // C==3: one staging buffer + one barrier, parity flips per tile.  C==1: buffers/barriers alternate, parity flips
   // every second tile.
   for (int it = 0; tile < tg.ntiles; tile += gridDim.x, ++it) {
-    const int fr = tile / tg.tiles_per_frame, rem = tile - fr * tg.tiles_per_frame;
-    const int cy = rem / tg.tiles_x, cx = rem - cy * tg.tiles_x;
+    int fr, cy, cx;
+    tile_coords(tg, tile, fr, cy, cx);
     const int x0r = 2 * OW * cx - 16;  // full-res x of region column 0
     const int y0r = 2 * OH * cy - 11;  // full-res y of region row 0
     const int buf = (C == 1) ? (it & 1) : 0;
@@ -314,11 +327,14 @@ __global__ void __launch_bounds__(front::NT, 3) front_kernel(const __grid_consta
       const int wq = tid % 24;  // word index - 2
       const uint8_t* colw = P + 8 + 4 * wq;
       for (int ti = tid / 24; ti < CTY; ti += NT / 24) {
-        uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+        // byte-wise min/max through the native 16x2 three-input min/max on the even and odd bytes (the 8x4 video
+        // intrinsics are emulated on sm_100)
+        uint32_t ve[5], vo[5], xe[5], xo[5];
 #pragma unroll
         for (int dy = 0; dy < 5; ++dy) {
           const int i = 5 * ti + dy;
-          uint32_t v = *reinterpret_cast<const uint32_t*>(colw + i * PP);
+          const uint32_t v = *reinterpret_cast<const uint32_t*>(colw + i * PP);
+          uint32_t lo = v, hi = v;
           if (edge_cta) {
             // pixels outside the image do not take part (corner_detector.cpp:44 clips the window)
             const int yh = OH * cy - 5 + i;
@@ -330,13 +346,19 @@ __global__ void __launch_bounds__(front::NT, 3) front_kernel(const __grid_consta
                 if (xh >= 0 && xh < geo.hw) keep |= 0xFFu << (8 * b);
               }
             }
-            mn = __vminu4(mn, v | ~keep);
-            mx = __vmaxu4(mx, v & keep);
-          } else {
-            mn = __vminu4(mn, v);
-            mx = __vmaxu4(mx, v);
+            lo = v | ~keep;
+            hi = v & keep;
           }
+          ve[dy] = lo & 0x00FF00FFu;
+          vo[dy] = __byte_perm(lo, 0u, 0x4341);
+          xe[dy] = hi & 0x00FF00FFu;
+          xo[dy] = __byte_perm(hi, 0u, 0x4341);
         }
+        const uint32_t mne = __vimin3_u16x2(__vimin3_u16x2(ve[0], ve[1], ve[2]), ve[3], ve[4]);
+        const uint32_t mno = __vimin3_u16x2(__vimin3_u16x2(vo[0], vo[1], vo[2]), vo[3], vo[4]);
+        const uint32_t mxe = __vimax3_u16x2(__vimax3_u16x2(xe[0], xe[1], xe[2]), xe[3], xe[4]);
+        const uint32_t mxo = __vimax3_u16x2(__vimax3_u16x2(xo[0], xo[1], xo[2]), xo[3], xo[4]);
+        const uint32_t mn = __byte_perm(mne, mno, 0x6240), mx = __byte_perm(mxe, mxo, 0x6240);
         *reinterpret_cast<uint32_t*>(cmn + ti * 96 + 4 * wq) = mn;  // cmn/cmx column index = j + 3
         *reinterpret_cast<uint32_t*>(cmx + ti * 96 + 4 * wq) = mx;
       }
@@ -451,6 +473,8 @@ static int launch_front_t(const CUtensorMap& tmap, int n, const FrameGeom& geo, 
   tg.tiles_y = (geo.hh + OH - 1) / OH;
   tg.tiles_per_frame = tg.tiles_x * tg.tiles_y;
   tg.ntiles = tg.tiles_per_frame * n;
+  tg.m_frame = tg.tiles_per_frame > 1 ? (uint32_t)((1ull << 32) / (uint64_t)tg.tiles_per_frame) : 0xFFFFFFFFu;
+  tg.m_row = tg.tiles_x > 1 ? (uint32_t)((1ull << 32) / (uint64_t)tg.tiles_x) : 0xFFFFFFFFu;
   int grid = sms * per_sm;  // persistent: one wave of resident CTAs
   if (grid > tg.ntiles) grid = tg.ntiles;
   front_kernel<C><<<grid, NT, Layout<C>::total, stream>>>(tmap, geo, tg, gray_out, gray_fstride, bin_out, bin_fstride);

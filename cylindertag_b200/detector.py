@@ -108,6 +108,12 @@ class Detector:
         C.check(self._lib.ctag_stage_time_ms(self._h, ms), "ctag_stage_time_ms")
         return dict(zip(C.STAGE_NAMES, [float(v) for v in ms]))
 
+    def stage_timeline_ms(self):
+        """Stage boundaries (ms since the detector was created) of the most recent collected batch."""
+        ms = (ctypes.c_float * (len(C.STAGE_NAMES) + 1))()
+        C.check(self._lib.ctag_stage_timeline_ms(self._h, ms), "ctag_stage_timeline_ms")
+        return [float(v) for v in ms]
+
     def launch_count(self):
         return int(self._lib.ctag_last_launch_count(self._h))
 

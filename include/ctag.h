@@ -148,6 +148,9 @@ enum {
 
 /* GPU time (ms, CUDA events on the detector's stream) of each stage in the most recent collected batch. */
 CTAG_API int ctag_stage_time_ms(const ctag_detector* det, float* ms_out /* CTAG_STAGE_COUNT */);
+/* Start of every stage and end of the last one (ms since the detector was created, same events) for the most recent
+ * collected batch: with several batches in flight these show how the stages of different batches overlap. */
+CTAG_API int ctag_stage_timeline_ms(const ctag_detector* det, float* ms_out /* CTAG_STAGE_COUNT + 1 */);
 /* Number of kernel launches issued by the most recent batch. */
 CTAG_API int ctag_last_launch_count(const ctag_detector* det);
 /* CUDA stream (cudaStream_t) the detector launches on, for callers that time with their own events. */
