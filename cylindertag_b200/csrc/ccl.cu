@@ -103,29 +103,65 @@ __global__ void __launch_bounds__(256) ccl_local_kernel(const uint8_t* __restric
     return;
   }
   const int l0 = ty * 32 + 4 * tq;  // tile-local index of the first owned block
+  // Horizontal runs first: block i is glued to block i-1 when the right column of i-1 and the left column of i both
+  // hold a pixel (any such pair is 8-adjacent).  Every block starts out pointing at the first block of its run, so
+  // the union-find below only links runs of adjacent rows and its chains stay shorter than the tile height instead
+  // of growing with the blob area.
+  int left3 = __shfl_up_sync(0xffffffffu, p4[3], 1);
+  if (tq == 0) left3 = 0;
+  uint32_t glue = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
+    const int prev = k ? p4[k - 1] : left3;
+    if ((p4[k] & 5) && (prev & 10)) glue |= 1u << k;
+  }
+  uint32_t H = glue << (4 * tq);  // the row's 32 glue bits: OR over the eight lanes of the row
+  H |= __shfl_xor_sync(0xffffffffu, H, 1);
+  H |= __shfl_xor_sync(0xffffffffu, H, 2);
+  H |= __shfl_xor_sync(0xffffffffu, H, 4);
+  int head[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = 4 * tq + k;
+    const uint32_t z = ~H & ((2u << i) - 1u);  // bit 0 of H is never set, so z != 0
+    head[k] = ty * 32 + 31 - __clz(z);
     pat[l0 + k] = (uint8_t)p4[k];
-    L[l0 + k] = p4[k] ? l0 + k : -1;
+    L[l0 + k] = p4[k] ? head[k] : -1;
   }
   __syncthreads();
+  // Links to the row above.  Many blocks of a run touch the same upper run; a link is skipped when a block further
+  // left (or the block's own N link) already implies it, so that a solid blob costs one union per row.
+  {
+    int right0 = __shfl_down_sync(0xffffffffu, p4[0], 1);
+    if (tq == 7) right0 = 0;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int p = p4[k], l = l0 + k, tx = 4 * tq + k;
-    if (p) {
-      if (ty > 0) {
-        int q = pat[l - 32];
-        if ((p & 3) && (q & 12)) uf_unite(L, l, l - 32);
-        if (tx > 0 && (p & 1) && (pat[l - 33] & 8)) uf_unite(L, l, l - 33);
-        if (tx < 31 && (p & 2) && (pat[l - 31] & 4)) uf_unite(L, l, l - 31);
+    for (int k = 0; k < 4; ++k) {
+      const int p = p4[k], l = l0 + k, tx = 4 * tq + k;
+      if (p && ty > 0) {
+        const int pm1 = k ? p4[k - 1] : left3, pp1 = k < 3 ? p4[k + 1] : right0;
+        const int q = pat[l - 32], qm = tx > 0 ? pat[l - 33] : 0, qp = tx < 31 ? pat[l - 31] : 0;
+        const bool gl = (H >> tx) & 1u, gr = tx < 31 && ((H >> (tx + 1)) & 1u);
+        const bool gu = (q & 5) && (qm & 10), gur = (qp & 5) && (q & 10);
+        const bool vn = (p & 3) && (q & 12), vnl = (pm1 & 3) && (qm & 12), vnr = (pp1 & 3) && (qp & 12);
+        const bool vnw = (p & 1) && (qm & 8), vne = (p & 2) && (qp & 4);
+        if (vn && !(gl && gu && vnl)) uf_unite(L, l, l - 32);
+        if (vnw && !(vn && gu) && !(gl && vnl)) uf_unite(L, l, l - 33);
+        if (vne && !(vn && gur) && !(gr && vnr)) uf_unite(L, l, l - 31);
       }
-      if (tx > 0 && (p & 5) && (pat[l - 1] & 10)) uf_unite(L, l, l - 1);
     }
   }
   __syncthreads();
+  // run heads look their root up and publish it; everybody else reads it from the head
   int r4[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) r4[k] = p4[k] ? uf_find(L, l0 + k) : -1;
+  for (int k = 0; k < 4; ++k) r4[k] = (p4[k] && head[k] == l0 + k) ? uf_find(L, l0 + k) : -1;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (p4[k] && head[k] == l0 + k) L[l0 + k] = r4[k];
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) r4[k] = p4[k] ? L[head[k]] : -1;
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < 4; ++k) {

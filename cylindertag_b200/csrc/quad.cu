@@ -82,10 +82,11 @@ __global__ void quad_prefix_kernel(const int* __restrict__ counters, int n, int*
 // lists in shared memory; large ones use the warp's global scratch (same code, different pointers).  Components with
 // four edges append a FitRec and copy their clusters to the point pool.
 constexpr int kEdgeWarps = 4;
+constexpr int kEdgeCtasPerSm = 8;  // the serial trace is latency bound: more resident warps, 64 registers each
 constexpr int kSmemPts = 256;       // points per list on the shared-memory fast path
 constexpr int kSmemVisWords = 256;  // bit-map words on the shared-memory fast path
 
-__global__ void __launch_bounds__(32 * kEdgeWarps) quad_edges_kernel(
+__global__ void __launch_bounds__(32 * kEdgeWarps, kEdgeCtasPerSm) quad_edges_kernel(
     int n_frames, FrameGeom g, const uint8_t* __restrict__ bin, size_t bin_fstride, const int* __restrict__ labels,
     const int* __restrict__ legal, int legal_cap, const int* __restrict__ prefix, int* __restrict__ qctl,
     uint8_t* __restrict__ scratch, QuadScratchLayout L, int* __restrict__ quad_status, FitRec* __restrict__ fits, int fit_cap,
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(32) quad_compact_kernel(const int* __restrict_
 size_t quad_fitrec_bytes() { return sizeof(FitRec); }
 size_t quad_fitresult_bytes() { return sizeof(FitResult); }
 size_t quad_traj_bytes_per_cta() { return sizeof(WelschIter) * 600; }
-int quad_edge_warps(int sms) { return sms * 4 * kEdgeWarps; }  // persistent: 4 CTAs x 4 warps per SM
+int quad_edge_warps(int sms) { return sms * kEdgeCtasPerSm * kEdgeWarps; }  // persistent warps
 int quad_exact_ctas(int sms) { return sms * 8; }
 void quad_build_pick_table(uint16_t* host_table, int max_count) { welsch_pick_table(host_table, max_count); }
 

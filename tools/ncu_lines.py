@@ -1,9 +1,10 @@
 """Per-CUDA-source-line hot spots from an .ncu-rep (needs -lineinfo + --import-source on).
-Usage: ncu_lines.py report.ncu-rep [top_n]"""
+Usage: ncu_lines.py report.ncu-rep [top_n] [kernel-name regex]"""
 import csv, io, subprocess, sys
 rep = sys.argv[1]
 topn = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
+kf = ["--kernel-name", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []
+txt = subprocess.run(["ncu", "-i", rep] + kf + ["--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
 cur_file = None
 hdr = None
