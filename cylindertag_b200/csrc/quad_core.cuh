@@ -69,6 +69,13 @@ CT_HD int w_sum_i(int v) {
   return v;
 #endif
 }
+CT_HD int popc32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+  return __popc(v);
+#else
+  return __builtin_popcount(v);
+#endif
+}
 CT_HD int w_bcast_i(int v, int src) {
 #ifdef __CUDA_ARCH__
   return __shfl_sync(0xffffffffu, v, src);
@@ -389,34 +396,92 @@ CT_HD void quad_stage_edges(const CompView& cv, const QuadScratch& sc, Lanes ln,
   // The ray-cast's `if (visited) break` can never fire before the first mask pixel (visited is a subset of mask), so
   // the result is the union of the top/bottom pixel of every column and the left/right pixel of every row.
   for (int i = ln.id; i < h * wpr; i += ln.n) sc.vis[i] = 0;
-  for (int x = ln.id; x < w; x += ln.n) sc.col_top[x] = -1, sc.col_bot[x] = -1;
-  w_sync();
-  for (int y = 0; y < h; ++y) {
-    int lmin = 0x7fffffff, lmax = -1;
-    for (int x = ln.id; x < w; x += ln.n) {
-      if (in_comp(cv, x, y)) {
-        if (sc.col_top[x] < 0) sc.col_top[x] = (int16_t)y;
-        sc.col_bot[x] = (int16_t)y;
-        lmin = x < lmin ? x : lmin;
-        lmax = x > lmax ? x : lmax;
+#ifdef __CUDA_ARCH__
+  const int xa = cv.x0 & ~3;  // 4-pixel aligned start: one binary word and two block labels per lane and row
+  if (ln.n == 32 && cv.x1 - xa < 128) {
+    // boxes up to 128 aligned columns (nearly all quads): four columns per lane, column extents in registers
+    w_sync();
+    const int cx0 = xa + 4 * ln.id;
+    uint32_t cmask = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if (cx0 + b >= cv.x0 && cx0 + b <= cv.x1) cmask |= 1u << b;
+    const bool second = (cx0 >> 1) + 1 < cv.bw;
+    int top[4] = {-1, -1, -1, -1}, bot[4] = {-1, -1, -1, -1};
+#pragma unroll 2
+    for (int y = 0; y < h; ++y) {
+      const int ay = cv.y0 + y;
+      uint32_t m = 0;
+      if (cmask) {
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(cv.bin + (size_t)ay * cv.bpitch + cx0);
+        const int* lb = cv.labels + (ay >> 1) * cv.bw + (cx0 >> 1);
+        const bool in0 = lb[0] == cv.root, in1 = second && lb[1] == cv.root;
+        m = (((v & 0x000000FFu) && in0) ? 1u : 0u) | (((v & 0x0000FF00u) && in0) ? 2u : 0u) |
+            (((v & 0x00FF0000u) && in1) ? 4u : 0u) | (((v & 0xFF000000u) && in1) ? 8u : 0u);
+        m &= cmask;
+      }
+      int lmin = m ? cx0 + __ffs(m) - 1 : 0x7fffffff, lmax = m ? cx0 + 31 - __clz(m) : -1;
+      lmin = w_min_i(lmin);
+      lmax = w_max_i(lmax);
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (m & (1u << b)) {
+          if (top[b] < 0) top[b] = y;
+          bot[b] = y;
+        }
+      if (ln.id == 0 && lmax >= 0) {
+        lmin -= cv.x0, lmax -= cv.x0;
+        sc.vis[y * wpr + (lmin >> 5)] |= 1u << (lmin & 31);
+        sc.vis[y * wpr + (lmax >> 5)] |= 1u << (lmax & 31);
       }
     }
-    lmin = w_min_i(lmin);
-    lmax = w_max_i(lmax);
-    if (ln.id == 0 && lmax >= 0) {
-      sc.vis[y * wpr + (lmin >> 5)] |= 1u << (lmin & 31);
-      sc.vis[y * wpr + (lmax >> 5)] |= 1u << (lmax & 31);
+    w_sync();
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int x = cx0 + b - cv.x0;
+      if (top[b] >= 0) {
+        bit_or(&sc.vis[top[b] * wpr + (x >> 5)], 1u << (x & 31));
+        bit_or(&sc.vis[bot[b] * wpr + (x >> 5)], 1u << (x & 31));
+      }
+      if (x == 0) sc.col_top[0] = (int16_t)top[b];
     }
-  }
-  w_sync();
-  for (int x = ln.id; x < w; x += ln.n) {
-    int t = sc.col_top[x], b = sc.col_bot[x];
-    if (t >= 0) {
-      bit_or(&sc.vis[t * wpr + (x >> 5)], 1u << (x & 31));
-      bit_or(&sc.vis[b * wpr + (x >> 5)], 1u << (x & 31));
+    w_sync();
+  } else
+#endif
+  {
+    for (int x = ln.id; x < w; x += ln.n) sc.col_top[x] = -1, sc.col_bot[x] = -1;
+    w_sync();
+    for (int y = 0; y < h; ++y) {
+      int lmin = 0x7fffffff, lmax = -1;
+      for (int x = ln.id; x < w; x += ln.n) {
+        if (in_comp(cv, x, y)) {
+          if (sc.col_top[x] < 0) sc.col_top[x] = (int16_t)y;
+          sc.col_bot[x] = (int16_t)y;
+          lmin = x < lmin ? x : lmin;
+          lmax = x > lmax ? x : lmax;
+        }
+      }
+      lmin = w_min_i(lmin);
+      lmax = w_max_i(lmax);
+      if (ln.id == 0 && lmax >= 0) {
+        sc.vis[y * wpr + (lmin >> 5)] |= 1u << (lmin & 31);
+        sc.vis[y * wpr + (lmax >> 5)] |= 1u << (lmax & 31);
+      }
     }
+    w_sync();
+    for (int x = ln.id; x < w; x += ln.n) {
+      int t = sc.col_top[x], b = sc.col_bot[x];
+      if (t >= 0) {
+        bit_or(&sc.vis[t * wpr + (x >> 5)], 1u << (x & 31));
+        bit_or(&sc.vis[b * wpr + (x >> 5)], 1u << (x & 31));
+      }
+    }
+    w_sync();
   }
-  w_sync();
+  // pixels on the bit map: once the trace has consumed them all, unwinding its stack cannot find anything new
+  int remaining = 0;
+  for (int i = ln.id; i < h * wpr; i += ln.n) remaining += popc32(sc.vis[i]);
+  remaining = w_sum_i(remaining);
 
   // ---- 2. start pixel + oriented trace (corner_detector.cpp:235-247, 407-418) -------------------------------------
   // get_orientedEdgePoints follows 8-neighbours in the order N,NE,E,SE,S,SW,W,NW, recursing on every hit; after the
@@ -429,7 +494,8 @@ CT_HD void quad_stage_edges(const CompView& cv, const QuadScratch& sc, Lanes ln,
     int fx = 0, fy = sc.col_top[0], fj = 0, sp = 0;
     P[n++] = pt_pack(fx + cv.x0, fy + cv.y0);
     sc.vis[fy * wpr] &= ~1u;
-    while (true) {
+    --remaining;
+    while (remaining > 0) {
       // Directions fj..7 are probed at a fixed position and the bit map only changes inside a recursive call, so
       // the first hit is the first set bit of the 8-neighbour mask at or after fj.
       uint32_t m = fj < 8 ? (nbr_mask(sc.vis, wpr, h, fx, fy) >> fj) : 0u;
@@ -450,6 +516,7 @@ CT_HD void quad_stage_edges(const CompView& cv, const QuadScratch& sc, Lanes ln,
       P[n++] = pt_pack(nx + cv.x0, ny + cv.y0);
       sc.stack[sp++] = nx | (ny << 12) | ((j + 1) << 24);  // caller resumes at direction j+1 from the new position
       fx = nx, fy = ny, fj = 0;
+      --remaining;
     }
   }
   w_sync();
