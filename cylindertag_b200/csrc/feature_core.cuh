@@ -124,10 +124,76 @@ struct EdgeMoments {  // one weighting of one edge
 };
 CT_HD void em_zero(EdgeMoments& m) { m.Mx = m.My = m.Mxx = m.Mxy = m.Myy = m.N = 0; }
 
-// Samples s = first, first+step, ... of the edge a->b; accumulates both weightings (1-alpha: "next", alpha: "last").
+// Accumulates one located sample (bestx, besty) into both weightings (1-alpha: "next", alpha: "last").
+CT_HD void em_add(EdgeMoments& nextm, EdgeMoments& lastm, double bestx, double besty, double alpha) {
+  double wn = 1 - alpha, wl = alpha;
+  nextm.Mx += bestx * wn;
+  nextm.My += besty * wn;
+  nextm.Mxx += bestx * bestx * wn;
+  nextm.Mxy += bestx * besty * wn;
+  nextm.Myy += besty * besty * wn;
+  nextm.N += wn;
+  lastm.Mx += bestx * wl;
+  lastm.My += besty * wl;
+  lastm.Mxx += bestx * bestx * wl;
+  lastm.Mxy += bestx * besty * wl;
+  lastm.Myy += besty * besty * wl;
+  lastm.N += wl;
+}
+
+// Samples s = first, first+step, ... of the edge a->b; accumulates both weightings.
 // The reference runs the identical sampling twice, once per weighting (:605-679 vs :681-755).
+// Along the normal it compares the pixels at offsets n+1 and n-1 for n = -win..win step 1/4: both belong to the one
+// ladder m = -(win+1)..(win+1) step 1/4, so every pixel is located and read once (n+1 = m, n-1 = m-2 = 8 steps back)
+// and kept in a 9-entry ring; the arithmetic per pixel and the order of the sums are the reference's.
+template <int WIN>
+CT_HD void edge_samples_w(const uint8_t* gray, int pitch, int cols, int rows, float ax, float ay, float bx, float by,
+                          int first, int step, double nx, double ny, int nsamples, EdgeMoments& nextm, EdgeMoments& lastm) {
+  constexpr int NM = 8 * WIN + 9;
+  for (int s = first; s < nsamples; s += step) {
+    double alpha = (15.0 + s) / (nsamples + 30);
+    double x0 = alpha * ax + (1 - alpha) * bx;
+    double y0 = alpha * ay + (1 - alpha) * by;
+    double Mn = 0, Mcount = 0;
+    float ring[9];
+    bool okr[9];
+#pragma unroll 1
+    for (int blk = 0; blk < NM; blk += 9) {  // ring slot = i mod 9 is a compile-time constant inside the body
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        const int i = blk + j;
+        if (i < NM) {
+          const double m = -(double)(WIN + 1) + 0.25 * i;
+          const int x = (int)(x0 + m * nx);
+          const int y = (int)(y0 + m * ny);
+          const bool ok = !(x < 0 || x >= cols || y < 0 || y >= rows);
+          const float gv = ok ? lut255f(gray[(size_t)y * pitch + x]) : 0.f;
+          if (i >= 8) {
+            const double n = m - 1;
+            const float g1 = gv, g2 = ring[(j + 1) % 9];
+            if (ok && okr[(j + 1) % 9] && !(g1 < g2)) {
+              double weight = (g2 - g1) * (g2 - g1);
+              Mn += weight * n;
+              Mcount += weight;
+            }
+          }
+          ring[j] = gv;
+          okr[j] = ok;
+        }
+      }
+    }
+    if (Mcount == 0) continue;
+    double n0 = Mn / Mcount;
+    em_add(nextm, lastm, x0 + n0 * nx, y0 + n0 * ny, alpha);
+  }
+}
+
 CT_HD void edge_samples(const uint8_t* gray, int pitch, int cols, int rows, float ax, float ay, float bx, float by, int win,
                         int first, int step, double nx, double ny, int nsamples, EdgeMoments& nextm, EdgeMoments& lastm) {
+  if (win == 5) {  // main.cpp's detect(..., 5, true, 5)
+    edge_samples_w<5>(gray, pitch, cols, rows, ax, ay, bx, by, first, step, nx, ny, nsamples, nextm, lastm);
+    return;
+  }
   const double range = win;
   for (int s = first; s < nsamples; s += step) {
     double alpha = (15.0 + s) / (nsamples + 30);
@@ -150,20 +216,7 @@ CT_HD void edge_samples(const uint8_t* gray, int pitch, int cols, int rows, floa
     }
     if (Mcount == 0) continue;
     double n0 = Mn / Mcount;
-    double bestx = x0 + n0 * nx, besty = y0 + n0 * ny;
-    double wn = 1 - alpha, wl = alpha;
-    nextm.Mx += bestx * wn;
-    nextm.My += besty * wn;
-    nextm.Mxx += bestx * bestx * wn;
-    nextm.Mxy += bestx * besty * wn;
-    nextm.Myy += besty * besty * wn;
-    nextm.N += wn;
-    lastm.Mx += bestx * wl;
-    lastm.My += besty * wl;
-    lastm.Mxx += bestx * bestx * wl;
-    lastm.Mxy += bestx * besty * wl;
-    lastm.Myy += besty * besty * wl;
-    lastm.N += wl;
+    em_add(nextm, lastm, x0 + n0 * nx, y0 + n0 * ny, alpha);
   }
 }
 
