@@ -181,85 +181,109 @@ CT_HD int welsch_restart_visit(PtFn pt, int count, Rng rng_at_restart, Visitor& 
   return welsch_restart_from_picks(pt, count, picked, np, visit);
 }
 
+// State of one restart between iterations (lets a GPU lane interleave restarts of different fits).
+struct WelschState {
+  float line[4], prev[4];
+  int i;     // next iteration
+  int nvis;  // iterates reported so far
+};
+
+// Initial line of a restart: plain moments of its (sorted) subset.
+template <typename PtFn>
+CT_HD void welsch_init(PtFn pt, const int* picked, int np, WelschState& st) {
+  double x = 0, y = 0, x2 = 0, y2 = 0, xy = 0, w = 0;
+  for (int a = 0; a < np; ++a) {
+    int p = pt(picked[a]);
+    float px = (float)pt_x(p), py = (float)pt_y(p);
+    x += px;
+    y += py;
+    x2 += px * px;
+    y2 += py * py;
+    xy += px * py;
+    w += 1.0f;
+  }
+  line_from_moments(x, y, x2, y2, xy, w, st.line);
+  st.prev[0] = st.prev[1] = st.prev[2] = st.prev[3] = 0.f;
+  st.i = 0;
+  st.nvis = 0;
+}
+
+// One iteration of the reweighting loop; returns false when the restart is over (converged or 30 iterations done).
+// `wcache` holds kWelschCache floats of thread-private scratch.
 template <typename PtFn, typename Visitor>
-CT_HD int welsch_restart_from_picks(PtFn pt, int count, const int* picked, int np, Visitor& visit) {
-  float line[4], prev[4] = {0, 0, 0, 0};
-  {
-    double x = 0, y = 0, x2 = 0, y2 = 0, xy = 0, w = 0;
-    for (int a = 0; a < np; ++a) {
-      int p = pt(picked[a]);
-      float px = (float)pt_x(p), py = (float)pt_y(p);
-      x += px;
-      y += py;
-      x2 += px * px;
-      y2 += py * py;
-      xy += px * py;
-      w += 1.0f;
+CT_HD bool welsch_step(PtFn pt, int count, WelschState& st, float* wcache, Visitor& visit) {
+  float* line = st.line;
+  float* prev = st.prev;
+  if (st.i >= 30) return false;
+  if (st.i > 0) {
+    double t = line[0] * prev[0] + line[1] * prev[1];
+    t = t > -1. ? t : -1.;
+    t = t < 1. ? t : 1.;
+    if (fabs(acos(t)) < 0.01f) {
+      float dx = (float)fabs(line[2] - prev[2]);
+      float dy = (float)fabs(line[3] - prev[3]);
+      float d = dx > dy ? dx : dy;
+      if (d < 0.01f) return false;
     }
-    line_from_moments(x, y, x2, y2, xy, w, line);
   }
   const float c = 1 / 2.9846f;
-  float wcache[kWelschCache];
-  int nvis = 0;
-  for (int i = 0; i < 30; ++i) {
-    if (i > 0) {
-      double t = line[0] * prev[0] + line[1] * prev[1];
-      t = t > -1. ? t : -1.;
-      t = t < 1. ? t : 1.;
-      if (fabs(acos(t)) < 0.01f) {
-        float dx = (float)fabs(line[2] - prev[2]);
-        float dy = (float)fabs(line[3] - prev[3]);
-        float d = dx > dy ? dx : dy;
-        if (d < 0.01f) break;
-      }
-    }
-    // residuals, error, raw weights.  For clusters of up to kWelschCache points the raw weights are kept (thread-local
-    // array) so that the refit pass does not have to evaluate exp again; larger clusters recompute them.
-    const float px0 = line[2], py0 = line[3], nx = line[1], ny = -line[0];
-    double err = 0, sum_w = 0;
-    const bool cached = count <= kWelschCache;
-    // unrolled so that the (independent) exp evaluations of neighbouring points overlap; the accumulations keep the
-    // library's order
+  // residuals, error, raw weights.  For clusters of up to kWelschCache points the raw weights are kept (thread-local
+  // array) so that the refit pass does not have to evaluate exp again; larger clusters recompute them.
+  const float px0 = line[2], py0 = line[3], nx = line[1], ny = -line[0];
+  double err = 0, sum_w = 0;
+  const bool cached = count <= kWelschCache;
+  // unrolled so that the (independent) exp evaluations of neighbouring points overlap; the accumulations keep the
+  // library's order
 #pragma unroll 4
-    for (int j = 0; j < count; ++j) {
-      int p = pt(j);
-      float x = (float)pt_x(p) - px0, y = (float)pt_y(p) - py0;
-      float r = (float)fabs(nx * x + ny * y);
-      err += r;
-      float wr = welsch_exp(-r * r * c * c);
-      if (cached) wcache[j] = wr;
-      sum_w += wr;
-    }
-    visit(nvis, err, line);
-    ++nvis;
-    // normalised weights + refit
-    double x = 0, y = 0, x2 = 0, y2 = 0, xy = 0, wsum = 0;
-    const bool norm = fabs(sum_w) > 1.1920928955078125e-07;
-    const double inv = norm ? 1. / sum_w : 0.;
-#pragma unroll 4
-    for (int j = 0; j < count; ++j) {
-      int p = pt(j);
-      float fx = (float)pt_x(p), fy = (float)pt_y(p);
-      float wr;
-      if (cached) {
-        wr = wcache[j];
-      } else {
-        float xx = fx - px0, yy = fy - py0;
-        float r = (float)fabs(nx * xx + ny * yy);
-        wr = welsch_exp(-r * r * c * c);
-      }
-      float w = norm ? (float)(wr * inv) : 1.f;
-      x += w * fx;
-      y += w * fy;
-      x2 += w * fx * fx;
-      y2 += w * fy * fy;
-      xy += w * fx * fy;
-      wsum += w;
-    }
-    prev[0] = line[0], prev[1] = line[1], prev[2] = line[2], prev[3] = line[3];
-    line_from_moments(x, y, x2, y2, xy, wsum, line);
+  for (int j = 0; j < count; ++j) {
+    int p = pt(j);
+    float x = (float)pt_x(p) - px0, y = (float)pt_y(p) - py0;
+    float r = (float)fabs(nx * x + ny * y);
+    err += r;
+    float wr = welsch_exp(-r * r * c * c);
+    if (cached) wcache[j] = wr;
+    sum_w += wr;
   }
-  return nvis;
+  visit(st.nvis, err, line);
+  ++st.nvis;
+  // normalised weights + refit
+  double x = 0, y = 0, x2 = 0, y2 = 0, xy = 0, wsum = 0;
+  const bool norm = fabs(sum_w) > 1.1920928955078125e-07;
+  const double inv = norm ? 1. / sum_w : 0.;
+#pragma unroll 4
+  for (int j = 0; j < count; ++j) {
+    int p = pt(j);
+    float fx = (float)pt_x(p), fy = (float)pt_y(p);
+    float wr;
+    if (cached) {
+      wr = wcache[j];
+    } else {
+      float xx = fx - px0, yy = fy - py0;
+      float r = (float)fabs(nx * xx + ny * yy);
+      wr = welsch_exp(-r * r * c * c);
+    }
+    float w = norm ? (float)(wr * inv) : 1.f;
+    x += w * fx;
+    y += w * fy;
+    x2 += w * fx * fx;
+    y2 += w * fy * fy;
+    xy += w * fx * fy;
+    wsum += w;
+  }
+  prev[0] = line[0], prev[1] = line[1], prev[2] = line[2], prev[3] = line[3];
+  line_from_moments(x, y, x2, y2, xy, wsum, line);
+  ++st.i;
+  return true;
+}
+
+template <typename PtFn, typename Visitor>
+CT_HD int welsch_restart_from_picks(PtFn pt, int count, const int* picked, int np, Visitor& visit) {
+  WelschState st;
+  welsch_init(pt, picked, np, st);
+  float wcache[kWelschCache];
+  while (welsch_step(pt, count, st, wcache, visit)) {
+  }
+  return st.nvis;
 }
 
 // Visitor that stores the whole trajectory (exact library bookkeeping through welsch_combine).

@@ -33,8 +33,9 @@ void quad_build_pick_table(uint16_t* host_table, int max_count);
 int launch_quad(int n, const FrameGeom& g, const uint8_t* bin, size_t bin_fstride, const int* labels, const int* legal,
                 int legal_cap, const int* counters, int* prefix, int* qctl, uint8_t* scratch, int edge_warps, void* fits,
                 int fit_cap, int* pool, int pool_cap, const uint16_t* pick_table, int table_max, void* results,
-                int* exact_list, void* traj, int exact_ctas, int sms, float* lines, int* quad_status, float* quad_corners,
-                int quad_cap, float* quads, int* quad_comp, int* n_quads, cudaStream_t stream, int* launches);
+                int* exact_list, int* fit_order, void* traj, int exact_ctas, int sms, float* lines, int* quad_status,
+                float* quad_corners, int quad_cap, float* quads, int* quad_comp, int* n_quads, cudaStream_t stream,
+                int* launches);
 
 // K5/K6 (feature.cu): quad pairing, coordinate lift, edge refinement.  fstate[frame] = {status, n_features,
 // n_features going on, overflow}.

@@ -52,7 +52,7 @@ static QuadScratchLayout make_layout(const FrameGeom& g) {
 size_t quad_scratch_bytes_per_warp(const FrameGeom& g) { return make_layout(g).total; }  // per persistent CTA
 
 // control words of the quad stage (device ints)
-enum { QC_WORK_EDGES = 0, QC_EXACT_COUNT = 1, QC_FIT_COUNT = 2, QC_POOL_CURSOR = 3, QC_OVERFLOW = 4, QC_WORDS = 8 };
+enum { QC_WORK_EDGES = 0, QC_EXACT_COUNT = 1, QC_FIT_COUNT = 2, QC_POOL_CURSOR = 3, QC_OVERFLOW = 4, QC_WORK_FIT = 5, QC_WORDS = 8 };
 
 // Component that reached four edges: what the line fits and the corner selection need.
 struct FitRec {
@@ -217,35 +217,120 @@ __device__ __forceinline__ int load_picks(const uint16_t* __restrict__ table, in
   return np;
 }
 
-__global__ void __launch_bounds__(128) quad_fit_kernel(const int* __restrict__ qctl, const FitRec* __restrict__ fits,
+// Fit edges sorted by point count, largest first (counting sort, one CTA): the lanes of a warp then walk clusters of
+// similar size, and the long restarts start first instead of forming the tail of the fit kernel.
+__global__ void __launch_bounds__(1024) quad_fitorder_kernel(const int* __restrict__ qctl, const FitRec* __restrict__ fits,
+                                                              int fit_cap, int* __restrict__ order) {
+  __shared__ int hist[1024];
+  __shared__ int wsum[32];
+  int nfit = qctl[QC_FIT_COUNT];
+  if (nfit > fit_cap) nfit = fit_cap;
+  const int nedge = 4 * nfit, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  hist[tid] = 0;
+  __syncthreads();
+  for (int e = tid; e < nedge; e += 1024) {
+    const FitRec* fr = fits + (e >> 2);
+    const int cnt = fr->cl_off[(e & 3) + 1] - fr->cl_off[e & 3];
+    atomicAdd(&hist[1023 - (cnt < 1023 ? cnt : 1023)], 1);
+  }
+  __syncthreads();
+  // exclusive scan of the 1024 buckets
+  const int v = hist[tid];
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = wsum[lane];
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += u;
+    }
+    wsum[lane] = winc - w;
+  }
+  __syncthreads();
+  hist[tid] = wsum[warp] + inc - v;
+  __syncthreads();
+  for (int e = tid; e < nedge; e += 1024) {
+    const FitRec* fr = fits + (e >> 2);
+    const int cnt = fr->cl_off[(e & 3) + 1] - fr->cl_off[e & 3];
+    order[atomicAdd(&hist[1023 - (cnt < 1023 ? cnt : 1023)], 1)] = e;
+  }
+}
+
+// Restarts converge after anything between 2 and 30 iterations, and fits with at most 10 points run a single restart:
+// a lane that handled one restart from start to end would idle most of the time.  Instead every lane keeps the state of
+// its current restart, all lanes advance by one iteration per trip, and a lane whose restart is over takes the next one
+// from the global counter right away.
+__global__ void __launch_bounds__(128) quad_fit_kernel(int* __restrict__ qctl, const FitRec* __restrict__ fits,
                                                        int fit_cap, const int* __restrict__ pool,
                                                        const uint16_t* __restrict__ pick_table, int table_max,
-                                                       FitResult* __restrict__ results) {
+                                                       const int* __restrict__ order, FitResult* __restrict__ results) {
   int nfit = qctl[QC_FIT_COUNT];
   if (nfit > fit_cap) nfit = fit_cap;
   const int total = 80 * nfit;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-    const int slot = t / 80, r = t - 80 * slot, c = r / 20, k = r - 20 * c;
-    const FitRec* fr = fits + slot;
-    const int count = fr->cl_off[c + 1] - fr->cl_off[c];
-    WelschBest best;
-    best.err = 1.7976931348623157e308;
-    best.eps = count * 1.1920928955078125e-07;
-    best.sub_eps = false;
-    best.line[0] = best.line[1] = best.line[2] = best.line[3] = 0.f;
-    // <= 10 points: every restart starts from all points and follows the same trajectory; restart 0 stands for all
-    if (count > 10 || k == 0) {
-      int picked[10];
-      const int np = load_picks(pick_table, table_max, count, k, picked);
-      PoolPts pa{pool + fr->pool_off + fr->cl_off[c]};
-      welsch_restart_from_picks(pa, count, picked, np, best);
+  const int lane = threadIdx.x & 31;
+  float wcache[kWelschCache];
+  WelschState st;
+  WelschBest best;
+  PoolPts pa{pool};
+  int t = 0, count = 0;
+  bool have = false, drained = false;
+  while (true) {
+    // refill: lanes without a restart draw consecutive items (one atomic per warp and trip)
+    while (true) {
+      const unsigned need = __ballot_sync(0xffffffffu, !have && !drained);
+      if (need == 0) break;
+      int base = 0;
+      if (lane == __ffs(need) - 1) base = atomicAdd(&qctl[QC_WORK_FIT], __popc(need));
+      base = __shfl_sync(0xffffffffu, base, __ffs(need) - 1);
+      if (!have && !drained) {
+        const int u = base + __popc(need & ((1u << lane) - 1u));  // position in the sorted work list
+        if (u >= total) {
+          drained = true;
+        } else {
+          const int ei = u / 20, k = u - 20 * ei, e = order[ei], slot = e >> 2, c = e & 3;
+          t = 20 * e + k;  // results stay indexed by (component, edge, restart)
+          const FitRec* fr = fits + slot;
+          count = fr->cl_off[c + 1] - fr->cl_off[c];
+          best.err = 1.7976931348623157e308;
+          best.eps = count * 1.1920928955078125e-07;
+          best.sub_eps = false;
+          best.line[0] = best.line[1] = best.line[2] = best.line[3] = 0.f;
+          // <= 10 points: every restart starts from all points and follows the same trajectory; restart 0 stands for all
+          if (count > 10 || k == 0) {
+            int picked[10];
+            const int np = load_picks(pick_table, table_max, count, k, picked);
+            pa.p = pool + fr->pool_off + fr->cl_off[c];
+            welsch_init(pa, picked, np, st);
+            have = true;
+          } else {
+            FitResult o;
+            o.err = best.err;
+            o.line[0] = o.line[1] = o.line[2] = o.line[3] = 0.f;
+            o.sub_eps = 0;
+            o.pad = 0;
+            results[t] = o;
+          }
+        }
+      }
     }
-    FitResult o;
-    o.err = best.err;
-    o.line[0] = best.line[0], o.line[1] = best.line[1], o.line[2] = best.line[2], o.line[3] = best.line[3];
-    o.sub_eps = best.sub_eps ? 1 : 0;
-    o.pad = 0;
-    results[t] = o;
+    if (__all_sync(0xffffffffu, !have)) break;
+    if (have && !welsch_step(pa, count, st, wcache, best)) {
+      FitResult o;
+      o.err = best.err;
+      o.line[0] = best.line[0], o.line[1] = best.line[1], o.line[2] = best.line[2], o.line[3] = best.line[3];
+      o.sub_eps = best.sub_eps ? 1 : 0;
+      o.pad = 0;
+      results[t] = o;
+      have = false;
+    }
   }
 }
 
@@ -371,15 +456,17 @@ void quad_build_pick_table(uint16_t* host_table, int max_count) { welsch_pick_ta
 int launch_quad(int n, const FrameGeom& g, const uint8_t* bin, size_t bin_fstride, const int* labels, const int* legal,
                 int legal_cap, const int* counters, int* prefix, int* qctl, uint8_t* scratch, int edge_warps, void* fits,
                 int fit_cap, int* pool, int pool_cap, const uint16_t* pick_table, int table_max, void* results,
-                int* exact_list, void* traj, int exact_ctas, int sms, float* lines, int* quad_status, float* quad_corners,
-                int quad_cap, float* quads, int* quad_comp, int* n_quads, cudaStream_t stream, int* launches) {
+                int* exact_list, int* fit_order, void* traj, int exact_ctas, int sms, float* lines, int* quad_status,
+                float* quad_corners, int quad_cap, float* quads, int* quad_comp, int* n_quads, cudaStream_t stream,
+                int* launches) {
   QuadScratchLayout L = make_layout(g);
   quad_prefix_kernel<<<1, 32, 0, stream>>>(counters, n, prefix, qctl);
   quad_edges_kernel<<<edge_warps / kEdgeWarps, 32 * kEdgeWarps, 0, stream>>>(
       n, g, bin, bin_fstride, labels, legal, legal_cap, prefix, qctl, scratch, L, quad_status, static_cast<FitRec*>(fits),
       fit_cap, pool, pool_cap);
-  quad_fit_kernel<<<sms * 16, 128, 0, stream>>>(qctl, static_cast<const FitRec*>(fits), fit_cap, pool, pick_table, table_max,
-                                                static_cast<FitResult*>(results));
+  quad_fitorder_kernel<<<1, 1024, 0, stream>>>(qctl, static_cast<const FitRec*>(fits), fit_cap, fit_order);
+  quad_fit_kernel<<<sms * 8, 128, 0, stream>>>(qctl, static_cast<const FitRec*>(fits), fit_cap, pool, pick_table, table_max,
+                                                fit_order, static_cast<FitResult*>(results));
   quad_fitmerge_kernel<<<(4 * fit_cap + 127) / 128, 128, 0, stream>>>(qctl, fit_cap, static_cast<const FitResult*>(results),
                                                                      lines, exact_list);
   quad_fitexact_kernel<<<exact_ctas, 32, 0, stream>>>(qctl, exact_list, static_cast<const FitRec*>(fits), pool, pick_table,
@@ -389,7 +476,7 @@ int launch_quad(int n, const FrameGeom& g, const uint8_t* bin, size_t bin_fstrid
   quad_compact_kernel<<<n, 32, 0, stream>>>(counters, legal_cap, quad_status, quad_corners, quad_cap, quads, quad_comp,
                                             n_quads);
   CTAG_CUDA_CHECK(cudaGetLastError());
-  if (launches) *launches += 7;
+  if (launches) *launches += 8;
   return CTAG_OK;
 }
 
