@@ -263,12 +263,14 @@ __global__ void __launch_bounds__(front::NT, 3) front_kernel(const __grid_consta
       {
         const uint8_t* src = g + (2 * rp) * RW + 8 * k;
         uint32_t* dst = HT + rp * HP + 4 * k;
+        // the word in front of k == 0 and the word behind k == 23 only feed the unused columns j' = 0 and 95: those
+        // two loads are redirected to a word of the thread's own span so that nothing outside the row (and outside
+        // the buffer) is read, without a branch
+        const int o0 = k ? -4 : 0, o3 = k < 23 ? 8 : 4;
         for (; rp < RH / 2; rp += NT / 24, src += 2 * (NT / 24) * RW, dst += (NT / 24) * HP) {
-          // the word in front of k == 0 and the word behind k == 23 only feed the unused columns j' = 0 and 95: do not
-          // read outside the row (and outside the buffer)
-          const uint32_t a0 = k ? *reinterpret_cast<const uint32_t*>(src - 4) : 0u, a3 = k < 23 ? *reinterpret_cast<const uint32_t*>(src + 8) : 0u;
+          const uint32_t a0 = *reinterpret_cast<const uint32_t*>(src + o0), a3 = *reinterpret_cast<const uint32_t*>(src + o3);
           const uint2 a12 = *reinterpret_cast<const uint2*>(src);
-          const uint32_t b0 = k ? *reinterpret_cast<const uint32_t*>(src + RW - 4) : 0u, b3 = k < 23 ? *reinterpret_cast<const uint32_t*>(src + RW + 8) : 0u;
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(src + RW + o0), b3 = *reinterpret_cast<const uint32_t*>(src + RW + o3);
           const uint2 b12 = *reinterpret_cast<const uint2*>(src + RW);
           const int h0 = dp4a_us(__byte_perm(a0, a12.x, 0x6543), COEF, 0), g0 = dp4a_us(__byte_perm(b0, b12.x, 0x6543), COEF, 0);
           const int h1 = dp4a_us(__byte_perm(a12.x, a12.y, 0x4321), COEF, 0), g1 = dp4a_us(__byte_perm(b12.x, b12.y, 0x4321), COEF, 0);
