@@ -70,6 +70,8 @@ SIGNATURES = {
     "ctag_max_in_flight": (_I, []),
     "ctag_stage_time_ms": (_I, [_P, ctypes.POINTER(ctypes.c_float)]),
     "ctag_stage_timeline_ms": (_I, [_P, ctypes.POINTER(ctypes.c_float)]),
+    "ctag_estimate_pose": (_I, [_P, _P, _I, _P, _P, _I, _P, _P, _P]),
+    "ctag_pose_select_points": (_I, [_P, _P, _P, _I]),
     "ctag_last_launch_count": (_I, [_P]),
     "ctag_stream": (_P, [_P]),
     "ctag_debug_get_gray": (_I, [_P, _I, _P, _SZ]),

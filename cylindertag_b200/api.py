@@ -2,9 +2,9 @@
 
 Same method names and argument meaning as the reference: construct from a `.marker` file or a state matrix, `detect`,
 `loadModel`, `loadCamera`, `estimatePose`, `drawAxis`.  `detect` runs entirely in the CUDA library (C ABI, include/ctag.h);
-`estimatePose` stays on the host as in the reference (CylinderTag.cpp:198-209, pose_estimation.cpp:50-143): OpenCV
-EPnP for the start, then a Levenberg-Marquardt refinement of the pinhole reprojection error on undistorted points
-(the reference uses Ceres; scipy's LM minimises the same 2-residual cost).
+`estimatePose` stays on the host as in the reference (CylinderTag.cpp:198-209, pose_estimation.cpp:50-143) and runs in
+the same library (ctag_estimate_pose, csrc/pose.cpp): EPnP for the start, then a Levenberg-Marquardt refinement of the
+pinhole reprojection error on undistorted points (the reference uses OpenCV's EPnP and Ceres on the same cost).
 """
 from __future__ import annotations
 
@@ -49,6 +49,7 @@ class PoseInfo:  # header/pose_estimation.h:22-25
     markerID: int = -1  # INDEX into the model list, not the dictionary row (pose_estimation.cpp:59,69)
     rvec: np.ndarray = None
     tvec: np.ndarray = None
+    rms_px: float = float("nan")  # reprojection RMS of the refined pose (not in the reference struct)
 
 
 def marker_from_record(rec) -> MarkerInfo:
@@ -186,27 +187,38 @@ def select_pose_points(mk: MarkerInfo, model: ModelInfo):
     return np.array(img_pts, np.float32).reshape(-1, 2), np.array(obj_pts, np.float32).reshape(-1, 3)
 
 
+def marker_to_record(mk: MarkerInfo):
+    """MarkerInfo -> ctag_marker record (the fields the pose stage reads)."""
+    rec = np.zeros((), C.MARKER_DTYPE)
+    n = len(mk.cornerLists)
+    rec["marker_id"], rec["n_features"] = mk.markerID, n
+    rec["feature_pos"][:] = -1
+    rec["feature_pos"][:n] = mk.featurePos[:n]
+    rec["feature_id"][:n] = mk.feature_ID[:n]
+    rec["id_left"][:n] = mk.feature_ID_left[:n]
+    rec["id_right"][:n] = mk.feature_ID_right[:n]
+    rec["corners"][:n] = np.asarray(mk.cornerLists, np.float32).reshape(n, 8, 2)
+    return rec
+
+
 def pnp_solver(mk: MarkerInfo, models, camera: CamInfo) -> PoseInfo:
-    """PoseEstimator::PnPSolver + PoseBA (pose_estimation.cpp:50-128)."""
-    import cv2
-    from scipy.optimize import least_squares
+    """PoseEstimator::PnPSolver + PoseBA (pose_estimation.cpp:50-128) through the library's host-side pose stage
+    (ctag_estimate_pose: corner selection, undistortion, EPnP, Levenberg-Marquardt; csrc/pose.cpp)."""
+    import ctypes
     idx = next((j for j, m in enumerate(models) if m.MarkerID == mk.markerID), -1)
     if idx < 0:
         return PoseInfo(-1)
-    img_pts, obj_pts = select_pose_points(mk, models[idx])
-    K = camera.Intrinsic.astype(np.float64)
-    D = camera.distCoeffs.astype(np.float64)
-    ok, rvec, tvec = cv2.solvePnP(obj_pts.astype(np.float64), img_pts.astype(np.float64), K, D, flags=cv2.SOLVEPNP_EPNP)
-    und = cv2.undistortPoints(img_pts.reshape(-1, 1, 2).astype(np.float64), K, D, P=K).reshape(-1, 2)
-    fx, fy, cx, cy = float(np.float32(K[0, 0])), float(np.float32(K[1, 1])), float(np.float32(K[0, 2])), float(np.float32(K[1, 2]))
-    X = obj_pts.astype(np.float64)
-
-    def resid(p):
-        R, _ = cv2.Rodrigues(p[:3])
-        Pc = X @ R.T + p[3:]
-        u = fx * Pc[:, 0] / Pc[:, 2] + cx
-        v = fy * Pc[:, 1] / Pc[:, 2] + cy
-        return np.concatenate([u - und[:, 0], v - und[:, 1]])
-
-    sol = least_squares(resid, np.concatenate([rvec.reshape(3), tvec.reshape(3)]), method="lm", xtol=1e-12, ftol=1e-15, gtol=1e-15)
-    return PoseInfo(idx, sol.x[:3].copy(), sol.x[3:].copy())
+    lib = C.load()
+    rec = marker_to_record(mk)
+    corners3 = np.ascontiguousarray(models[idx].corners, np.float32)
+    K = np.ascontiguousarray(camera.Intrinsic, np.float32).reshape(9)
+    D = np.ascontiguousarray(camera.distCoeffs, np.float32).reshape(-1)
+    rvec, tvec = np.zeros(3, np.float64), np.zeros(3, np.float64)
+    rms = ctypes.c_double(0)
+    rc = lib.ctag_estimate_pose(rec.ctypes.data, corners3.ctypes.data, corners3.shape[0], K.ctypes.data, D.ctypes.data,
+                                int(D.size), rvec.ctypes.data, tvec.ctypes.data, ctypes.addressof(rms))
+    if rc != C.OK:
+        return PoseInfo(-1)
+    p = PoseInfo(idx, rvec, tvec)
+    p.rms_px = float(rms.value)
+    return p

@@ -134,6 +134,22 @@ CTAG_API int ctag_detect_batch_enqueue(ctag_detector* det, const void* frames_de
 CTAG_API int ctag_detect_batch_collect(ctag_detector* det, ctag_marker* out, int cap_per_frame, int* n_out, ctag_frame_info* info);
 CTAG_API int ctag_max_in_flight(void);
 
+/* ---- pose stage (host code, no GPU work) --------------------------------------- */
+
+/* Replaces PoseEstimator::PnPSolver + PoseBA (pose_estimation.cpp:50-143; called from CylinderTag::estimatePose,
+ * CylinderTag.cpp:198-209) for one marker: corner selection (pose_estimation.cpp:72-95), 5-coefficient undistortion
+ * (:97-101), EPnP initial pose (:103) and Levenberg-Marquardt on the pinhole reprojection residual (:14-41,105-128).
+ *   model_corners  [n_model_corners][3] floats of the marker's reconstructed model, index = featurePos * 8 + k
+ *                  (.model layout, CylinderTag.cpp:168-188)
+ *   intrinsic      3x3 row-major camera matrix, dist: k1 k2 p1 p2 k3 (cameraParams.yml, both dt: f)
+ *   rvec, tvec     3 doubles each: x_cam = R(rvec) x_model + tvec;  rms_px (optional): reprojection RMS in pixels
+ * Returns CTAG_ERR_ARG when fewer than 4 corners qualify or a corner has no model point. */
+CTAG_API int ctag_estimate_pose(const ctag_marker* marker, const float* model_corners, int n_model_corners,
+                                const float* intrinsic, const float* dist, int n_dist, double* rvec, double* tvec,
+                                double* rms_px);
+/* The corner selection alone: fills (feature index, corner index 0..7) pairs, returns their number. */
+CTAG_API int ctag_pose_select_points(const ctag_marker* marker, int* feature_of_point, int* corner_of_point, int cap);
+
 /* ---- instrumentation ------------------------------------------------------------------------ */
 
 /* Stage identifiers for ctag_stage_time_ms / ctag_debug_*. */

@@ -10,8 +10,10 @@
 //   loadCamera(path, camera)                  CylinderTag.cpp:192-196 (OpenCV YAML 1.0, cameraMatrix + distCoeffs)
 // The build image has no OpenCV C++ headers, so minimal stand-in types are defined here; define CTAG_WITH_OPENCV
 // before including to get cv::Mat / cv::Point2f based overloads instead.
-// estimatePose / drawAxis are host-side and outside the CUDA hot path; the Python mirror
-// (cylindertag_b200.CylinderTag) implements estimatePose, this header declares the data types they exchange.
+//   estimatePose(img, markers, models, camera, poses, useDensePoseRefine)   CylinderTag.cpp:198-209
+//       (host side, ctag_estimate_pose: corner selection, undistortion, EPnP, Levenberg-Marquardt; markers without a
+//        model are erased from the result like the reference's markerID == -1 poses)
+// drawAxis is a debugging overlay; the Python mirror (cylindertag_b200.CylinderTag) has it.
 #pragma once
 #include <cstdint>
 #include <cstdio>
@@ -79,6 +81,101 @@ struct PoseInfo {
   double rvec[3] = {0, 0, 0}, tvec[3] = {0, 0, 0};
 };
 
+// CylinderTag::loadModel (CylinderTag.cpp:161-190): `model_num model_size`, then per model ID, base, axis and
+// 8 * model_size rows `corner_index x y z`.
+inline void load_model(const std::string& path, std::vector<ModelInfo>& reconstruct_model) {
+  std::ifstream in(path);
+  if (!in.is_open()) throw std::string("loadModel, could not open the model file\n");
+  int model_num = 0, model_size = 0;
+  in >> model_num >> model_size;
+  reconstruct_model.assign(model_num, ModelInfo());
+  for (int i = 0; i < model_num; ++i) {
+    ModelInfo& m = reconstruct_model[i];
+    in >> m.MarkerID >> m.base.x >> m.base.y >> m.base.z >> m.axis.x >> m.axis.y >> m.axis.z;
+    m.corners.assign((size_t)model_size * 8, Point3f());
+    for (int j = 0; j < 8 * model_size; ++j) {
+      int id = 0;
+      Point3f p;
+      in >> id >> p.x >> p.y >> p.z;
+      if (id >= 0 && id < 8 * model_size) m.corners[id] = p;
+    }
+  }
+}
+
+// one `data: [ ... ]` matrix of an OpenCV YAML 1.0 file
+inline std::vector<float> yaml_matrix(const std::string& txt, const std::string& key) {
+  std::vector<float> out;
+  size_t p = txt.find(key);
+  if (p == std::string::npos) return out;
+  size_t a = txt.find('[', p), b = txt.find(']', a);
+  if (a == std::string::npos || b == std::string::npos) return out;
+  std::string body = txt.substr(a + 1, b - a - 1);
+  for (char& ch : body)
+    if (ch == ',' || ch == '\n') ch = ' ';
+  std::stringstream ss(body);
+  double v;
+  while (ss >> v) out.push_back((float)v);  // dt: f
+  return out;
+}
+
+// CylinderTag::loadCamera (CylinderTag.cpp:192-196)
+inline void load_camera(const std::string& path, CamInfo& camera) {
+  std::ifstream in(path);
+  std::stringstream ss;
+  ss << in.rdbuf();
+  const std::string txt = ss.str();
+  std::vector<float> k = yaml_matrix(txt, "cameraMatrix"), dcf = yaml_matrix(txt, "distCoeffs");
+  for (size_t i = 0; i < 9 && i < k.size(); ++i) camera.Intrinsic[i] = k[i];
+  camera.distCoeffs = dcf;
+}
+
+// ctag_marker view of a MarkerInfo (the fields the pose stage reads)
+inline ctag_marker to_record(const MarkerInfo& m) {
+  ctag_marker c = ctag_marker();
+  c.marker_id = m.markerID;
+  const int n = (int)m.cornerLists.size() < CTAG_MAX_FEATURES ? (int)m.cornerLists.size() : CTAG_MAX_FEATURES;
+  c.n_features = n;
+  for (int k = 0; k < CTAG_MAX_FEATURES; ++k) c.feature_pos[k] = -1;
+  for (int k = 0; k < n; ++k) {
+    c.feature_pos[k] = k < (int)m.featurePos.size() ? m.featurePos[k] : -1;
+    c.feature_id[k] = k < (int)m.feature_ID.size() ? m.feature_ID[k] : -1;
+    c.id_left[k] = k < (int)m.feature_ID_left.size() ? m.feature_ID_left[k] : -1;
+    c.id_right[k] = k < (int)m.feature_ID_right.size() ? m.feature_ID_right[k] : -1;
+    for (int q = 0; q < 8 && q < (int)m.cornerLists[k].size(); ++q)
+      c.corners[k][q][0] = m.cornerLists[k][q].x, c.corners[k][q][1] = m.cornerLists[k][q].y;
+  }
+  return c;
+}
+
+// PoseEstimator::PnPSolver + PoseBA for every marker (pose_estimation.cpp:50-143) through ctag_estimate_pose.
+// PoseInfo::markerID is the INDEX of the model in `reconstruct_model` (pose_estimation.cpp:59,69); markers whose ID has
+// no model, or with too few usable corners, produce no pose (the reference erases its markerID == -1 entries,
+// CylinderTag.cpp:206-208).  Host code only: no detector, no GPU.
+inline void estimate_poses(const std::vector<MarkerInfo>& markers, const std::vector<ModelInfo>& reconstruct_model,
+                           const CamInfo& camera, std::vector<PoseInfo>& pose) {
+  pose.clear();
+  for (const MarkerInfo& mk : markers) {
+    int idx = -1;
+    for (size_t j = 0; j < reconstruct_model.size(); ++j)
+      if (reconstruct_model[j].MarkerID == mk.markerID) {
+        idx = (int)j;
+        break;
+      }
+    if (idx < 0) continue;
+    const ModelInfo& model = reconstruct_model[idx];
+    ctag_marker rec = to_record(mk);
+    std::vector<float> pts(model.corners.size() * 3);
+    for (size_t i = 0; i < model.corners.size(); ++i)
+      pts[3 * i] = model.corners[i].x, pts[3 * i + 1] = model.corners[i].y, pts[3 * i + 2] = model.corners[i].z;
+    PoseInfo p;
+    if (ctag_estimate_pose(&rec, pts.data(), (int)model.corners.size(), camera.Intrinsic, camera.distCoeffs.data(),
+                           (int)camera.distCoeffs.size(), p.rvec, p.tvec, nullptr) != CTAG_OK)
+      continue;
+    p.markerID = idx;
+    pose.push_back(p);
+  }
+}
+
 class CylinderTag {
  public:
   // Load state matrix of CylinderTag from file (CylinderTag.cpp:6-9,16-41)
@@ -131,34 +228,17 @@ class CylinderTag {
 #endif
 
   // Load reconstructed model (CylinderTag.cpp:161-190)
-  void loadModel(const std::string& path, std::vector<ModelInfo>& reconstruct_model) {
-    std::ifstream in(path);
-    if (!in.is_open()) throw std::string("loadModel, could not open the model file\n");
-    int model_num = 0, model_size = 0;
-    in >> model_num >> model_size;
-    reconstruct_model.assign(model_num, ModelInfo());
-    for (int i = 0; i < model_num; ++i) {
-      ModelInfo& m = reconstruct_model[i];
-      in >> m.MarkerID >> m.base.x >> m.base.y >> m.base.z >> m.axis.x >> m.axis.y >> m.axis.z;
-      m.corners.assign((size_t)model_size * 8, Point3f());
-      for (int j = 0; j < 8 * model_size; ++j) {
-        int id = 0;
-        Point3f p;
-        in >> id >> p.x >> p.y >> p.z;
-        if (id >= 0 && id < 8 * model_size) m.corners[id] = p;
-      }
-    }
-  }
+  void loadModel(const std::string& path, std::vector<ModelInfo>& reconstruct_model) { load_model(path, reconstruct_model); }
 
   // Load camera intrinsic (CylinderTag.cpp:192-196): OpenCV YAML 1.0 with cameraMatrix (3x3) and distCoeffs (5x1)
-  void loadCamera(const std::string& path, CamInfo& camera) {
-    std::ifstream in(path);
-    std::stringstream ss;
-    ss << in.rdbuf();
-    const std::string txt = ss.str();
-    std::vector<float> k = yaml_matrix(txt, "cameraMatrix"), dcf = yaml_matrix(txt, "distCoeffs");
-    for (size_t i = 0; i < 9 && i < k.size(); ++i) camera.Intrinsic[i] = k[i];
-    camera.distCoeffs = dcf;
+  void loadCamera(const std::string& path, CamInfo& camera) { load_camera(path, camera); }
+
+  // Marker Localization (CylinderTag.cpp:198-209).  `img` and `useDensePoseRefine` are unused, as in the reference.
+  void estimatePose(const ImageView& img, const std::vector<MarkerInfo>& markers, const std::vector<ModelInfo>& reconstruct_model,
+                    const CamInfo& camera, std::vector<PoseInfo>& pose, bool useDensePoseRefine = false) {
+    (void)img;
+    (void)useDensePoseRefine;
+    estimate_poses(markers, reconstruct_model, camera, pose);
   }
 
   ctag_detector* handle() { return det_; }
@@ -189,20 +269,6 @@ class CylinderTag {
     return m;
   }
 
-  static std::vector<float> yaml_matrix(const std::string& txt, const std::string& key) {
-    std::vector<float> out;
-    size_t p = txt.find(key);
-    if (p == std::string::npos) return out;
-    size_t a = txt.find('[', p), b = txt.find(']', a);
-    if (a == std::string::npos || b == std::string::npos) return out;
-    std::string body = txt.substr(a + 1, b - a - 1);
-    for (char& ch : body)
-      if (ch == ',' || ch == '\n') ch = ' ';
-    std::stringstream ss(body);
-    double v;
-    while (ss >> v) out.push_back((float)v);  // dt: f
-    return out;
-  }
 };
 
 }  // namespace ctag_api

@@ -1,5 +1,6 @@
 // Compile-and-link check of the C++ mirror class against the shared library (no GPU needed to build; at run time it
 // exercises the loaders and the error paths; detection itself is covered by the gpu tests through the same C ABI).
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include "cylindertag/CylinderTag.h"
@@ -23,5 +24,45 @@ int main(int argc, char** argv) {
     std::printf("missing: %s", s.c_str());
   }
   std::printf("created=%d models=%zu fx=%.3f ndist=%zu\n", created, models.size(), cam.Intrinsic[0], cam.distCoeffs.size());
+  // Pose stage (host code, no detector needed): project three features of model 0 with a known pose through the
+  // pinhole model (no distortion) and recover it.
+  {
+    std::vector<ModelInfo> mm;
+    CamInfo cc;
+    load_model(argv[2], mm);
+    load_camera(argv[3], cc);
+    cc.distCoeffs.assign(5, 0.f);
+    const double rv[3] = {0.2, -0.3, 0.1}, tv[3] = {-250.0, 100.0, 300.0};
+    const double th = std::sqrt(rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2]);
+    const double x = rv[0] / th, y = rv[1] / th, z = rv[2] / th, c = std::cos(th), s = std::sin(th), c1 = 1 - c;
+    const double R[9] = {c + c1 * x * x, c1 * x * y - s * z, c1 * x * z + s * y, c1 * x * y + s * z, c + c1 * y * y,
+                         c1 * y * z - s * x, c1 * x * z - s * y, c1 * y * z + s * x, c + c1 * z * z};
+    MarkerInfo mk;
+    mk.markerID = mm[0].MarkerID;
+    for (int f = 3; f < 6; ++f) {
+      std::vector<Point2f> cl(8);
+      for (int k = 0; k < 8; ++k) {
+        const Point3f& P = mm[0].corners[f * 8 + k];
+        const double X = R[0] * P.x + R[1] * P.y + R[2] * P.z + tv[0], Y = R[3] * P.x + R[4] * P.y + R[5] * P.z + tv[1],
+                     Z = R[6] * P.x + R[7] * P.y + R[8] * P.z + tv[2];
+        cl[k].x = (float)(cc.Intrinsic[0] * X / Z + cc.Intrinsic[2]);
+        cl[k].y = (float)(cc.Intrinsic[4] * Y / Z + cc.Intrinsic[5]);
+      }
+      mk.cornerLists.push_back(cl);
+      mk.featurePos.push_back(f);
+      mk.feature_ID.push_back(0);
+      mk.feature_ID_left.push_back(1);
+      mk.feature_ID_right.push_back(1);
+    }
+    MarkerInfo unknown = mk;
+    unknown.markerID = 12345;  // no model: erased from the result
+    std::vector<PoseInfo> poses;
+    estimate_poses({unknown, mk}, mm, cc, poses);
+    double er = 0, et = 0;
+    if (poses.size() == 1)
+      for (int k = 0; k < 3; ++k) er = std::fmax(er, std::fabs(poses[0].rvec[k] - rv[k])), et = std::fmax(et, std::fabs(poses[0].tvec[k] - tv[k]));
+    std::printf("poses=%zu model_index=%d rot_err_ok=%d trans_err_ok=%d\n", poses.size(), poses.empty() ? -9 : poses[0].markerID,
+                (int)(poses.size() == 1 && er < 1e-4), (int)(poses.size() == 1 && et < 3e-2));
+  }
   return 0;
 }
