@@ -66,10 +66,10 @@ struct Slot {
       *d_st_y1 = nullptr, *d_roots_tmp = nullptr, *d_span_count = nullptr, *d_legal = nullptr, *d_counters = nullptr;
   int legal_cap = 0, spans = 0;
   int *d_prefix = nullptr, *d_qctl = nullptr, *d_quad_status = nullptr, *d_quad_comp = nullptr, *d_n_quads = nullptr,
-      *d_exact_list = nullptr, *d_fit_order = nullptr, *d_pool = nullptr;
+      *d_exact_list = nullptr, *d_fit_order = nullptr, *d_frame_fit = nullptr, *d_pool = nullptr;
   float *d_quad_corners = nullptr, *d_quads = nullptr, *d_lines = nullptr;
   void *d_fits = nullptr, *d_traj = nullptr, *d_fit_results = nullptr, *d_geom = nullptr, *d_feats = nullptr;
-  int edge_warps = 0, exact_ctas = 0, fit_cap = 0, pool_cap = 0;
+  int edge_warps = 0, exact_ctas = 0, fit_cap = 0, fit_per_frame = 0, pool_cap = 0;
   int *d_fstate = nullptr, *d_packed_count = nullptr, *d_summary = nullptr;
   ctag_marker *d_markers = nullptr, *d_packed = nullptr;
   int* h_summary = nullptr;         // pinned
@@ -202,11 +202,14 @@ static int ensure_workspace(ctag_detector* d, Slot* s, int n, int w, int h) {
   // components that reach four edges / their cluster points: the reference caps a frame at 1000 quads
   // (isVisited[1000]), so 1024 four-edge components per frame is already past its envelope; overflow drops the
   // component and flags the frame instead of writing out of bounds
-  s->fit_cap = cap * (s->legal_cap < 1024 ? s->legal_cap : 1024);
+  s->fit_per_frame = s->legal_cap < 1024 ? s->legal_cap : 1024;
+  s->fit_cap = cap * s->fit_per_frame;
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_frame_fit, (size_t)2 * cap));
   CTAG_CUDA_CHECK(slot_alloc_bytes(s, &s->d_fit_results, quad_fitresult_bytes() * 80 * (size_t)s->fit_cap));
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_exact_list, (size_t)4 * s->fit_cap));
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_fit_order, (size_t)4 * s->fit_cap));
-  const long long per_frame_pts = (long long)g.hw * g.hh < 262144 ? (long long)g.hw * g.hh : 262144;
+  // boundary points are distinct foreground pixels: one int per half-res pixel cannot overflow
+  const long long per_frame_pts = (long long)g.hw * g.hh;
   s->pool_cap = (int)(per_frame_pts * cap < 0x7fffffff ? per_frame_pts * cap : 0x7fffffff);
   CTAG_CUDA_CHECK(slot_alloc_bytes(s, &s->d_fits, quad_fitrec_bytes() * s->fit_cap));
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_lines, (size_t)16 * s->fit_cap));
@@ -268,7 +271,7 @@ static int enqueue_on_slot(ctag_detector* d, Slot* s, const void* frames_dev, in
   if (rc != CTAG_OK) return rc;
   CTAG_CUDA_CHECK(cudaEventRecord(s->ev[2], st));
   rc = launch_quad(n, s->geo, s->d_bin, s->bin_fstride, s->d_labels, s->d_legal, s->legal_cap, s->d_counters, s->d_prefix,
-                   s->d_qctl, s->d_quad_scratch, s->edge_warps, s->d_fits, s->fit_cap, s->d_pool, s->pool_cap,
+                   s->d_qctl, s->d_quad_scratch, s->edge_warps, s->d_fits, s->fit_cap, s->fit_per_frame, s->d_frame_fit, s->d_pool, s->pool_cap,
                    d->d_pick_table, kPickTableMax, s->d_fit_results, s->d_exact_list, s->d_fit_order, s->d_traj, s->exact_ctas, d->sms,
                    s->d_lines, s->d_quad_status, s->d_quad_corners, kQuadCap, s->d_quads, s->d_quad_comp, s->d_n_quads, st,
                    &s->launches);
@@ -279,7 +282,7 @@ static int enqueue_on_slot(ctag_detector* d, Slot* s, const void* frames_dev, in
   if (rc != CTAG_OK) return rc;
   CTAG_CUDA_CHECK(cudaEventRecord(s->ev[4], st));
   rc = launch_decode(n, s->d_feats, kFeatCap, s->d_fstate, d->d_state, d->rows, d->cols, d->feature_size, s->d_markers,
-                     kMarkerCap, s->d_counters, s->d_n_quads, kQuadCap, s->d_qctl + 4 /* QC_OVERFLOW */, s->d_packed,
+                     kMarkerCap, s->d_counters, s->d_n_quads, kQuadCap, s->d_qctl + 4 /* QC_OVERFLOW */, s->d_frame_fit + n, s->d_packed,
                      s->d_packed_count, s->d_summary, st, &s->launches);
   if (rc != CTAG_OK) return rc;
   CTAG_CUDA_CHECK(cudaEventRecord(s->ev[5], st));

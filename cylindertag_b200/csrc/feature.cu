@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(32) decode_kernel(const FeatureRec* __restrict
                                                     int scols, int fsz, ctag_marker* __restrict__ markers, int marker_cap,
                                                     const int* __restrict__ counters, const int* __restrict__ n_quads,
                                                     int quad_cap, const int* __restrict__ batch_overflow,
+                                                    const int* __restrict__ frame_overflow,
                                                     ctag_marker* __restrict__ packed, int* __restrict__ packed_count,
                                                     int* __restrict__ summary /* [frame][12] */) {
   extern __shared__ int smem_i[];
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(32) decode_kernel(const FeatureRec* __restrict
     s[4] = fstate[fr * 4 + 1];          // n_features
     s[5] = ngroups;
     s[6] = nm;
-    s[7] = (flagged || fstate[fr * 4 + 3] || counters[fr * 4 + 2] || nq > quad_cap || nm > marker_cap || *batch_overflow) ? 1 : 0;
+    s[7] = (flagged || fstate[fr * 4 + 3] || counters[fr * 4 + 2] || nq > quad_cap || nm > marker_cap || *batch_overflow || frame_overflow[fr]) ? 1 : 0;
     s[8] = stale;
     s[9] = off;                         // offset of this frame's markers in the packed list
     s[10] = nstore;
@@ -210,7 +211,8 @@ int launch_features(int n, const FrameGeom& g, const float* quads, const int* n_
 
 int launch_decode(int n, const void* feats, int feat_cap, const int* fstate, const int* state, int srows, int scols, int fsz,
                   ctag_marker* markers, int marker_cap, const int* counters, const int* n_quads, int quad_cap,
-                  const int* batch_overflow, ctag_marker* packed, int* packed_count, int* summary, cudaStream_t stream,
+                  const int* batch_overflow, const int* frame_overflow, ctag_marker* packed, int* packed_count, int* summary,
+                  cudaStream_t stream,
                   int* launches) {
   size_t smem = decode_smem_bytes(srows, scols);
   if (smem > 200 * 1024) return CTAG_ERR_UNSUPPORTED;
@@ -218,7 +220,7 @@ int launch_decode(int n, const void* feats, int feat_cap, const int* fstate, con
     CTAG_CUDA_CHECK(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CTAG_CUDA_CHECK(cudaMemsetAsync(packed_count, 0, sizeof(int), stream));
   decode_kernel<<<n, 32, smem, stream>>>(static_cast<const FeatureRec*>(feats), feat_cap, fstate, state, srows, scols, fsz,
-                                         markers, marker_cap, counters, n_quads, quad_cap, batch_overflow, packed, packed_count, summary);
+                                         markers, marker_cap, counters, n_quads, quad_cap, batch_overflow, frame_overflow, packed, packed_count, summary);
   CTAG_CUDA_CHECK(cudaGetLastError());
   if (launches) *launches += 1;
   return CTAG_OK;

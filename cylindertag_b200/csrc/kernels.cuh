@@ -32,7 +32,7 @@ int quad_exact_ctas(int sms);
 void quad_build_pick_table(uint16_t* host_table, int max_count);
 int launch_quad(int n, const FrameGeom& g, const uint8_t* bin, size_t bin_fstride, const int* labels, const int* legal,
                 int legal_cap, const int* counters, int* prefix, int* qctl, uint8_t* scratch, int edge_warps, void* fits,
-                int fit_cap, int* pool, int pool_cap, const uint16_t* pick_table, int table_max, void* results,
+                int fit_cap, int fit_per_frame, int* frame_fit, int* pool, int pool_cap, const uint16_t* pick_table, int table_max, void* results,
                 int* exact_list, int* fit_order, void* traj, int exact_ctas, int sms, float* lines, int* quad_status,
                 float* quad_corners, int quad_cap, float* quads, int* quad_comp, int* n_quads, cudaStream_t stream,
                 int* launches);
@@ -50,7 +50,7 @@ int launch_features(int n, const FrameGeom& g, const float* quads, const int* n_
 size_t decode_smem_bytes(int srows, int scols);
 int launch_decode(int n, const void* feats, int feat_cap, const int* fstate, const int* state, int srows, int scols, int fsz,
                   ctag_marker* markers, int marker_cap, const int* counters, const int* n_quads, int quad_cap,
-                  const int* batch_overflow, ctag_marker* packed, int* packed_count, int* summary, cudaStream_t stream,
+                  const int* batch_overflow, const int* frame_overflow, ctag_marker* packed, int* packed_count, int* summary, cudaStream_t stream,
                   int* launches);
 
 }  // namespace ctag

@@ -65,7 +65,10 @@ struct FitRec {
 };
 
 // prefix[f] = number of legal components in frames < f; prefix[n] = total.  Also resets the control words.
-__global__ void quad_prefix_kernel(const int* __restrict__ counters, int n, int* __restrict__ prefix, int* __restrict__ qctl) {
+// frame_fit[f] = four-edge components of frame f so far, frame_fit[n + f] = 1 when frame f ran out of its fit quota.
+__global__ void quad_prefix_kernel(const int* __restrict__ counters, int n, int* __restrict__ prefix, int* __restrict__ qctl,
+                                   int* __restrict__ frame_fit) {
+  for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) frame_fit[i] = 0;
   if (threadIdx.x == 0) {
     int acc = 0;
     for (int f = 0; f < n; ++f) {
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(32 * kEdgeWarps, kEdgeCtasPerSm) quad_edges_ke
     int n_frames, FrameGeom g, const uint8_t* __restrict__ bin, size_t bin_fstride, const int* __restrict__ labels,
     const int* __restrict__ legal, int legal_cap, const int* __restrict__ prefix, int* __restrict__ qctl,
     uint8_t* __restrict__ scratch, QuadScratchLayout L, int* __restrict__ quad_status, FitRec* __restrict__ fits, int fit_cap,
-    int* __restrict__ pool, int pool_cap) {
+    int fit_per_frame, int* __restrict__ frame_fit, int* __restrict__ pool, int pool_cap) {
   __shared__ uint32_t s_vis[kEdgeWarps][kSmemVisWords];
   __shared__ int s_pts_a[kEdgeWarps][kSmemPts + 8], s_pts_b[kEdgeWarps][kSmemPts + 8], s_stack[kEdgeWarps][kSmemPts + 8],
       s_cl[kEdgeWarps][kSmemPts + 8];
@@ -151,11 +154,18 @@ __global__ void __launch_bounds__(32 * kEdgeWarps, kEdgeCtasPerSm) quad_edges_ke
     int slot = -1, poff = 0;
     if (ed.cnt == 4) {
       if (lane == 0) {
-        slot = atomicAdd(&qctl[QC_FIT_COUNT], 1);
-        poff = atomicAdd(&qctl[QC_POOL_CURSOR], ed.cl_off[4]);
-        if (slot >= fit_cap || poff + ed.cl_off[4] > pool_cap) {
-          atomicExch(&qctl[QC_OVERFLOW], 1);
+        // every frame owns a quota of fit slots (the batch capacity is the sum of the quotas), so a cluttered frame
+        // can only exhaust -- and flag -- itself, never a neighbour in the batch
+        if (atomicAdd(&frame_fit[fr], 1) >= fit_per_frame) {
+          frame_fit[n_frames + fr] = 1;
           slot = -2;
+        } else {
+          slot = atomicAdd(&qctl[QC_FIT_COUNT], 1);
+          poff = atomicAdd(&qctl[QC_POOL_CURSOR], ed.cl_off[4]);
+          if (slot >= fit_cap || poff + ed.cl_off[4] > pool_cap) {  // cannot happen with the sizes api.cu allocates
+            atomicExch(&qctl[QC_OVERFLOW], 1);
+            slot = -2;
+          }
         }
       }
       slot = __shfl_sync(0xffffffffu, slot, 0);
@@ -455,15 +465,15 @@ void quad_build_pick_table(uint16_t* host_table, int max_count) { welsch_pick_ta
 
 int launch_quad(int n, const FrameGeom& g, const uint8_t* bin, size_t bin_fstride, const int* labels, const int* legal,
                 int legal_cap, const int* counters, int* prefix, int* qctl, uint8_t* scratch, int edge_warps, void* fits,
-                int fit_cap, int* pool, int pool_cap, const uint16_t* pick_table, int table_max, void* results,
+                int fit_cap, int fit_per_frame, int* frame_fit, int* pool, int pool_cap, const uint16_t* pick_table, int table_max, void* results,
                 int* exact_list, int* fit_order, void* traj, int exact_ctas, int sms, float* lines, int* quad_status,
                 float* quad_corners, int quad_cap, float* quads, int* quad_comp, int* n_quads, cudaStream_t stream,
                 int* launches) {
   QuadScratchLayout L = make_layout(g);
-  quad_prefix_kernel<<<1, 32, 0, stream>>>(counters, n, prefix, qctl);
+  quad_prefix_kernel<<<1, 32, 0, stream>>>(counters, n, prefix, qctl, frame_fit);
   quad_edges_kernel<<<edge_warps / kEdgeWarps, 32 * kEdgeWarps, 0, stream>>>(
       n, g, bin, bin_fstride, labels, legal, legal_cap, prefix, qctl, scratch, L, quad_status, static_cast<FitRec*>(fits),
-      fit_cap, pool, pool_cap);
+      fit_cap, fit_per_frame, frame_fit, pool, pool_cap);
   quad_fitorder_kernel<<<1, 1024, 0, stream>>>(qctl, static_cast<const FitRec*>(fits), fit_cap, fit_order);
   quad_fit_kernel<<<sms * 8, 128, 0, stream>>>(qctl, static_cast<const FitRec*>(fits), fit_cap, pool, pick_table, table_max,
                                                 fit_order, static_cast<FitResult*>(results));
