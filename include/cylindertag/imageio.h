@@ -1,0 +1,115 @@
+// imageio.h -- minimal frame ingest for programs that use the mirror class without OpenCV:
+// uncompressed BMP (8-bit palettised gray, 24-bit BGR, 32-bit BGRA; bottom-up or top-down) and binary PGM/PPM.
+// Stands in for cv::imread at main.cpp:29 for the formats the reference's sample data uses (test.bmp).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "CylinderTag.h"
+
+namespace ctag_api {
+
+struct Image {
+  std::vector<uint8_t> data;  // rows x cols x channels, tightly packed; 3-channel data is B,G,R like cv::imread
+  int rows = 0, cols = 0, channels = 0;
+  bool empty() const { return data.empty(); }
+  ImageView view() const { return ImageView{data.data(), rows, cols, (size_t)cols * channels, channels}; }
+};
+
+namespace detail {
+inline uint32_t rd32(const uint8_t* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+inline uint16_t rd16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+}  // namespace detail
+
+// Returns an empty image on any error (like cv::imread).
+inline Image imread(const std::string& path) {
+  Image img;
+  FILE* f = std::fopen(path.c_str(), "rb");
+  if (!f) return img;
+  std::vector<uint8_t> buf;
+  uint8_t tmp[65536];
+  size_t n;
+  while ((n = std::fread(tmp, 1, sizeof(tmp), f)) > 0) buf.insert(buf.end(), tmp, tmp + n);
+  std::fclose(f);
+  if (buf.size() >= 54 && buf[0] == 'B' && buf[1] == 'M') {
+    const uint32_t off = detail::rd32(&buf[10]), hdr = detail::rd32(&buf[14]);
+    if (hdr < 40) return img;
+    const int32_t w = (int32_t)detail::rd32(&buf[18]), hs = (int32_t)detail::rd32(&buf[22]);
+    const int bpp = detail::rd16(&buf[28]);
+    const uint32_t comp = detail::rd32(&buf[30]);
+    if (w <= 0 || hs == 0 || (comp != 0 && !(comp == 3 && bpp == 32)) || (bpp != 8 && bpp != 24 && bpp != 32)) return img;
+    const int h = hs < 0 ? -hs : hs;
+    const size_t stride = (((size_t)w * bpp + 31) / 32) * 4;
+    if (off + stride * h > buf.size()) return img;
+    const uint8_t* pal = &buf[14 + hdr];
+    bool gray_palette = bpp == 8;
+    if (bpp == 8) {
+      uint32_t ncol = detail::rd32(&buf[46]);
+      if (ncol == 0 || ncol > 256) ncol = 256;
+      if (14 + hdr + 4 * (size_t)ncol > buf.size()) return img;
+      for (uint32_t c = 0; c < ncol && gray_palette; ++c) gray_palette = pal[4 * c] == pal[4 * c + 1] && pal[4 * c] == pal[4 * c + 2];
+    }
+    img.rows = h, img.cols = w, img.channels = (bpp == 8 && gray_palette) ? 1 : 3;
+    img.data.resize((size_t)h * w * img.channels);
+    for (int y = 0; y < h; ++y) {
+      const uint8_t* src = &buf[off + stride * (size_t)(hs < 0 ? y : h - 1 - y)];
+      uint8_t* dst = &img.data[(size_t)y * w * img.channels];
+      if (bpp == 8 && gray_palette) {
+        for (int x = 0; x < w; ++x) dst[x] = pal[4 * src[x]];
+      } else if (bpp == 8) {
+        for (int x = 0; x < w; ++x) std::memcpy(dst + 3 * x, pal + 4 * src[x], 3);
+      } else if (bpp == 24) {
+        std::memcpy(dst, src, (size_t)3 * w);
+      } else {
+        for (int x = 0; x < w; ++x) std::memcpy(dst + 3 * x, src + 4 * x, 3);
+      }
+    }
+    return img;
+  }
+  if (buf.size() > 2 && buf[0] == 'P' && (buf[1] == '5' || buf[1] == '6')) {
+    size_t p = 2;
+    int vals[3], got = 0;
+    while (got < 3 && p < buf.size()) {
+      while (p < buf.size() && (buf[p] == ' ' || buf[p] == '\n' || buf[p] == '\r' || buf[p] == '\t')) ++p;
+      if (p < buf.size() && buf[p] == '#') {
+        while (p < buf.size() && buf[p] != '\n') ++p;
+        continue;
+      }
+      int v = 0, digits = 0;
+      while (p < buf.size() && buf[p] >= '0' && buf[p] <= '9') v = v * 10 + (buf[p++] - '0'), ++digits;
+      if (!digits) return img;
+      vals[got++] = v;
+    }
+    ++p;  // single whitespace after maxval
+    const int ch = buf[1] == '5' ? 1 : 3;
+    if (got < 3 || vals[2] != 255 || p + (size_t)vals[0] * vals[1] * ch > buf.size()) return img;
+    img.cols = vals[0], img.rows = vals[1], img.channels = ch;
+    img.data.assign(buf.begin() + p, buf.begin() + p + (size_t)vals[0] * vals[1] * ch);
+    if (ch == 3)  // PPM is R,G,B: swap to B,G,R
+      for (size_t i = 0; i + 2 < img.data.size(); i += 3) {
+        const uint8_t t = img.data[i];
+        img.data[i] = img.data[i + 2];
+        img.data[i + 2] = t;
+      }
+    return img;
+  }
+  return img;
+}
+
+// cv::cvtColor(COLOR_BGR2GRAY) for 8-bit data (main.cpp:36): (3735 B + 19235 G + 9798 R + 16384) >> 15.
+// (The batched C entry point ctag_detect_batch(channels = 3) does this on the GPU; this host version is for the
+//  single-image flow of the mirror class, whose detect() takes a gray image like the reference's.)
+inline Image bgr2gray(const Image& bgr) {
+  if (bgr.channels == 1) return bgr;
+  Image g;
+  g.rows = bgr.rows, g.cols = bgr.cols, g.channels = 1;
+  g.data.resize((size_t)bgr.rows * bgr.cols);
+  for (size_t i = 0; i < g.data.size(); ++i)
+    g.data[i] = (uint8_t)((3735u * bgr.data[3 * i] + 19235u * bgr.data[3 * i + 1] + 9798u * bgr.data[3 * i + 2] + 16384u) >> 15);
+  return g;
+}
+
+}  // namespace ctag_api

@@ -1,0 +1,40 @@
+"""examples/main_image.cpp = the image branch of the reference's main.cpp on the C++ mirror (gpu): BMP in, markers and
+poses out, compared with the oracle's known answers for test.bmp."""
+import os
+import subprocess
+
+import cv2
+import numpy as np
+import pytest
+
+from oracle import ctag_oracle as o
+from oracle import pose_oracle as po
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DATA = os.path.join(ROOT, "tests", "golden", "data")
+
+
+def test_main_image_flow(tmp_path, test_gray, marker_path):
+    exe = tmp_path / "main_image"
+    libdir = os.path.join(ROOT, "cylindertag_b200", "lib")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "main_image.cpp"),
+                    "-o", str(exe), "-L", libdir, "-lctag_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    bmp = tmp_path / "test.bmp"
+    cv2.imwrite(str(bmp), cv2.cvtColor(test_gray, cv2.COLOR_GRAY2BGR))  # 24-bit like the reference's test.bmp
+    out = subprocess.run([str(exe), str(bmp), marker_path, os.path.join(DATA, "CTag_2f12c.model"),
+                          os.path.join(DATA, "cameraParams.yml")], capture_output=True, text=True, check=True).stdout
+    lines = out.strip().splitlines()
+    assert lines[0] == "markers 5 poses 5"
+    assert [int(l.split()[1]) for l in lines if l.startswith("marker ")] == [23, 0, 1, 17, 5]
+    state, fs = o.load_marker_file(marker_path)
+    d = o.detect(test_gray, state, fs, 5, True, 5)
+    want = po.estimate_pose(d.markers, po.load_model(os.path.join(DATA, "CTag_2f12c.model")),
+                            *po.load_camera(os.path.join(DATA, "cameraParams.yml")))
+    got = [l.split() for l in lines if l.startswith("pose ")]
+    assert [int(g[2]) for g in got] == [w[0] for w in want]
+    for g, w in zip(got, want):
+        rvec = np.array([float(v) for v in g[6:9]])
+        tvec = np.array([float(v) for v in g[10:13]])
+        assert np.abs(rvec - w[1]).max() < 2e-4            # printed with 5 decimals
+        assert np.linalg.norm(tvec - w[2]) < 2e-4 * np.linalg.norm(w[2]) + 1e-3
