@@ -266,11 +266,13 @@ __global__ void __launch_bounds__(front::NT, 3) front_kernel(const __grid_consta
         // the word in front of k == 0 and the word behind k == 23 only feed the unused columns j' = 0 and 95: those
         // two loads are redirected to a word of the thread's own span so that nothing outside the row (and outside
         // the buffer) is read, without a branch
-        const int o0 = k ? -4 : 0, o3 = k < 23 ? 8 : 4;
-        for (; rp < RH / 2; rp += NT / 24, src += 2 * (NT / 24) * RW, dst += (NT / 24) * HP) {
-          const uint32_t a0 = *reinterpret_cast<const uint32_t*>(src + o0), a3 = *reinterpret_cast<const uint32_t*>(src + o3);
+        const uint8_t* s0 = src + (k ? -4 : 0);
+        const uint8_t* s3 = src + (k < 23 ? 8 : 4);
+        for (; rp < RH / 2; rp += NT / 24, src += 2 * (NT / 24) * RW, s0 += 2 * (NT / 24) * RW, s3 += 2 * (NT / 24) * RW,
+                            dst += (NT / 24) * HP) {
+          const uint32_t a0 = *reinterpret_cast<const uint32_t*>(s0), a3 = *reinterpret_cast<const uint32_t*>(s3);
           const uint2 a12 = *reinterpret_cast<const uint2*>(src);
-          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(src + RW + o0), b3 = *reinterpret_cast<const uint32_t*>(src + RW + o3);
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(s0 + RW), b3 = *reinterpret_cast<const uint32_t*>(s3 + RW);
           const uint2 b12 = *reinterpret_cast<const uint2*>(src + RW);
           const int h0 = dp4a_us(__byte_perm(a0, a12.x, 0x6543), COEF, 0), g0 = dp4a_us(__byte_perm(b0, b12.x, 0x6543), COEF, 0);
           const int h1 = dp4a_us(__byte_perm(a12.x, a12.y, 0x4321), COEF, 0), g1 = dp4a_us(__byte_perm(b12.x, b12.y, 0x4321), COEF, 0);
