@@ -370,6 +370,24 @@ def main():
                 "clocks": clocks}
         if e2e:
             line["e2e"] = e2e
+        if not a.no_e2e and world == 1:
+            # informational: warm latency of the single-frame entry point on BASELINE config 0 (the reference's own
+            # test image: host gray frame in, markers out, wall clock around the synchronous ctag_detect call)
+            try:
+                import cv2
+                tb = cv2.imread(os.path.join(DATA, "test_gray.png"), cv2.IMREAD_GRAYSCALE)
+                det1 = Detector(state=state, feature_size=fs, device=local)
+                for _ in range(5):
+                    det1.detect(tb, 5, True, 5, cap=64)
+                lat = []
+                for _ in range(50):
+                    t0 = time.perf_counter()
+                    rec1, _st = det1.detect(tb, 5, True, 5, cap=64)
+                    lat.append(time.perf_counter() - t0)
+                line["single_frame"] = {"workload": "test.bmp 1920x1200 gray, ctag_detect(adaptiveThresh=5, cornerSubPix=true, dist=5), host frame in, markers out",
+                                        "median_ms": float(np.median(lat) * 1e3), "markers": int(len(rec1))}
+            except Exception as exc:  # pragma: no cover
+                line["single_frame"] = {"error": str(exc)}
         if not a.no_cpu and world == 1:
             cores = os.cpu_count() or 1
             if cpu_port_available() is not None:

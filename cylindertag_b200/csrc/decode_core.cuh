@@ -313,20 +313,40 @@ CT_HD int organize_and_decode(const FeatureRec* feats, int nf, const int* state,
         sc.cover[t] = cov;
       }
       w_sync();
-      // ---- ... then the sequential max / second bookkeeping, which is not a true runner-up (SURVEY C-8) ----
-      if (ln.id == 0) {
-        int maxc = -1, second = -1, pi = 0, pj = 0, direc = 1;
-        for (int t = 0; t < 2 * srows * scols; ++t) {
-          int cov = sc.cover[t];
-          if (cov > maxc) {
-            maxc = cov;
-            int rc = t % (srows * scols);
-            pi = rc / scols;
-            pj = rc - pi * scols;
-            direc = t < srows * scols ? 1 : -1;
-          } else if (cov > second) {
-            second = cov;
+      // ---- ... then the max / second bookkeeping of the reference's single sequential scan
+      //   if (cov > max) { max = cov; remember t } else if (cov > second) second = cov;
+      // which is not a true runner-up (SURVEY C-8): `second` only sees entries that did not raise the maximum.  The
+      // scan is cut into one contiguous chunk per lane; a lane replays its chunk starting from the maximum of all
+      // earlier chunks, which reproduces every comparison of the sequential scan.
+      int maxc, second, tbest;
+      {
+        const int T = 2 * srows * scols, per = (T + ln.n - 1) / ln.n;
+        const int t0 = ln.id * per, t1 = t0 + per < T ? t0 + per : T;
+        int lmax = -1;
+        for (int t = t0; t < t1; ++t) lmax = sc.cover[t] > lmax ? sc.cover[t] : lmax;
+        int run = w_prefix_max_excl_i(lmax, ln.id, -1);
+        int sec = -1, first = 0x7fffffff;
+        for (int t = t0; t < t1; ++t) {
+          const int cov = sc.cover[t];
+          if (cov > run) {
+            run = cov;
+            first = t;  // last record of this chunk; the global maximum's first occurrence is the last record overall
+          } else if (cov > sec) {
+            sec = cov;
           }
+        }
+        maxc = w_max_i(lmax);
+        second = w_max_i(sec);
+        // the record that set the global maximum: the lane whose chunk raised the running maximum to maxc
+        tbest = w_min_i((first != 0x7fffffff && run == maxc && lmax == maxc) ? first : 0x7fffffff);
+      }
+      if (ln.id == 0) {
+        int pi = 0, pj = 0, direc = 1;
+        if (maxc > -1 && tbest != 0x7fffffff) {
+          int rc = tbest % (srows * scols);
+          pi = rc / scols;
+          pj = rc - pi * scols;
+          direc = tbest < srows * scols ? 1 : -1;
         }
         double need = 0.8 * legal < legal - 1.0 ? 0.8 * legal : legal - 1.0;
         if ((double)maxc >= need && maxc > second) {

@@ -69,6 +69,22 @@ CT_HD int w_sum_i(int v) {
   return v;
 #endif
 }
+// max of v over the lanes below this one (identity `none` for lane 0)
+CT_HD int w_prefix_max_excl_i(int v, int lane, int none) {
+#ifdef __CUDA_ARCH__
+  int inc = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc = inc > u ? inc : u;
+  }
+  const int ex = __shfl_up_sync(0xffffffffu, inc, 1);
+  return lane == 0 ? none : ex;
+#else
+  (void)v;
+  (void)lane;
+  return none;
+#endif
+}
 CT_HD int popc32(uint32_t v) {
 #ifdef __CUDA_ARCH__
   return __popc(v);
