@@ -353,9 +353,15 @@ def main():
         front_ms = stage_acc["front"]
         alg_bytes = (4.25 if ch == 3 else 1.25) * w * h * a.batch
         achieved = alg_bytes / (front_ms / 1000.0) / 1e9
-        traffic = None
+        # DRAM bytes of one launch of this kernel from the committed `ncu --set full` capture (same workload shape);
+        # null for shapes that were not captured
+        traffic, traffic_detail = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "front_traffic.json"))).get(a.res)
+            traffic_detail = json.load(open(os.path.join(ROOT, "profiles", "front_traffic.json"))).get(a.res)
+            if traffic_detail and ch == 3 and a.batch == traffic_detail.get("frames_per_launch"):
+                traffic = traffic_detail["dram_bytes_total"]
+            else:
+                traffic_detail = None
         except Exception:
             pass
         line = {"metric": "detect_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps,
@@ -363,6 +369,7 @@ def main():
                 "vs_baseline": None, "dtype": "u8/int32 dense, f32/f64 sparse", "data": "synthetic", "config": config,
                 "roofline": {"bound": "hbm", "kernel": f"front_kernel<{ch}> (" + ("gray + " if ch == 3 else "") + "cubic decimation + adaptive threshold)",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                             "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)", "traffic_detail": traffic_detail,
                              "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                              "kernel_ms_per_launch": front_ms},
                 "stages_ms_per_step_unoverlapped": stage_acc, "pipelining": f"{depth} batches in flight, one stream each",
