@@ -209,7 +209,10 @@ __global__ void __launch_bounds__(front::NT, 3) front_kernel(const __grid_consta
         uint8_t* dst = g + gq * 16 + row * RW;
         const int x = x0r + gq * 16;
         const bool own_col = gq >= 1 && gq <= 10 && x < geo.w;
-        uint8_t* gp = gray_out + (size_t)fr * gray_fstride + (ptrdiff_t)(y0r + row) * geo.gpitch + x;
+        // store address = CTA-uniform base (kept in uniform registers) + a 32-bit per-thread offset
+        uint8_t* tile_base = gray_out + (size_t)fr * gray_fstride + (ptrdiff_t)y0r * geo.gpitch + x0r;
+        asm volatile("" : "+l"(tile_base));  // keep the pointer live: recomputing the 64-bit products per store costs more
+        const uint32_t toff = (uint32_t)row * (uint32_t)geo.gpitch + (uint32_t)gq * 16u;
         constexpr int RS = NT / 12;  // row step
         uint4 o[4];
 #pragma unroll
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(front::NT, 3) front_kernel(const __grid_consta
             o[u].z = gray4(b.z, b.w, c.x);
             o[u].w = gray4(c.y, c.z, c.w);
             if (own_col && r >= 11 && r < 11 + 2 * OH && y0r + r < geo.h)
-              *reinterpret_cast<uint4*>(gp + (size_t)(u * RS) * geo.gpitch) = o[u];
+              *reinterpret_cast<uint4*>(tile_base + (toff + (uint32_t)(u * RS) * (uint32_t)geo.gpitch)) = o[u];
           }
         }
         __syncthreads();  // every BGR byte has been read: the gray tile may overwrite box 0
