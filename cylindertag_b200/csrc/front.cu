@@ -292,30 +292,64 @@ __global__ void __launch_bounds__(front::NT, 3) front_kernel(const __grid_consta
     }
     __syncthreads();
 
-    // ---- phase C: vertical taps + round-half-even + saturate: P[i][8 + j'] from row pairs i and i+1 -----------------
-    {
+    // ---- phase C+D1: vertical taps + round-half-even + saturate: P[i][8 + j'] from row pairs i and i+1, and in the
+    //      same registers the column extrema of the five rows of a threshold-tile row (first half of the 5x5 tile
+    //      min/max, corner_detector.cpp:42-53).  One thread per (tile row, word of four patch columns): it walks its
+    //      five half-res rows top down, so every HT row is loaded once and reused for the next output row. -------------
+    const bool edge_cta = (cx == 0) || (cy == 0) || (OW * cx + OW + 5 > geo.hw) || (OH * cy + OH + 5 > geo.hh);
+    if (tid < 24 * CTY) {
       const uint32_t C01 = 0x000013FDu;  // (-3, 19) on bytes 0,1
       const uint32_t C23 = 0x0000FD13u;  // (19, -3)
-      const int k = tid % 24;
-      int i = tid / 24;  // half-res rows i, i+16, ...
-      {
-        const uint32_t* src = HT + i * HP + 4 * k;
-        uint8_t* dst = P + i * PP + (POFF - HOFF) + 4 * k;  // 4-byte aligned
-        for (; i < 50; i += NT / 24, src += (NT / 24) * HP, dst += (NT / 24) * PP) {
-          const uint4 a = *reinterpret_cast<const uint4*>(src);
-          const uint4 b = *reinterpret_cast<const uint4*>(src + HP);
-          int v0 = dp2a_lo_ss(b.x, C23, dp2a_lo_ss(a.x, C01, 0));
-          int v1 = dp2a_lo_ss(b.y, C23, dp2a_lo_ss(a.y, C01, 0));
-          int v2 = dp2a_lo_ss(b.z, C23, dp2a_lo_ss(a.z, C01, 0));
-          int v3 = dp2a_lo_ss(b.w, C23, dp2a_lo_ss(a.w, C01, 0));
-          // v / 1024 rounded half to even (what cv::resize's float path does), then saturate_cast<uchar>
-          v0 = (v0 + 511 + ((v0 >> 10) & 1)) >> 10;
-          v1 = (v1 + 511 + ((v1 >> 10) & 1)) >> 10;
-          v2 = (v2 + 511 + ((v2 >> 10) & 1)) >> 10;
-          v3 = (v3 + 511 + ((v3 >> 10) & 1)) >> 10;
-          *reinterpret_cast<uint32_t*>(dst) = pack_sat_u8(v1, v0, pack_sat_u8(v3, v2, 0u));
+      const int k = tid % 24, ti = tid / 24;
+      const uint32_t* src = HT + (5 * ti) * HP + 4 * k;
+      uint8_t* dst = P + (5 * ti) * PP + (POFF - HOFF) + 4 * k;  // 4-byte aligned; patch columns 8 + 4k .. (j = 4k - 3 ..)
+      uint32_t keepx = 0xFFFFFFFFu;
+      if (edge_cta) {
+        // pixels outside the image do not take part in the extrema (corner_detector.cpp:44 clips the window)
+        keepx = 0u;
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+          const int xh = OW * cx - 8 + 4 * k + bb;
+          if (xh >= 0 && xh < geo.hw) keepx |= 0xFFu << (8 * bb);
         }
       }
+      uint4 a = *reinterpret_cast<const uint4*>(src);
+      // byte-wise min/max through the native 16x2 three-input min/max on the even and odd bytes (the 8x4 video
+      // intrinsics are emulated on sm_100)
+      uint32_t ve[5], vo[5], xe[5], xo[5];
+#pragma unroll
+      for (int dy = 0; dy < 5; ++dy) {
+        const uint4 b = *reinterpret_cast<const uint4*>(src + (dy + 1) * HP);
+        int v0 = dp2a_lo_ss(b.x, C23, dp2a_lo_ss(a.x, C01, 0));
+        int v1 = dp2a_lo_ss(b.y, C23, dp2a_lo_ss(a.y, C01, 0));
+        int v2 = dp2a_lo_ss(b.z, C23, dp2a_lo_ss(a.z, C01, 0));
+        int v3 = dp2a_lo_ss(b.w, C23, dp2a_lo_ss(a.w, C01, 0));
+        // v / 1024 rounded half to even (what cv::resize's float path does), then saturate_cast<uchar>
+        v0 = (v0 + 511 + ((v0 >> 10) & 1)) >> 10;
+        v1 = (v1 + 511 + ((v1 >> 10) & 1)) >> 10;
+        v2 = (v2 + 511 + ((v2 >> 10) & 1)) >> 10;
+        v3 = (v3 + 511 + ((v3 >> 10) & 1)) >> 10;
+        const uint32_t w = pack_sat_u8(v1, v0, pack_sat_u8(v3, v2, 0u));
+        *reinterpret_cast<uint32_t*>(dst + dy * PP) = w;
+        uint32_t lo = w, hi = w;
+        if (edge_cta) {
+          const int yh = OH * cy - 5 + 5 * ti + dy;
+          const uint32_t keep = (yh >= 0 && yh < geo.hh) ? keepx : 0u;
+          lo = w | ~keep;
+          hi = w & keep;
+        }
+        ve[dy] = lo & 0x00FF00FFu;
+        vo[dy] = __byte_perm(lo, 0u, 0x4341);
+        xe[dy] = hi & 0x00FF00FFu;
+        xo[dy] = __byte_perm(hi, 0u, 0x4341);
+        a = b;
+      }
+      const uint32_t mne = __vimin3_u16x2(__vimin3_u16x2(ve[0], ve[1], ve[2]), ve[3], ve[4]);
+      const uint32_t mno = __vimin3_u16x2(__vimin3_u16x2(vo[0], vo[1], vo[2]), vo[3], vo[4]);
+      const uint32_t mxe = __vimax3_u16x2(__vimax3_u16x2(xe[0], xe[1], xe[2]), xe[3], xe[4]);
+      const uint32_t mxo = __vimax3_u16x2(__vimax3_u16x2(xo[0], xo[1], xo[2]), xo[3], xo[4]);
+      *reinterpret_cast<uint32_t*>(cmn + ti * 96 + 4 * k) = __byte_perm(mne, mno, 0x6240);  // cmn/cmx column index = j + 3
+      *reinterpret_cast<uint32_t*>(cmx + ti * 96 + 4 * k) = __byte_perm(mxe, mxo, 0x6240);
     }
     __syncthreads();
     if (C == 3) {
@@ -327,51 +361,7 @@ __global__ void __launch_bounds__(front::NT, 3) front_kernel(const __grid_consta
       }
     }
 
-    // ---- phase D: 5x5 tile min/max over valid pixels (corner_detector.cpp:42-53): column extrema, then 5 columns -----
-    const bool edge_cta = (cx == 0) || (cy == 0) || (OW * cx + OW + 5 > geo.hw) || (OH * cy + OH + 5 > geo.hh);
-    {
-      // one thread per (tile row, aligned word of 4 patch columns): 5 word loads, byte-wise min/max in registers.
-      // Patch columns 8..103 (words 2..25) cover j = -3..92; the tile pass only reads j = 0..89.
-      const int wq = tid % 24;  // word index - 2
-      const uint8_t* colw = P + 8 + 4 * wq;
-      for (int ti = tid / 24; ti < CTY; ti += NT / 24) {
-        // byte-wise min/max through the native 16x2 three-input min/max on the even and odd bytes (the 8x4 video
-        // intrinsics are emulated on sm_100)
-        uint32_t ve[5], vo[5], xe[5], xo[5];
-#pragma unroll
-        for (int dy = 0; dy < 5; ++dy) {
-          const int i = 5 * ti + dy;
-          const uint32_t v = *reinterpret_cast<const uint32_t*>(colw + i * PP);
-          uint32_t lo = v, hi = v;
-          if (edge_cta) {
-            // pixels outside the image do not take part (corner_detector.cpp:44 clips the window)
-            const int yh = OH * cy - 5 + i;
-            uint32_t keep = 0u;
-            if (yh >= 0 && yh < geo.hh) {
-#pragma unroll
-              for (int b = 0; b < 4; ++b) {
-                const int xh = OW * cx - 8 + 4 * wq + b;
-                if (xh >= 0 && xh < geo.hw) keep |= 0xFFu << (8 * b);
-              }
-            }
-            lo = v | ~keep;
-            hi = v & keep;
-          }
-          ve[dy] = lo & 0x00FF00FFu;
-          vo[dy] = __byte_perm(lo, 0u, 0x4341);
-          xe[dy] = hi & 0x00FF00FFu;
-          xo[dy] = __byte_perm(hi, 0u, 0x4341);
-        }
-        const uint32_t mne = __vimin3_u16x2(__vimin3_u16x2(ve[0], ve[1], ve[2]), ve[3], ve[4]);
-        const uint32_t mno = __vimin3_u16x2(__vimin3_u16x2(vo[0], vo[1], vo[2]), vo[3], vo[4]);
-        const uint32_t mxe = __vimax3_u16x2(__vimax3_u16x2(xe[0], xe[1], xe[2]), xe[3], xe[4]);
-        const uint32_t mxo = __vimax3_u16x2(__vimax3_u16x2(xo[0], xo[1], xo[2]), xo[3], xo[4]);
-        const uint32_t mn = __byte_perm(mne, mno, 0x6240), mx = __byte_perm(mxe, mxo, 0x6240);
-        *reinterpret_cast<uint32_t*>(cmn + ti * 96 + 4 * wq) = mn;  // cmn/cmx column index = j + 3
-        *reinterpret_cast<uint32_t*>(cmx + ti * 96 + 4 * wq) = mx;
-      }
-    }
-    __syncthreads();
+    // ---- phase D2: 5x5 tile min/max from five column extrema ----------------------------------------------------------
     if (tid < CTX * CTY) {
       const int ti = tid / CTX, tj = tid - ti * CTX;
       int mn = 255, mx = 0;
