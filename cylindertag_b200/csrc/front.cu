@@ -17,6 +17,7 @@
 // HBM traffic per frame (N = w*h): BGR input 3N read + N gray write + N/4 binary write; gray input N + N/4.
 #include "common.cuh"
 #include "kernels.cuh"
+#include <cstdlib>
 
 namespace ctag {
 
@@ -435,6 +436,400 @@ __global__ void __launch_bounds__(front::NT, 3) front_kernel(const __grid_consta
   }
 }
 
+// =====================================================================================================================
+// BGR input, sliding variant.  Vertically adjacent tiles share 22 of their 102 region rows (and 10 of their 50 half-res
+// rows).  A CTA therefore walks RUNS of consecutive tiles of one tile column top down and keeps the gray tile and the
+// half-res patch in shared memory between them: only the 80 new full-res rows are staged (TMA) and converted, only the
+// 40 new half-res rows go through the vertical pass.  The first tile of a run / of a column loads its 22 extra rows with
+// a second, 22-row tensor map.  Shared memory: [stage 3 x 192 x 80 | g | P | small], HT aliases the staging area
+// (74.4 KB per CTA, three CTAs per SM).
+namespace front {
+constexpr int SROWS = 80;            // rows staged per tile after the first
+constexpr int OVR = RH - SROWS;      // 22 rows shared with the tile above
+constexpr int SBOX = RW * SROWS;     // bytes of one colour box slot in the staging area
+struct SlideLayout {
+  static constexpr int stage = 0;
+  static constexpr int h = 0;  // HT (RH/2 x HP words = 19584 B) lives in the staging area between phase A and phase C
+  static constexpr int g = 3 * SBOX;
+  static constexpr int p = g + BOX;
+  static constexpr int small_ = p + P_BYTES;
+  static constexpr int tmin = small_;
+  static constexpr int tmax = small_ + 192;
+  static constexpr int cmn = small_ + 384;
+  static constexpr int cmx = small_ + 384 + 960;
+  static constexpr int thr16 = small_ + 2304 + 128;
+  static constexpr int mbar = small_ + 2304 + 128 + 640;
+  static constexpr int total = small_ + 2304 + 128 + 640 + 16;
+};
+static_assert(H_BYTES <= 3 * SBOX, "HT must fit into the staging area");
+}  // namespace front
+
+struct RunGrid {
+  int tiles_x, tiles_y, tiles_per_frame, ntiles;
+  uint32_t m_frame, m_col;  // floor(2^32 / tiles_per_frame), floor(2^32 / tiles_y)
+  int wave_runs;            // runs per full wave (= grid size)
+  int full_waves, len, tail_len, nruns;
+};
+
+// run r -> [t0, t1) in column-major tile order (frame, tile column, tile row)
+__device__ __forceinline__ void run_range(const RunGrid& rg, int r, int& t0, int& t1) {
+  const int full = rg.full_waves * rg.wave_runs;
+  if (r < full) {
+    t0 = r * rg.len;
+    t1 = t0 + rg.len;
+  } else {
+    t0 = full * rg.len + (r - full) * rg.tail_len;
+    t1 = t0 + rg.tail_len;
+  }
+  if (t1 > rg.ntiles) t1 = rg.ntiles;
+}
+__device__ __forceinline__ void run_tile_coords(const RunGrid& rg, int t, int& fr, int& cx, int& cy) {
+  uint32_t q = __umulhi((uint32_t)t, rg.m_frame);
+  uint32_t rem = (uint32_t)t - q * (uint32_t)rg.tiles_per_frame;
+  if (rem >= (uint32_t)rg.tiles_per_frame) { ++q; rem -= (uint32_t)rg.tiles_per_frame; }
+  uint32_t c = __umulhi(rem, rg.m_col);
+  uint32_t r = rem - c * (uint32_t)rg.tiles_y;
+  if (r >= (uint32_t)rg.tiles_y) { ++c; r -= (uint32_t)rg.tiles_y; }
+  fr = (int)q; cx = (int)c; cy = (int)r;
+}
+
+// rows [row0, row0 + nrows) of the region of tile (fr, cx, cy) -> staging area (three colour box slots of SBOX bytes)
+__device__ __forceinline__ void issue_rows_load(const CUtensorMap* tmap, uint32_t mbar, uint32_t dst, int fr, int cx, int cy,
+                                                int row0, int nrows) {
+  using namespace front;
+  const int x0r = 2 * OW * cx - 16, y0r = 2 * OH * cy - 11;
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(3 * RW * nrows) : "memory");
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        :
+        : "r"(dst + b * SBOX), "l"(tmap), "r"(mbar), "r"(3 * x0r + RW * b), "r"(y0r + row0), "r"(fr)
+        : "memory");
+  }
+}
+
+// BGR -> gray for staged rows [0, nrows) -> gray tile rows [row0, row0 + nrows), and the global store of the owned ones.
+// thread -> (16-pixel group gq, row): eight consecutive lanes take the four groups of one colour box on two consecutive
+// rows; their 16-byte slots (3*(gq&3) + 4*row) mod 8 are all different, so the 128-bit loads from the box and the 128-bit
+// store into the gray tile are free of bank conflicts.
+__device__ __forceinline__ void convert_rows(const uint8_t* stage, uint8_t* g, int row0, int nrows, int tid, uint8_t* tile_base,
+                                             uint32_t gpitch, int x0r, int rlim, int img_w) {
+  using namespace front;
+  const int rest = tid >> 3;
+  const int gq = (rest % 3) * 4 + (tid & 3);
+  const int row = 2 * (rest / 3) + ((tid >> 2) & 1);  // staged rows row, row+32, row+64
+  const uint8_t* src = stage + (gq >> 2) * SBOX + (gq & 3) * 48 + row * RW;
+  uint8_t* dst = g + (row0 + row) * RW + gq * 16;
+  const bool own_col = gq >= 1 && gq <= 10 && x0r + gq * 16 < img_w;
+  const uint32_t toff = (uint32_t)(row0 + row) * gpitch + (uint32_t)gq * 16u;
+  constexpr int RS = NT / 12;
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const int sr = row + u * RS;
+    if (sr < nrows) {
+      const uint4* s4 = reinterpret_cast<const uint4*>(src + u * RS * RW);
+      const uint4 a = s4[0], b = s4[1], c = s4[2];
+      uint4 o;
+      o.x = gray4(a.x, a.y, a.z);
+      o.y = gray4(a.w, b.x, b.y);
+      o.z = gray4(b.z, b.w, c.x);
+      o.w = gray4(c.y, c.z, c.w);
+      *reinterpret_cast<uint4*>(dst + u * RS * RW) = o;
+      const int r = row0 + sr;  // region row
+      if (own_col && r >= 11 && r < rlim) *reinterpret_cast<uint4*>(tile_base + (toff + (uint32_t)(u * RS) * gpitch)) = o;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(front::NT, 3)
+    front_bgr_slide_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_constant__ CUtensorMap tmap_top, FrameGeom geo,
+                           RunGrid rg, uint8_t* __restrict__ gray_out, size_t gray_fstride, uint8_t* __restrict__ bin_out,
+                           size_t bin_fstride) {
+  using namespace front;
+  using L = SlideLayout;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x;
+  const uint32_t mbar = smem_u32(smem + L::mbar);
+  const uint32_t stage_u32 = smem_u32(smem + L::stage);
+  const uint8_t* stage = smem + L::stage;
+  uint32_t* HT = reinterpret_cast<uint32_t*>(smem + L::h);
+  uint8_t* g = smem + L::g;
+  uint8_t* P = smem + L::p;
+  uint8_t* tmin = smem + L::tmin;
+  uint8_t* tmax = smem + L::tmax;
+  uint8_t* cmn = smem + L::cmn;
+  uint8_t* cmx = smem + L::cmx;
+  uint8_t* thr16 = smem + L::thr16;
+
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  int run = blockIdx.x, t = 0, t_end = 0;
+  if (run < rg.nruns) run_range(rg, run, t, t_end);
+  bool valid = run < rg.nruns && t < t_end;
+  int fr = 0, cx = 0, cy = 0;
+  bool first = true;
+  if (valid) {
+    run_tile_coords(rg, t, fr, cx, cy);
+    if (tid == 0) issue_rows_load(&tmap_top, mbar, stage_u32, fr, cx, cy, 0, OVR);
+  }
+  uint32_t loads = 0;  // completed-phase counter of the mbarrier (parity = loads & 1)
+
+  while (valid) {
+    // ---- the tile after this one (the run continues one tile down / at the top of the next column, or the CTA's next
+    //      run starts) ---------------------------------------------------------------------------------------------
+    int nt = t + 1, nrun = run, nt_end = t_end;
+    int nfr = fr, ncx = cx, ncy = cy + 1;
+    bool nvalid = true, nfirst = false;
+    if (nt < t_end) {
+      if (ncy == rg.tiles_y) {  // top of the next tile column: nothing to reuse
+        ncy = 0;
+        nfirst = true;
+        if (++ncx == rg.tiles_x) ncx = 0, ++nfr;
+      }
+    } else {
+      nrun = run + gridDim.x;
+      nfirst = true;
+      nvalid = false;
+      if (nrun < rg.nruns) {
+        run_range(rg, nrun, nt, nt_end);
+        nvalid = nt < nt_end;
+        if (nvalid) run_tile_coords(rg, nt, nfr, ncx, ncy);
+      }
+    }
+
+    const int x0r = 2 * OW * cx - 16;  // full-res x of region column 0
+    const int y0r = 2 * OH * cy - 11;  // full-res y of region row 0
+    uint8_t* tile_base = gray_out + (size_t)fr * gray_fstride + (ptrdiff_t)y0r * geo.gpitch + x0r;
+    asm volatile("" : "+l"(tile_base));  // keep the pointer live: recomputing the 64-bit products per store costs more
+    const int rlim = min(11 + 2 * OH, geo.h - y0r);
+
+    if (!first) {
+      // Reuse from the tile above: its half-res rows 40..49 are rows 0..9 here, its column extrema of tile rows 8,9 are
+      // those of tile rows 0,1 (the gray rows were moved right after its horizontal pass).  Everybody has to be done
+      // with the previous tile's threshold phases first.
+      __syncthreads();
+      if (tid < 70) {  // 10 patch rows of PP = 112 bytes = 70 uint4
+        reinterpret_cast<uint4*>(P)[tid] = reinterpret_cast<const uint4*>(P + 40 * PP)[tid];
+      } else if (tid >= 96 && tid < 96 + 48) {  // 2 x 96 bytes of cmn, 2 x 96 bytes of cmx
+        const int q = tid - 96, arr = q / 24, w = q - arr * 24;
+        uint32_t* base = reinterpret_cast<uint32_t*>(arr ? cmx : cmn);
+        base[w] = base[8 * 24 + w];
+        base[24 + w] = base[9 * 24 + w];
+      }
+    }
+
+    // ---- phase A: BGR -> gray for the staged rows -----------------------------------------------------------------
+    mbar_wait(mbar, loads & 1);
+    ++loads;
+    if (first) {
+      convert_rows(stage, g, 0, OVR, tid, tile_base, (uint32_t)geo.gpitch, x0r, rlim, geo.w);
+      __syncthreads();  // staging area free again
+      if (tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue_rows_load(&tmap_main, mbar, stage_u32, fr, cx, cy, OVR, SROWS);
+      }
+      mbar_wait(mbar, loads & 1);
+      ++loads;
+    }
+    convert_rows(stage, g, OVR, SROWS, tid, tile_base, (uint32_t)geo.gpitch, x0r, rlim, geo.w);
+    __syncthreads();
+
+    // ---- replicate-border patch (TMA zero-fills outside the image; INTER_CUBIC uses BORDER_REPLICATE) ---------
+    {
+      const int rW = geo.w - x0r, rH = geo.h - y0r;
+      const bool left = (cx == 0), right = (rW < RW), top = (cy == 0), bottom = (rH < RH);
+      if (left | right | top | bottom) {
+        if (left)
+          for (int r = tid; r < RH; r += NT) g[r * RW + 15] = g[r * RW + 16];
+        if (right)
+          for (int r = tid; r < RH; r += NT) g[r * RW + rW] = g[r * RW + rW - 1];
+        __syncthreads();
+        if (top)
+          for (int c = tid; c < RW; c += NT) g[10 * RW + c] = g[11 * RW + c];
+        if (bottom)
+          for (int c = tid; c < RW; c += NT) g[rH * RW + c] = g[(rH - 1) * RW + c];
+        __syncthreads();
+      }
+    }
+
+    // ---- phase B: horizontal taps on row pairs (see front_kernel) into HT, which takes over the staging area -------
+    {
+      const uint32_t COEF = 0xFD1313FDu;  // (-3, 19, 19, -3) as signed bytes
+      const int k = tid % 24;
+      int rp = tid / 24;
+      const uint8_t* src = g + (2 * rp) * RW + 8 * k;
+      uint32_t* dst = HT + rp * HP + 4 * k;
+      const uint8_t* s0 = src + (k ? -4 : 0);
+      const uint8_t* s3 = src + (k < 23 ? 8 : 4);
+      for (; rp < RH / 2; rp += NT / 24, src += 2 * (NT / 24) * RW, s0 += 2 * (NT / 24) * RW, s3 += 2 * (NT / 24) * RW,
+                          dst += (NT / 24) * HP) {
+        const uint32_t a0 = *reinterpret_cast<const uint32_t*>(s0), a3 = *reinterpret_cast<const uint32_t*>(s3);
+        const uint2 a12 = *reinterpret_cast<const uint2*>(src);
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(s0 + RW), b3 = *reinterpret_cast<const uint32_t*>(s3 + RW);
+        const uint2 b12 = *reinterpret_cast<const uint2*>(src + RW);
+        const int h0 = dp4a_us(__byte_perm(a0, a12.x, 0x6543), COEF, 0), g0 = dp4a_us(__byte_perm(b0, b12.x, 0x6543), COEF, 0);
+        const int h1 = dp4a_us(__byte_perm(a12.x, a12.y, 0x4321), COEF, 0), g1 = dp4a_us(__byte_perm(b12.x, b12.y, 0x4321), COEF, 0);
+        const int h2 = dp4a_us(__byte_perm(a12.x, a12.y, 0x6543), COEF, 0), g2 = dp4a_us(__byte_perm(b12.x, b12.y, 0x6543), COEF, 0);
+        const int h3 = dp4a_us(__byte_perm(a12.y, a3, 0x4321), COEF, 0), g3 = dp4a_us(__byte_perm(b12.y, b3, 0x4321), COEF, 0);
+        uint4 o;
+        o.x = __byte_perm((uint32_t)h0, (uint32_t)g0, 0x5410);
+        o.y = __byte_perm((uint32_t)h1, (uint32_t)g1, 0x5410);
+        o.z = __byte_perm((uint32_t)h2, (uint32_t)g2, 0x5410);
+        o.w = __byte_perm((uint32_t)h3, (uint32_t)g3, 0x5410);
+        *reinterpret_cast<uint4*>(dst) = o;
+      }
+    }
+    __syncthreads();
+    // the gray tile is dead: hand its last 22 rows (patched) to the tile below; rows 11..21 of that tile are owned by it
+    // and have not been written to the gray output yet (here they are rows 91..101, outside this tile's owned rows)
+    if (nvalid && !nfirst && tid < OVR * RW / 16) {
+      const uint4 v = reinterpret_cast<const uint4*>(g + SROWS * RW)[tid];
+      reinterpret_cast<uint4*>(g)[tid] = v;
+      const int row = tid / 12, gq = tid - row * 12;  // row of the tile below
+      if (row >= 11 && gq >= 1 && gq <= 10 && x0r + gq * 16 < geo.w && y0r + SROWS + row < geo.h)
+        *reinterpret_cast<uint4*>(tile_base + ((uint32_t)(SROWS + row) * (uint32_t)geo.gpitch + (uint32_t)gq * 16u)) = v;
+    }
+
+    // ---- phase C+D1: vertical taps + rounding + column extrema for the NEW tile rows (all ten for a first tile) -----
+    const bool edge_cta = (cx == 0) || (cy == 0) || (OW * cx + OW + 5 > geo.hw) || (OH * cy + OH + 5 > geo.hh);
+    {
+      const int ti0 = first ? 0 : 2;
+      if (tid < 24 * (CTY - ti0)) {
+        const uint32_t C01 = 0x000013FDu;  // (-3, 19) on bytes 0,1
+        const uint32_t C23 = 0x0000FD13u;  // (19, -3)
+        const int k = tid % 24, ti = ti0 + tid / 24;
+        const uint32_t* src = HT + (5 * ti) * HP + 4 * k;
+        uint8_t* dst = P + (5 * ti) * PP + (POFF - HOFF) + 4 * k;
+        uint32_t keepx = 0xFFFFFFFFu;
+        if (edge_cta) {
+          keepx = 0u;
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb) {
+            const int xh = OW * cx - 8 + 4 * k + bb;
+            if (xh >= 0 && xh < geo.hw) keepx |= 0xFFu << (8 * bb);
+          }
+        }
+        uint4 a = *reinterpret_cast<const uint4*>(src);
+        uint32_t ve[5], vo[5], xe[5], xo[5];
+#pragma unroll
+        for (int dy = 0; dy < 5; ++dy) {
+          const uint4 b = *reinterpret_cast<const uint4*>(src + (dy + 1) * HP);
+          int v0 = dp2a_lo_ss(b.x, C23, dp2a_lo_ss(a.x, C01, 0));
+          int v1 = dp2a_lo_ss(b.y, C23, dp2a_lo_ss(a.y, C01, 0));
+          int v2 = dp2a_lo_ss(b.z, C23, dp2a_lo_ss(a.z, C01, 0));
+          int v3 = dp2a_lo_ss(b.w, C23, dp2a_lo_ss(a.w, C01, 0));
+          v0 = (v0 + 511 + ((v0 >> 10) & 1)) >> 10;
+          v1 = (v1 + 511 + ((v1 >> 10) & 1)) >> 10;
+          v2 = (v2 + 511 + ((v2 >> 10) & 1)) >> 10;
+          v3 = (v3 + 511 + ((v3 >> 10) & 1)) >> 10;
+          const uint32_t w = pack_sat_u8(v1, v0, pack_sat_u8(v3, v2, 0u));
+          *reinterpret_cast<uint32_t*>(dst + dy * PP) = w;
+          uint32_t lo = w, hi = w;
+          if (edge_cta) {
+            const int yh = OH * cy - 5 + 5 * ti + dy;
+            const uint32_t keep = (yh >= 0 && yh < geo.hh) ? keepx : 0u;
+            lo = w | ~keep;
+            hi = w & keep;
+          }
+          ve[dy] = lo & 0x00FF00FFu;
+          vo[dy] = __byte_perm(lo, 0u, 0x4341);
+          xe[dy] = hi & 0x00FF00FFu;
+          xo[dy] = __byte_perm(hi, 0u, 0x4341);
+          a = b;
+        }
+        const uint32_t mne = __vimin3_u16x2(__vimin3_u16x2(ve[0], ve[1], ve[2]), ve[3], ve[4]);
+        const uint32_t mno = __vimin3_u16x2(__vimin3_u16x2(vo[0], vo[1], vo[2]), vo[3], vo[4]);
+        const uint32_t mxe = __vimax3_u16x2(__vimax3_u16x2(xe[0], xe[1], xe[2]), xe[3], xe[4]);
+        const uint32_t mxo = __vimax3_u16x2(__vimax3_u16x2(xo[0], xo[1], xo[2]), xo[3], xo[4]);
+        *reinterpret_cast<uint32_t*>(cmn + ti * 96 + 4 * k) = __byte_perm(mne, mno, 0x6240);
+        *reinterpret_cast<uint32_t*>(cmx + ti * 96 + 4 * k) = __byte_perm(mxe, mxo, 0x6240);
+      }
+    }
+    __syncthreads();
+    // HT is dead, the staging area is free: load the next tile's rows behind the threshold phases
+    if (tid == 0 && nvalid) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (nfirst) issue_rows_load(&tmap_top, mbar, stage_u32, nfr, ncx, ncy, 0, OVR);
+      else issue_rows_load(&tmap_main, mbar, stage_u32, nfr, ncx, ncy, OVR, SROWS);
+    }
+
+    // ---- phase D2: 5x5 tile min/max from five column extrema ----------------------------------------------------------
+    if (tid < CTX * CTY) {
+      const int ti = tid / CTX, tj = tid - ti * CTX;
+      int mn = 255, mx = 0;
+#pragma unroll
+      for (int dx = 0; dx < 5; ++dx) {
+        mn = min(mn, (int)cmn[ti * 96 + HOFF + 5 * tj + dx]);
+        mx = max(mx, (int)cmx[ti * 96 + HOFF + 5 * tj + dx]);
+      }
+      tmin[tid] = (uint8_t)mn;
+      tmax[tid] = (uint8_t)mx;
+    }
+    __syncthreads();
+
+    // ---- phase E: 3x3 tile dilation -> integer threshold per owned tile (corner_detector.cpp:54-78) -----------
+    if (tid < OTX * OTY) {
+      const int oi = tid / OTX, oj = tid - oi * OTX;
+      const int ty = OTY * cy + oi, tx = OTX * cx + oj;
+      int tt = 0;  // border ring / outside: threshold 0 -> background (SURVEY C-1)
+      if (tx >= 1 && tx <= geo.cn - 2 && ty >= 1 && ty <= geo.rn - 2) {
+        int mn = 255, mx = 0;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            mn = min(mn, (int)tmin[(oi + dy) * CTX + oj + dx]);
+            mx = max(mx, (int)tmax[(oi + dy) * CTX + oj + dx]);
+          }
+        const float thr = fminf(0.3f, __fmul_rn(__fadd_rn(lut255(mx), lut255(mn)), 0.5f));
+        tt = min(max((int)(thr * 255.0f), 0), 255);
+        while (tt > 0 && !(lut255(tt - 1) < thr)) --tt;
+        while (tt < 256 && lut255(tt) < thr) ++tt;
+      }
+      uint8_t* dst = thr16 + oi * OW + 5 * oj;
+#pragma unroll
+      for (int q = 0; q < 5; ++q) dst[q] = (uint8_t)tt;
+    }
+    __syncthreads();
+
+    // ---- phase F: threshold the owned 80x40 pixels, 16 per thread, 128-bit stores -----------------------------
+    if (tid < OH * 5) {
+      const int i = tid / 5, q = tid - i * 5;
+      const int yh = OH * cy + i, xh0 = OW * cx + 16 * q;
+      if (yh < geo.hh && xh0 < geo.bpitch) {
+        const uint4 v = *reinterpret_cast<const uint4*>(P + (i + 5) * PP + 16 + 16 * q);
+        const uint4 th = *reinterpret_cast<const uint4*>(thr16 + (i / 5) * OW + 16 * q);
+        const uint32_t vw[4] = {v.x, v.y, v.z, v.w}, tw[4] = {th.x, th.y, th.z, th.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int ww = 0; ww < 4; ++ww) {
+          const uint32_t d = (vw[ww] | 0x80808080u) - tw[ww];
+          const uint32_t lt = ~(d | vw[ww]) & 0x80808080u;
+          o[ww] = (lt >> 7) * 255u;
+        }
+        if (xh0 + 16 > geo.hw) {
+#pragma unroll
+          for (int ww = 0; ww < 4; ++ww)
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb)
+              if (xh0 + 4 * ww + bb >= geo.hw) o[ww] &= ~(255u << (8 * bb));
+        }
+        *reinterpret_cast<uint4*>(bin_out + (size_t)fr * bin_fstride + (size_t)yh * geo.bpitch + xh0) =
+            make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+
+    t = nt, t_end = nt_end, run = nrun, valid = nvalid, first = nfirst;
+    fr = nfr, cx = ncx, cy = ncy;
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -480,6 +875,40 @@ static int launch_front_t(const CUtensorMap& tmap, int n, const FrameGeom& geo, 
   return CTAG_OK;
 }
 
+static int launch_front_slide(const CUtensorMap& tmap_main, const CUtensorMap& tmap_top, int n, const FrameGeom& geo,
+                              uint8_t* gray_out, size_t gray_fstride, uint8_t* bin_out, size_t bin_fstride, cudaStream_t stream) {
+  using namespace front;
+  CTAG_CUDA_CHECK(cudaFuncSetAttribute(front_bgr_slide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SlideLayout::total));
+  int dev = 0, sms = 0, per_sm = 0;
+  CTAG_CUDA_CHECK(cudaGetDevice(&dev));
+  CTAG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CTAG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, front_bgr_slide_kernel, NT, SlideLayout::total));
+  if (per_sm < 1) per_sm = 1;
+  RunGrid rg;
+  rg.tiles_x = (geo.hw + OW - 1) / OW;
+  rg.tiles_y = (geo.hh + OH - 1) / OH;
+  rg.tiles_per_frame = rg.tiles_x * rg.tiles_y;
+  rg.ntiles = rg.tiles_per_frame * n;
+  rg.m_frame = rg.tiles_per_frame > 1 ? (uint32_t)((1ull << 32) / (uint64_t)rg.tiles_per_frame) : 0xFFFFFFFFu;
+  rg.m_col = rg.tiles_y > 1 ? (uint32_t)((1ull << 32) / (uint64_t)rg.tiles_y) : 0xFFFFFFFFu;
+  // Runs of consecutive tiles (column-major order: a run walks down a tile column) are dealt round-robin to one wave of
+  // resident CTAs, so neighbouring CTAs work on neighbouring columns at the same time (their halo columns meet in L2).
+  // Full waves use runs of kRun tiles; what is left is split evenly over the CTAs so that everybody finishes together.
+  const int kRun = rg.tiles_y;  // whole tile columns: one 22-row top load per column
+  int grid = sms * per_sm;
+  if (grid > rg.ntiles) grid = rg.ntiles;
+  rg.wave_runs = grid;
+  rg.len = kRun;
+  rg.full_waves = rg.ntiles / (grid * kRun);
+  const int rest = rg.ntiles - rg.full_waves * grid * kRun;
+  rg.tail_len = rest > 0 ? (rest + grid - 1) / grid : 1;
+  rg.nruns = rg.full_waves * grid + (rest > 0 ? (rest + rg.tail_len - 1) / rg.tail_len : 0);
+  front_bgr_slide_kernel<<<grid, NT, SlideLayout::total, stream>>>(tmap_main, tmap_top, geo, rg, gray_out, gray_fstride, bin_out,
+                                                                  bin_fstride);
+  CTAG_CUDA_CHECK(cudaGetLastError());
+  return CTAG_OK;
+}
+
 int launch_front(const void* frames_dev, int n, const FrameGeom& geo, int channels, size_t pitch, size_t frame_stride,
                  uint8_t* gray_out, size_t gray_fstride, uint8_t* bin_out, size_t bin_fstride, cudaStream_t stream) {
   using namespace front;
@@ -500,6 +929,20 @@ int launch_front(const void* frames_dev, int n, const FrameGeom& geo, int channe
   if (r != CUDA_SUCCESS) {
     set_last_error_text("cuTensorMapEncodeTiled failed");
     return CTAG_ERR_CUDA;
+  }
+  if (channels == 3 && !getenv("CTAG_FRONT_NOSLIDE")) {
+    CUtensorMap tmap_main, tmap_top;
+    cuuint32_t box_main[3] = {(cuuint32_t)RW, (cuuint32_t)SROWS, 1}, box_top[3] = {(cuuint32_t)RW, (cuuint32_t)OVR, 1};
+    if (enc(&tmap_main, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(frames_dev), dims, strides, box_main, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ||
+        enc(&tmap_top, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(frames_dev), dims, strides, box_top, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      set_last_error_text("cuTensorMapEncodeTiled failed");
+      return CTAG_ERR_CUDA;
+    }
+    return launch_front_slide(tmap_main, tmap_top, n, geo, gray_out, gray_fstride, bin_out, bin_fstride, stream);
   }
   return channels == 3 ? launch_front_t<3>(tmap, n, geo, gray_out, gray_fstride, bin_out, bin_fstride, stream)
                        : launch_front_t<1>(tmap, n, geo, gray_out, gray_fstride, bin_out, bin_fstride, stream);
