@@ -509,6 +509,17 @@ __device__ __forceinline__ void issue_rows_load(const CUtensorMap* tmap, uint32_
   }
 }
 
+// the same rows into L2 only: issued a phase ahead of the real load, which then does not wait on DRAM
+__device__ __forceinline__ void prefetch_rows_l2(const CUtensorMap* tmap, int fr, int cx, int cy, int row0) {
+  using namespace front;
+  const int x0r = 2 * OW * cx - 16, y0r = 2 * OH * cy - 11;
+#pragma unroll
+  for (int b = 0; b < 3; ++b)
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(3 * x0r + RW * b),
+                 "r"(y0r + row0), "r"(fr)
+                 : "memory");
+}
+
 // BGR -> gray for staged rows [0, nrows) -> gray tile rows [row0, row0 + nrows), and the global store of the owned ones.
 // thread -> (16-pixel group gq, row): eight consecutive lanes take the four groups of one colour box on two consecutive
 // rows; their 16-byte slots (3*(gq&3) + 4*row) mod 8 are all different, so the 128-bit loads from the box and the 128-bit
@@ -639,6 +650,15 @@ __global__ void __launch_bounds__(front::NT, 3)
     }
     convert_rows(stage, g, OVR, SROWS, tid, tile_base, (uint32_t)geo.gpitch, x0r, rlim, geo.w);
     __syncthreads();
+    // the staging area is busy (HT) until the vertical pass is over: meanwhile pull the next tile's rows into L2
+    if (tid == 0 && nvalid) {
+      if (nfirst) {
+        prefetch_rows_l2(&tmap_top, nfr, ncx, ncy, 0);
+        prefetch_rows_l2(&tmap_main, nfr, ncx, ncy, OVR);
+      } else {
+        prefetch_rows_l2(&tmap_main, nfr, ncx, ncy, OVR);
+      }
+    }
 
     // ---- replicate-border patch (TMA zero-fills outside the image; INTER_CUBIC uses BORDER_REPLICATE) ---------
     {

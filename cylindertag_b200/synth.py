@@ -273,3 +273,34 @@ def synthetic_frame(seed: int, w: int, h: int, state: np.ndarray, n_markers: int
     frame = render_frame(w, h, [s for _, s in specs], rng, blur_sigma=float(rng.uniform(0.3, 1.2)),
                          noise_sigma=float(rng.uniform(0.5, 3.0)), channels=channels)
     return frame, specs
+
+
+def video_sequence(gray: np.ndarray, n_frames: int = 120, seed: int = 2024, first: int = 0, count: int | None = None):
+    """BASELINE.json config 2 substitute: the reference's test.avi is not shipped, so a deterministic
+    `n_frames`-long sequence is made from test.bmp by seeded small homographies (rotation <= 3 deg, scale 0.95-1.05,
+    shift <= 20 px, perspective terms <= 2e-5), Gaussian blur sigma in [0, 1] and noise sigma in [0, 3] DN, all drawn
+    from ONE default_rng(seed) stream in frame order.  Returns frames [first, first + count) as a (count, h, w) u8 array
+    (the draws of the skipped frames are still consumed, so frame i is the same whatever slice is asked for)."""
+    h, w = gray.shape
+    rng = np.random.default_rng(seed)
+    count = n_frames - first if count is None else count
+    out = []
+    for i in range(min(n_frames, first + count)):
+        ang = math.radians(rng.uniform(-3.0, 3.0))
+        sc = rng.uniform(0.95, 1.05)
+        tx, ty = rng.uniform(-20.0, 20.0, size=2)
+        px, py = rng.uniform(-2e-5, 2e-5, size=2)
+        blur = rng.uniform(0.0, 1.0)
+        nsig = rng.uniform(0.0, 3.0)
+        nseed = int(rng.integers(0, 2**31 - 1))
+        if i < first:
+            continue
+        c, s = sc * math.cos(ang), sc * math.sin(ang)
+        cx, cy = 0.5 * w, 0.5 * h
+        H = np.array([[c, -s, cx - c * cx + s * cy + tx], [s, c, cy - s * cx - c * cy + ty], [px, py, 1.0 - px * cx - py * cy]])
+        fr = cv2.warpPerspective(gray, H, (w, h), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REPLICATE)
+        if blur > 0.05:
+            fr = cv2.GaussianBlur(fr, (0, 0), blur)
+        noise = np.random.default_rng(nseed).normal(0.0, nsig, size=fr.shape)
+        out.append(np.clip(np.rint(fr.astype(np.float64) + noise), 0, 255).astype(np.uint8))
+    return np.stack(out)
