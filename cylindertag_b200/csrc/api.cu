@@ -6,6 +6,7 @@
 // come back in FIFO order).
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <fstream>
@@ -43,7 +44,18 @@ static FrameGeom make_geom(int w, int h) {
   return g;
 }
 
-constexpr int kSlots = 4;
+constexpr int kMaxSlots = 8;
+// batches in flight per detector: 4 unless CTAG_SLOTS (1..8) says otherwise (read once per process)
+static int slot_count() {
+  static int n = 0;
+  if (!n) {
+    const char* e = getenv("CTAG_SLOTS");
+    int v = e ? atoi(e) : 4;
+    n = v < 1 ? 1 : (v > kMaxSlots ? kMaxSlots : v);
+  }
+  return n;
+}
+#define kSlots (slot_count())
 constexpr int kQuadCap = CTAG_MAX_FRAME_QUADS;
 constexpr int kFeatCap = CTAG_MAX_FRAME_FEATURES;
 constexpr int kMarkerCap = CTAG_MAX_FRAME_FEATURES / 2;
@@ -92,7 +104,7 @@ struct ctag_detector {
   int rows = 0, cols = 0, feature_size = 0;
   int32_t* d_state = nullptr;
   uint16_t* d_pick_table = nullptr;  // cv::fitLine restart subsets per point count (fit_core.cuh)
-  Slot slot[kSlots];
+  Slot slot[kMaxSlots];
   cudaEvent_t epoch = nullptr;  // recorded once at creation: origin of ctag_stage_timeline_ms
   float stage_stamp_ms[CTAG_STAGE_COUNT + 1] = {};
   int next_enqueue = 0, next_collect = 0, in_flight = 0;
@@ -466,7 +478,7 @@ int ctag_detect_batch(ctag_detector* d, const void* frames, int n, int w, int h,
   const size_t dfs = dpitch * h;
   const int chunk = n < 8 ? n : (n + 3) / 4;  // small batches stay whole (the debug getters then see all frames)
   int done = 0, queued = 0;
-  int q_first[kSlots], q_count[kSlots];
+  int q_first[kMaxSlots], q_count[kMaxSlots];
   while (done < n) {
     while (queued < n && d->in_flight < kSlots) {
       const int c = n - queued < chunk ? n - queued : chunk;
