@@ -72,6 +72,9 @@ SIGNATURES = {
     "ctag_stage_timeline_ms": (_I, [_P, ctypes.POINTER(ctypes.c_float)]),
     "ctag_estimate_pose": (_I, [_P, _P, _I, _P, _P, _I, _P, _P, _P]),
     "ctag_pose_select_points": (_I, [_P, _P, _P, _I]),
+    "ctag_project_points": (_I, [_P, _I, _P, _P, _P, _P, _I, _P]),
+    "ctag_gray_to_3ch": (_I, [_P, _I, _I, _SZ, _P, _SZ]),
+    "ctag_draw_axis": (_I, [_P, _I, _I, _SZ, _P, _P, _I, _P, _P, _P, _P, _I, _P, _P, _I]),
     "ctag_last_launch_count": (_I, [_P]),
     "ctag_stream": (_P, [_P]),
     "ctag_debug_get_gray": (_I, [_P, _I, _P, _SZ]),

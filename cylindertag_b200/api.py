@@ -147,26 +147,32 @@ class CylinderTag:
         return poses
 
     def drawAxis(self, img, markers, reconstruct_model, poses, camera, axisLength=5):
-        """CylinderTag.cpp:211-246 without the imshow window: returns the BGR overlay image."""
-        import cv2
-        out = cv2.cvtColor(np.asarray(img), cv2.COLOR_GRAY2BGR)
+        """CylinderTag.cpp:211-246 without the imshow window: returns the 3-channel overlay image (host code in the
+        library: ctag_gray_to_3ch + ctag_draw_axis per pose; pose[i] is paired with markers[i] like the reference)."""
+        lib = C.load()
+        gray = np.ascontiguousarray(img, np.uint8)
+        h, w = gray.shape
+        out = np.empty((h, w, 3), np.uint8)
+        rc = lib.ctag_gray_to_3ch(gray.ctypes.data, w, h, gray.strides[0], out.ctypes.data, out.strides[0])
+        if rc != C.OK:
+            raise RuntimeError("drawAxis, " + C.strerror(rc))
+        K = np.ascontiguousarray(camera.Intrinsic, np.float32).reshape(9)
+        D = np.ascontiguousarray(camera.distCoeffs, np.float32).reshape(-1)
         for i, pose in enumerate(poses):
-            if i >= len(markers):
-                break
+            if i >= len(markers) or not 0 <= pose.markerID < len(reconstruct_model):
+                continue
             model = reconstruct_model[pose.markerID]
-            pts3 = [model.corners[markers[i].featurePos[j] * 8 + k] for j in range(len(markers[i].cornerLists)) for k in range(8)]
-            base = model.base.astype(np.float64)
-            pts3 += [base, base + model.axis * axisLength, base + np.array([0.0372, 0.0372, 0.9986]) * axisLength,
-                     base + np.array([0.9980, -0.0520, -0.0353]) * axisLength]
-            ip, _ = cv2.projectPoints(np.array(pts3, np.float64), pose.rvec, pose.tvec, camera.Intrinsic.astype(np.float64),
-                                      camera.distCoeffs.astype(np.float64))
-            ip = ip.reshape(-1, 2)
-            for p in ip[:-5]:
-                cv2.circle(out, (int(p[0]), int(p[1])), 5, (255, 234, 32), -1)
-            o = (int(ip[-4][0]), int(ip[-4][1]))
-            for k, col in ((-3, (255, 0, 0)), (-2, (0, 255, 0)), (-1, (0, 0, 255))):
-                cv2.arrowedLine(out, o, (int(ip[k][0]), int(ip[k][1])), col, 10, cv2.LINE_AA, 0, 0.2)
-            cv2.circle(out, o, 8, (247, 235, 235), -1)
+            rec = marker_to_record(markers[i])
+            corners3 = np.ascontiguousarray(model.corners, np.float32)
+            base = np.ascontiguousarray(model.base, np.float32)
+            axis = np.ascontiguousarray(model.axis, np.float32)
+            rvec = np.ascontiguousarray(pose.rvec, np.float64).reshape(3)
+            tvec = np.ascontiguousarray(pose.tvec, np.float64).reshape(3)
+            rc = lib.ctag_draw_axis(out.ctypes.data, w, h, out.strides[0], rec.ctypes.data, corners3.ctypes.data,
+                                    corners3.shape[0], base.ctypes.data, axis.ctypes.data, K.ctypes.data, D.ctypes.data,
+                                    int(D.size), rvec.ctypes.data, tvec.ctypes.data, int(axisLength))
+            if rc != C.OK:
+                raise RuntimeError("drawAxis, " + C.strerror(rc))
         return out
 
 

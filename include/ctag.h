@@ -150,6 +150,24 @@ CTAG_API int ctag_estimate_pose(const ctag_marker* marker, const float* model_co
 /* The corner selection alone: fills (feature index, corner index 0..7) pairs, returns their number. */
 CTAG_API int ctag_pose_select_points(const ctag_marker* marker, int* feature_of_point, int* corner_of_point, int cap);
 
+/* ---- drawAxis overlay (host code, no GPU work) --------------------------------- */
+
+/* cv::projectPoints as called at CylinderTag.cpp:234: points3 [n][3] model points -> out_xy [n][2] pixels through
+ * R(rvec) X + tvec, the pinhole division, the k1 k2 p1 p2 k3 lens model and the 3x3 row-major camera matrix. */
+CTAG_API int ctag_project_points(const float* points3, int n, const double* rvec, const double* tvec, const float* intrinsic,
+                                 const float* dist, int n_dist, float* out_xy);
+/* cvtColor(img, imgMark, COLOR_GRAY2RGB) (CylinderTag.cpp:214): gray w x h -> three equal channels, interleaved. */
+CTAG_API int ctag_gray_to_3ch(const uint8_t* gray, int w, int h, size_t pitch, uint8_t* out3, size_t out_pitch);
+/* The body of CylinderTag::drawAxis's loop over poses (CylinderTag.cpp:219-243) for one (marker, pose) pair, drawn
+ * into a caller-owned 3-channel 8-bit image instead of an imshow window: filled circles (r = 5, colour 255,234,32) on
+ * the projected model corners of the marker's features, arrows (thickness 10, tip 0.2; colours 255,0,0 / 0,255,0 /
+ * 0,0,255 in channel order) from the projected base point along the model axis and the two directions the reference
+ * hard-codes, scaled by axis_length, and a filled circle (r = 8, colour 247,235,235) on the base point.
+ *   model_corners [n_model_corners][3], base[3], axis[3]: the ModelInfo of the pose (.model, CylinderTag.cpp:168-188) */
+CTAG_API int ctag_draw_axis(uint8_t* img3, int w, int h, size_t pitch, const ctag_marker* marker, const float* model_corners,
+                            int n_model_corners, const float* base, const float* axis, const float* intrinsic,
+                            const float* dist, int n_dist, const double* rvec, const double* tvec, int axis_length);
+
 /* ---- instrumentation ------------------------------------------------------------------------ */
 
 /* Stage identifiers for ctag_stage_time_ms / ctag_debug_*. */

@@ -13,7 +13,9 @@
 //   estimatePose(img, markers, models, camera, poses, useDensePoseRefine)   CylinderTag.cpp:198-209
 //       (host side, ctag_estimate_pose: corner selection, undistortion, EPnP, Levenberg-Marquardt; markers without a
 //        model are erased from the result like the reference's markerID == -1 poses)
-// drawAxis is a debugging overlay; the Python mirror (cylindertag_b200.CylinderTag) has it.
+//   drawAxis(img, markers, models, poses, camera, axisLength)   CylinderTag.cpp:211-246
+//       (host side, ctag_draw_axis; the reference shows the overlay with imshow, here it is kept in overlay() as a
+//        3-channel image -- there is no highgui in this build)
 #pragma once
 #include <cstdint>
 #include <cstdio>
@@ -176,6 +178,39 @@ inline void estimate_poses(const std::vector<MarkerInfo>& markers, const std::ve
   }
 }
 
+// 3-channel 8-bit image the overlay is drawn into (rows x cols x 3, interleaved, channel order of the reference's
+// Scalar values)
+struct Overlay {
+  int rows = 0, cols = 0;
+  std::vector<uint8_t> data;
+};
+
+// CylinderTag::drawAxis (CylinderTag.cpp:211-246) through ctag_gray_to_3ch / ctag_draw_axis: gray -> 3 channels, then
+// per pose the projected model corners, the three arrows and the base point.  pose[i] is drawn with markers[i] like
+// the reference does (so after estimatePose erased a marker without a model the pairs are shifted, SURVEY 8f-4:
+// replicated, guarded against running off the end).  Host code only: no detector, no GPU.
+inline void draw_axis(const ImageView& img, const std::vector<MarkerInfo>& markers, const std::vector<ModelInfo>& reconstruct_model,
+                      const std::vector<PoseInfo>& pose, const CamInfo& camera, int axisLength, Overlay& out) {
+  out.rows = img.rows, out.cols = img.cols;
+  out.data.assign((size_t)img.rows * img.cols * 3, 0);
+  int rc = ctag_gray_to_3ch(img.data, img.cols, img.rows, img.step, out.data.data(), (size_t)img.cols * 3);
+  if (rc != CTAG_OK) throw std::string("drawAxis, ") + ctag_strerror(rc) + "\n";
+  for (size_t i = 0; i < pose.size() && i < markers.size(); ++i) {
+    const int id = pose[i].markerID;
+    if (id < 0 || id >= (int)reconstruct_model.size()) continue;
+    const ModelInfo& model = reconstruct_model[id];
+    ctag_marker rec = to_record(markers[i]);
+    std::vector<float> pts(model.corners.size() * 3);
+    for (size_t k = 0; k < model.corners.size(); ++k)
+      pts[3 * k] = model.corners[k].x, pts[3 * k + 1] = model.corners[k].y, pts[3 * k + 2] = model.corners[k].z;
+    const float base[3] = {model.base.x, model.base.y, model.base.z}, axis[3] = {model.axis.x, model.axis.y, model.axis.z};
+    rc = ctag_draw_axis(out.data.data(), img.cols, img.rows, (size_t)img.cols * 3, &rec, pts.data(), (int)model.corners.size(),
+                        base, axis, camera.Intrinsic, camera.distCoeffs.data(), (int)camera.distCoeffs.size(), pose[i].rvec,
+                        pose[i].tvec, axisLength);
+    if (rc != CTAG_OK) throw std::string("drawAxis, ") + ctag_strerror(rc) + "\n";
+  }
+}
+
 class CylinderTag {
  public:
   // Load state matrix of CylinderTag from file (CylinderTag.cpp:6-9,16-41)
@@ -241,11 +276,20 @@ class CylinderTag {
     estimate_poses(markers, reconstruct_model, camera, pose);
   }
 
+  // Axis overlay (CylinderTag.cpp:211-246).  The reference opens a highgui window; here the image is kept and returned
+  // by overlay() (draw_axis above does the work; host code).
+  void drawAxis(const ImageView& img, const std::vector<MarkerInfo>& markers, const std::vector<ModelInfo>& reconstruct_model,
+                const std::vector<PoseInfo>& pose, const CamInfo& camera, int axisLength = 5) {
+    draw_axis(img, markers, reconstruct_model, pose, camera, axisLength, overlay_);
+  }
+  const Overlay& overlay() const { return overlay_; }
+
   ctag_detector* handle() { return det_; }
 
  private:
   static constexpr int kCap = 64;
   ctag_detector* det_ = nullptr;
+  Overlay overlay_;
 
   static MarkerInfo convert(const ctag_marker& c) {
     MarkerInfo m;

@@ -99,6 +99,17 @@ inline Image imread(const std::string& path) {
   return img;
 }
 
+// binary PPM (P6) / PGM (P5) writer for 3- / 1-channel 8-bit data, e.g. the drawAxis overlay
+inline bool imwrite_pnm(const std::string& path, const uint8_t* data, int rows, int cols, int channels) {
+  if (!data || rows <= 0 || cols <= 0 || (channels != 1 && channels != 3)) return false;
+  FILE* f = std::fopen(path.c_str(), "wb");
+  if (!f) return false;
+  std::fprintf(f, "P%d\n%d %d\n255\n", channels == 3 ? 6 : 5, cols, rows);
+  const size_t n = (size_t)rows * cols * channels;
+  const bool ok = std::fwrite(data, 1, n, f) == n;
+  return std::fclose(f) == 0 && ok;
+}
+
 // cv::cvtColor(COLOR_BGR2GRAY) for 8-bit data (main.cpp:36): (3735 B + 19235 G + 9798 R + 16384) >> 15.
 // (The batched C entry point ctag_detect_batch(channels = 3) does this on the GPU; this host version is for the
 //  single-image flow of the mirror class, whose detect() takes a gray image like the reference's.)

@@ -63,6 +63,29 @@ int main(int argc, char** argv) {
       for (int k = 0; k < 3; ++k) er = std::fmax(er, std::fabs(poses[0].rvec[k] - rv[k])), et = std::fmax(et, std::fabs(poses[0].tvec[k] - tv[k]));
     std::printf("poses=%zu model_index=%d rot_err_ok=%d trans_err_ok=%d\n", poses.size(), poses.empty() ? -9 : poses[0].markerID,
                 (int)(poses.size() == 1 && er < 1e-4), (int)(poses.size() == 1 && et < 3e-2));
+    // drawAxis overlay (host code): a flat gray image, the recovered pose; the corner discs carry (255, 234, 32) at the
+    // image points the marker was built from, everything far from the drawing stays gray
+    if (poses.size() == 1) {
+      const int W = 1920, H = 1200;
+      std::vector<uint8_t> gray((size_t)W * H, 90);
+      Overlay ov;
+      // the test pose looks far off-axis: move the principal point so that the marker lands inside the image
+      CamInfo cs = cc;
+      const float sx = 960.f - mk.cornerLists[1][0].x, sy = 600.f - mk.cornerLists[1][0].y;
+      cs.Intrinsic[2] += sx, cs.Intrinsic[5] += sy;
+      draw_axis(ImageView{gray.data(), H, W, (size_t)W, 1}, {mk}, mm, poses, cs, 30, ov);
+      int discs = 0, painted = 0;
+      for (int f = 0; f < 3; ++f)
+        for (int k = 0; k < 8; ++k) {
+          if (f == 2 && k == 7) continue;  // the reference's loop bound skips the last corner
+          const int px = (int)std::lround(mk.cornerLists[f][k].x + sx), py = (int)std::lround(mk.cornerLists[f][k].y + sy);
+          if (px < 0 || py < 0 || px >= W || py >= H) continue;
+          const uint8_t* p = &ov.data[((size_t)py * W + px) * 3];
+          discs += (p[0] == 255 && p[1] == 234 && p[2] == 32);
+        }
+      for (size_t i = 0; i < (size_t)W * H; ++i) painted += !(ov.data[3 * i] == 90 && ov.data[3 * i + 1] == 90 && ov.data[3 * i + 2] == 90);
+      std::printf("overlay=%dx%d discs=%d painted_ok=%d\n", ov.cols, ov.rows, discs, (int)(painted > 1500 && painted < 200000));
+    }
   }
   return 0;
 }

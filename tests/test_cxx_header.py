@@ -18,6 +18,9 @@ def test_cxx_header_compiles_links_and_reports_errors(tmp_path):
                           os.path.join(data, "cameraParams.yml")], capture_output=True, text=True, check=True).stdout
     assert "missing: load_from_file, could not open the file" in out
     assert "poses=1 model_index=0 rot_err_ok=1 trans_err_ok=1" in out  # host-side pose stage, no GPU involved
+    line = next(l for l in out.splitlines() if l.startswith("overlay="))  # host-side drawAxis, no GPU involved
+    assert line.startswith("overlay=1920x1200 ") and line.endswith("painted_ok=1")
+    assert int(line.split("discs=")[1].split()[0]) >= 20  # 23 marked corners; arrows may cover a few
     import torch
     if torch.cuda.is_available():
         assert "created=1 models=6" in out and "fx=4328.5" in out and "ndist=5" in out

@@ -22,8 +22,9 @@ def test_main_image_flow(tmp_path, test_gray, marker_path):
                     "-o", str(exe), "-L", libdir, "-lctag_b200", f"-Wl,-rpath,{libdir}"], check=True)
     bmp = tmp_path / "test.bmp"
     cv2.imwrite(str(bmp), cv2.cvtColor(test_gray, cv2.COLOR_GRAY2BGR))  # 24-bit like the reference's test.bmp
+    ppm = tmp_path / "overlay.ppm"
     out = subprocess.run([str(exe), str(bmp), marker_path, os.path.join(DATA, "CTag_2f12c.model"),
-                          os.path.join(DATA, "cameraParams.yml")], capture_output=True, text=True, check=True).stdout
+                          os.path.join(DATA, "cameraParams.yml"), str(ppm)], capture_output=True, text=True, check=True).stdout
     lines = out.strip().splitlines()
     assert lines[0] == "markers 5 poses 5"
     assert [int(l.split()[1]) for l in lines if l.startswith("marker ")] == [23, 0, 1, 17, 5]
@@ -38,3 +39,17 @@ def test_main_image_flow(tmp_path, test_gray, marker_path):
         tvec = np.array([float(v) for v in g[10:13]])
         assert np.abs(rvec - w[1]).max() < 2e-4            # printed with 5 decimals
         assert np.linalg.norm(tvec - w[2]) < 2e-4 * np.linalg.norm(w[2]) + 1e-3
+    # drawAxis(..., 30) of the demo (main.cpp:41) went to a file: same picture as the Python mirror draws from its own
+    # detections and poses (both call ctag_draw_axis; poses agree to ~1e-6, so at most a few edge pixels may differ)
+    from cylindertag_b200 import CylinderTag
+    overlay = cv2.imread(str(ppm), cv2.IMREAD_UNCHANGED)[..., ::-1]  # P6 is read as RGB -> BGR by OpenCV: undo
+    tag = CylinderTag(marker_path)
+    models = tag.loadModel(os.path.join(DATA, "CTag_2f12c.model"))
+    cam = tag.loadCamera(os.path.join(DATA, "cameraParams.yml"))
+    markers = []
+    tag.detect(test_gray, markers, 5, True, 5)
+    poses = tag.estimatePose(test_gray, markers, models, cam, False)
+    mine = tag.drawAxis(test_gray, markers, models, poses, cam, 30)
+    assert overlay.shape == mine.shape
+    assert (np.any(overlay != mine, axis=2)).sum() <= 200
+    assert np.any(mine != test_gray[..., None], axis=2).sum() > 20000
