@@ -267,12 +267,12 @@ static int enqueue_on_slot(ctag_detector* d, Slot* s, const void* frames_dev, in
     s->gray_fs = s->gray_fstride;
   }
   cudaStream_t st = s->stream;
-  CTAG_CUDA_CHECK(cudaEventRecord(s->ev[0], st));
   if (window == kWin) {
     rc = launch_front(frames_dev, n, s->geo, channels, pitch, frame_stride, s->d_gray, s->gray_fstride, s->d_bin,
-                      s->bin_fstride, st);
+                      s->bin_fstride, st, s->ev[0]);
     s->launches += 1;
   } else {
+    CTAG_CUDA_CHECK(cudaEventRecord(s->ev[0], st));
     rc = launch_front_generic(frames_dev, n, s->geo, channels, pitch, frame_stride, window, s->d_gray, s->gray_fstride,
                               s->d_half, s->d_tiles, s->d_bin, s->bin_fstride, st, &s->launches);
   }

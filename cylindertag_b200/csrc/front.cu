@@ -455,6 +455,153 @@ __global__ void __launch_bounds__(front::NT, 3)
   }
 }
 
+// =====================================================================================================================
+// Gray input, sliding variant (detect()'s own contract: the caller hands over a gray frame).  Same walk as the BGR
+// kernel, but nothing is converted: TMA writes the 80 new rows straight into the gray tile, and because the
+// horizontal-pass buffer has its own storage here, its 11 overlapping row pairs are kept as well -- only the 40 new row
+// pairs go through the horizontal pass and only the 40 new half-res rows through the vertical pass; the gray tile is
+// dead after the horizontal pass, so the next tile's rows are loaded behind everything that follows.
+// Shared memory: [g | HT | P | small] = 46.8 KB per CTA, four CTAs per SM.
+namespace front {
+struct GraySlideLayout {
+  static constexpr int g = 0;
+  static constexpr int h = BOX;
+  static constexpr int p = BOX + H_BYTES;
+  static constexpr int small_ = p + P_BYTES;
+  static constexpr int tmin = small_ + S_TMIN;
+  static constexpr int tmax = small_ + S_TMAX;
+  static constexpr int cmn = small_ + S_CMN;
+  static constexpr int cmx = small_ + S_CMX;
+  static constexpr int thr16 = small_ + S_THR16;
+  static constexpr int mbar = small_ + S_MBAR;
+  static constexpr int total = small_ + S_BYTES;
+};
+constexpr int HKEEP = OVR / 2;  // 11 row pairs of HT shared with the tile above
+}  // namespace front
+
+// rows of the gray region of tile (fr, cx, cy) -> gray tile: all 102 (two boxes) for the first tile of a run, else the
+// 80 new ones; one mbarrier phase either way
+__device__ __forceinline__ void issue_gray_rows(const CUtensorMap* tmap_main, const CUtensorMap* tmap_top, uint32_t mbar,
+                                                uint32_t g_u32, int fr, int cx, int cy, bool first) {
+  using namespace front;
+  const int x0r = 2 * OW * cx - 16, y0r = 2 * OH * cy - 11;
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(RW * (first ? RH : SROWS)) : "memory");
+  if (first)
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        :
+        : "r"(g_u32), "l"(tmap_top), "r"(mbar), "r"(x0r), "r"(y0r), "r"(fr)
+        : "memory");
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      :
+      : "r"(g_u32 + OVR * RW), "l"(tmap_main), "r"(mbar), "r"(x0r), "r"(y0r + OVR), "r"(fr)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(front::NT, 4)
+    front_gray_slide_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_constant__ CUtensorMap tmap_top, FrameGeom geo,
+                            RunGrid rg, uint8_t* __restrict__ bin_out, size_t bin_fstride) {
+  using namespace front;
+  using L = GraySlideLayout;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x;
+  const uint32_t mbar = smem_u32(smem + L::mbar);
+  const uint32_t g_u32 = smem_u32(smem + L::g);
+  uint8_t* g = smem + L::g;
+  uint32_t* HT = reinterpret_cast<uint32_t*>(smem + L::h);
+  uint8_t* P = smem + L::p;
+  uint8_t* tmin = smem + L::tmin;
+  uint8_t* tmax = smem + L::tmax;
+  uint8_t* cmn = smem + L::cmn;
+  uint8_t* cmx = smem + L::cmx;
+  uint8_t* thr16 = smem + L::thr16;
+
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  int run = blockIdx.x, t = 0, t_end = 0;
+  if (run < rg.nruns) run_range(rg, run, t, t_end);
+  bool valid = run < rg.nruns && t < t_end;
+  int fr = 0, cx = 0, cy = 0;
+  bool first = true;
+  if (valid) {
+    run_tile_coords(rg, t, fr, cx, cy);
+    if (tid == 0) issue_gray_rows(&tmap_main, &tmap_top, mbar, g_u32, fr, cx, cy, true);
+  }
+  uint32_t loads = 0;  // completed-phase counter of the mbarrier (parity = loads & 1)
+
+  while (valid) {
+    // the tile after this one (see front_bgr_slide_kernel)
+    int nt = t + 1, nrun = run, nt_end = t_end;
+    int nfr = fr, ncx = cx, ncy = cy + 1;
+    bool nvalid = true, nfirst = false;
+    if (nt < t_end) {
+      if (ncy == rg.tiles_y) {
+        ncy = 0;
+        nfirst = true;
+        if (++ncx == rg.tiles_x) ncx = 0, ++nfr;
+      }
+    } else {
+      nrun = run + gridDim.x;
+      nfirst = true;
+      nvalid = false;
+      if (nrun < rg.nruns) {
+        run_range(rg, nrun, nt, nt_end);
+        nvalid = nt < nt_end;
+        if (nvalid) run_tile_coords(rg, nt, nfr, ncx, ncy);
+      }
+    }
+    const int x0r = 2 * OW * cx - 16, y0r = 2 * OH * cy - 11;
+
+    if (!first) {
+      // from the tile above: half-res rows 40..49 -> 0..9, column extrema of tile rows 8,9 -> 0,1 (its HT row pairs
+      // 40..50 were moved to 0..10 behind its vertical pass).  Its threshold phases have to be over.
+      __syncthreads();
+      if (tid < 70) {
+        reinterpret_cast<uint4*>(P)[tid] = reinterpret_cast<const uint4*>(P + 40 * PP)[tid];
+      } else if (tid >= 96 && tid < 96 + 48) {
+        const int q = tid - 96, arr = q / 24, w = q - arr * 24;
+        uint32_t* base = reinterpret_cast<uint32_t*>(arr ? cmx : cmn);
+        base[w] = base[8 * 24 + w];
+        base[24 + w] = base[9 * 24 + w];
+      }
+    }
+    mbar_wait(mbar, loads & 1);
+    ++loads;
+
+    phase_border(g, geo, cx, cy, x0r, y0r, tid, first ? 0 : OVR);
+    phase_horizontal(g, HT, tid, first ? 0 : HKEEP);
+    __syncthreads();
+    // the gray tile is dead: the next tile's rows arrive behind the rest of this one
+    if (tid == 0 && nvalid) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue_gray_rows(&tmap_main, &tmap_top, mbar, g_u32, nfr, ncx, ncy, nfirst);
+    }
+
+    const bool edge_cta = (cx == 0) || (cy == 0) || (OW * cx + OW + 5 > geo.hw) || (OH * cy + OH + 5 > geo.hh);
+    phase_vertical_extrema(HT, P, cmn, cmx, geo, cx, cy, edge_cta, first ? 0 : 2, tid);
+    __syncthreads();
+    // HT row pairs 40..50 are row pairs 0..10 of the tile below (threads that have no tile extrema to compute)
+    if (nvalid && !nfirst && tid >= NT - HKEEP * HP / 4) {
+      const int q = tid - (NT - HKEEP * HP / 4);
+      reinterpret_cast<uint4*>(HT)[q] = reinterpret_cast<const uint4*>(HT + (RH / 2 - HKEEP) * HP)[q];
+    }
+    phase_tile_extrema(cmn, cmx, tmin, tmax, tid);
+    __syncthreads();
+    phase_threshold(tmin, tmax, thr16, geo, cx, cy, tid);
+    __syncthreads();
+    phase_compare_store(P, thr16, bin_out, bin_fstride, geo, fr, cx, cy, tid);
+
+    t = nt, t_end = nt_end, run = nrun, valid = nvalid, first = nfirst;
+    fr = nfr, cx = ncx, cy = ncy;
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -476,16 +623,36 @@ int front_smem_bytes(int channels) {
   return channels == 3 ? front::Layout<3>::total : front::Layout<1>::total;
 }
 
+// Resident CTAs of `kernel` on the current device (SMs x CTAs per SM).  The shared-memory opt-in and the occupancy query
+// are done once per kernel and device, not per batch: they cost host time in front of every launch otherwise.
+static int resident_ctas(const void* kernel, int smem_bytes, int slot, int* out) {
+  constexpr int kMaxDev = 64, kKernels = 4;
+  static int cache[kKernels][kMaxDev];  // 0 = not yet known
+  int dev = 0;
+  CTAG_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDev || !cache[slot][dev]) {
+    int sms = 0, per_sm = 0;
+    CTAG_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CTAG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CTAG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, front::NT, smem_bytes));
+    if (per_sm < 1) per_sm = 1;
+    if (dev < 0 || dev >= kMaxDev) {
+      *out = sms * per_sm;
+      return CTAG_OK;
+    }
+    cache[slot][dev] = sms * per_sm;
+  }
+  *out = cache[slot][dev];
+  return CTAG_OK;
+}
+
 template <int C>
 static int launch_front_t(const CUtensorMap& tmap, int n, const FrameGeom& geo, uint8_t* gray_out, size_t gray_fstride,
-                          uint8_t* bin_out, size_t bin_fstride, cudaStream_t stream) {
+                          uint8_t* bin_out, size_t bin_fstride, cudaStream_t stream, cudaEvent_t ev_start) {
   using namespace front;
-  CTAG_CUDA_CHECK(cudaFuncSetAttribute(front_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Layout<C>::total));
-  int dev = 0, sms = 0, per_sm = 0;
-  CTAG_CUDA_CHECK(cudaGetDevice(&dev));
-  CTAG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  CTAG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, front_kernel<C>, NT, Layout<C>::total));
-  if (per_sm < 1) per_sm = 1;
+  int grid = 0;
+  const int rc = resident_ctas((const void*)front_kernel<C>, Layout<C>::total, C == 3 ? 0 : 1, &grid);
+  if (rc != CTAG_OK) return rc;
   TileGrid tg;
   tg.tiles_x = (geo.hw + OW - 1) / OW;
   tg.tiles_y = (geo.hh + OH - 1) / OH;
@@ -493,22 +660,18 @@ static int launch_front_t(const CUtensorMap& tmap, int n, const FrameGeom& geo, 
   tg.ntiles = tg.tiles_per_frame * n;
   tg.m_frame = tg.tiles_per_frame > 1 ? (uint32_t)((1ull << 32) / (uint64_t)tg.tiles_per_frame) : 0xFFFFFFFFu;
   tg.m_row = tg.tiles_x > 1 ? (uint32_t)((1ull << 32) / (uint64_t)tg.tiles_x) : 0xFFFFFFFFu;
-  int grid = sms * per_sm;  // persistent: one wave of resident CTAs
-  if (grid > tg.ntiles) grid = tg.ntiles;
+  if (grid > tg.ntiles) grid = tg.ntiles;  // persistent: one wave of resident CTAs
+  if (ev_start) CTAG_CUDA_CHECK(cudaEventRecord(ev_start, stream));
   front_kernel<C><<<grid, NT, Layout<C>::total, stream>>>(tmap, geo, tg, gray_out, gray_fstride, bin_out, bin_fstride);
   CTAG_CUDA_CHECK(cudaGetLastError());
   return CTAG_OK;
 }
 
-static int launch_front_slide(const CUtensorMap& tmap_main, const CUtensorMap& tmap_top, int n, const FrameGeom& geo,
-                              uint8_t* gray_out, size_t gray_fstride, uint8_t* bin_out, size_t bin_fstride, cudaStream_t stream) {
+static int make_run_grid(const void* kernel, int smem_bytes, int slot, int n, const FrameGeom& geo, RunGrid* out, int* grid_out) {
   using namespace front;
-  CTAG_CUDA_CHECK(cudaFuncSetAttribute(front_bgr_slide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SlideLayout::total));
-  int dev = 0, sms = 0, per_sm = 0;
-  CTAG_CUDA_CHECK(cudaGetDevice(&dev));
-  CTAG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  CTAG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, front_bgr_slide_kernel, NT, SlideLayout::total));
-  if (per_sm < 1) per_sm = 1;
+  int grid = 0;
+  const int rc = resident_ctas(kernel, smem_bytes, slot, &grid);
+  if (rc != CTAG_OK) return rc;
   RunGrid rg;
   rg.tiles_x = (geo.hw + OW - 1) / OW;
   rg.tiles_y = (geo.hh + OH - 1) / OH;
@@ -520,7 +683,6 @@ static int launch_front_slide(const CUtensorMap& tmap_main, const CUtensorMap& t
   // resident CTAs, so neighbouring CTAs work on neighbouring columns at the same time (their halo columns meet in L2).
   // Full waves use runs of kRun tiles; what is left is split evenly over the CTAs so that everybody finishes together.
   const int kRun = rg.tiles_y;  // whole tile columns: one 22-row top load per column
-  int grid = sms * per_sm;
   if (grid > rg.ntiles) grid = rg.ntiles;
   rg.wave_runs = grid;
   rg.len = kRun;
@@ -528,14 +690,36 @@ static int launch_front_slide(const CUtensorMap& tmap_main, const CUtensorMap& t
   const int rest = rg.ntiles - rg.full_waves * grid * kRun;
   rg.tail_len = rest > 0 ? (rest + grid - 1) / grid : 1;
   rg.nruns = rg.full_waves * grid + (rest > 0 ? (rest + rg.tail_len - 1) / rg.tail_len : 0);
-  front_bgr_slide_kernel<<<grid, NT, SlideLayout::total, stream>>>(tmap_main, tmap_top, geo, rg, gray_out, gray_fstride, bin_out,
-                                                                  bin_fstride);
+  *out = rg;
+  *grid_out = grid;
+  return CTAG_OK;
+}
+
+static int launch_front_slide(const CUtensorMap& tmap_main, const CUtensorMap& tmap_top, int n, const FrameGeom& geo, int channels,
+                              uint8_t* gray_out, size_t gray_fstride, uint8_t* bin_out, size_t bin_fstride, cudaStream_t stream,
+                              cudaEvent_t ev_start) {
+  using namespace front;
+  RunGrid rg;
+  int grid = 0;
+  if (channels == 3) {
+    const int rc = make_run_grid((const void*)front_bgr_slide_kernel, SlideLayout::total, 2, n, geo, &rg, &grid);
+    if (rc != CTAG_OK) return rc;
+    if (ev_start) CTAG_CUDA_CHECK(cudaEventRecord(ev_start, stream));
+    front_bgr_slide_kernel<<<grid, NT, SlideLayout::total, stream>>>(tmap_main, tmap_top, geo, rg, gray_out, gray_fstride, bin_out,
+                                                                    bin_fstride);
+  } else {
+    const int rc = make_run_grid((const void*)front_gray_slide_kernel, GraySlideLayout::total, 3, n, geo, &rg, &grid);
+    if (rc != CTAG_OK) return rc;
+    if (ev_start) CTAG_CUDA_CHECK(cudaEventRecord(ev_start, stream));
+    front_gray_slide_kernel<<<grid, NT, GraySlideLayout::total, stream>>>(tmap_main, tmap_top, geo, rg, bin_out, bin_fstride);
+  }
   CTAG_CUDA_CHECK(cudaGetLastError());
   return CTAG_OK;
 }
 
 int launch_front(const void* frames_dev, int n, const FrameGeom& geo, int channels, size_t pitch, size_t frame_stride,
-                 uint8_t* gray_out, size_t gray_fstride, uint8_t* bin_out, size_t bin_fstride, cudaStream_t stream) {
+                 uint8_t* gray_out, size_t gray_fstride, uint8_t* bin_out, size_t bin_fstride, cudaStream_t stream,
+                 cudaEvent_t ev_start) {
   using namespace front;
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) {
@@ -555,7 +739,7 @@ int launch_front(const void* frames_dev, int n, const FrameGeom& geo, int channe
     set_last_error_text("cuTensorMapEncodeTiled failed");
     return CTAG_ERR_CUDA;
   }
-  if (channels == 3 && !getenv("CTAG_FRONT_NOSLIDE")) {
+  if (!getenv("CTAG_FRONT_NOSLIDE")) {
     CUtensorMap tmap_main, tmap_top;
     cuuint32_t box_main[3] = {(cuuint32_t)RW, (cuuint32_t)SROWS, 1}, box_top[3] = {(cuuint32_t)RW, (cuuint32_t)OVR, 1};
     if (enc(&tmap_main, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(frames_dev), dims, strides, box_main, estr,
@@ -567,10 +751,11 @@ int launch_front(const void* frames_dev, int n, const FrameGeom& geo, int channe
       set_last_error_text("cuTensorMapEncodeTiled failed");
       return CTAG_ERR_CUDA;
     }
-    return launch_front_slide(tmap_main, tmap_top, n, geo, gray_out, gray_fstride, bin_out, bin_fstride, stream);
+    return launch_front_slide(tmap_main, tmap_top, n, geo, channels, gray_out, gray_fstride, bin_out, bin_fstride, stream,
+                              ev_start);
   }
-  return channels == 3 ? launch_front_t<3>(tmap, n, geo, gray_out, gray_fstride, bin_out, bin_fstride, stream)
-                       : launch_front_t<1>(tmap, n, geo, gray_out, gray_fstride, bin_out, bin_fstride, stream);
+  return channels == 3 ? launch_front_t<3>(tmap, n, geo, gray_out, gray_fstride, bin_out, bin_fstride, stream, ev_start)
+                       : launch_front_t<1>(tmap, n, geo, gray_out, gray_fstride, bin_out, bin_fstride, stream, ev_start);
 }
 
 }  // namespace ctag

@@ -88,15 +88,16 @@ __device__ __forceinline__ float lut255(int v) { return __fmul_rn((float)v, (flo
 
 // ---- replicate-border patch (TMA zero-fills outside the image; INTER_CUBIC uses BORDER_REPLICATE).  Contains its own
 //      CTA barriers (taken by all threads or none: the conditions are uniform). ------------------------------------------
-__device__ __forceinline__ void phase_border(uint8_t* g, const FrameGeom& geo, int cx, int cy, int x0r, int y0r, int tid) {
+__device__ __forceinline__ void phase_border(uint8_t* g, const FrameGeom& geo, int cx, int cy, int x0r, int y0r, int tid,
+                                             int r0 = 0) {  // rows below r0 are already patched (sliding kernels)
   using namespace front;
   const int rW = geo.w - x0r, rH = geo.h - y0r;
   const bool left = (cx == 0), right = (rW < RW), top = (cy == 0), bottom = (rH < RH);
   if (left | right | top | bottom) {
     if (left)
-      for (int r = tid; r < RH; r += NT) g[r * RW + 15] = g[r * RW + 16];
+      for (int r = r0 + tid; r < RH; r += NT) g[r * RW + 15] = g[r * RW + 16];
     if (right)
-      for (int r = tid; r < RH; r += NT) g[r * RW + rW] = g[r * RW + rW - 1];
+      for (int r = r0 + tid; r < RH; r += NT) g[r * RW + rW] = g[r * RW + rW - 1];
     __syncthreads();
     if (top)
       for (int c = tid; c < RW; c += NT) g[10 * RW + c] = g[11 * RW + c];
@@ -110,11 +111,11 @@ __device__ __forceinline__ void phase_border(uint8_t* g, const FrameGeom& geo, i
 //      pair, the layout the vertical dp2a wants.  j' = j + 3 (x = 80cx - 8 + j'), so h[row][j'] uses region columns
 //      2j'-1..2j'+2 and every group of four j' starts on an 8-byte boundary of the gray row; columns j' = 0..2 and 93..95
 //      are never used. ----------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void phase_horizontal(const uint8_t* g, uint32_t* HT, int tid) {
+__device__ __forceinline__ void phase_horizontal(const uint8_t* g, uint32_t* HT, int tid, int rp0 = 0) {  // row pairs >= rp0
   using namespace front;
   const uint32_t COEF = 0xFD1313FDu;  // (-3, 19, 19, -3) as signed bytes
   const int k = tid % 24;
-  int rp = tid / 24;  // row pairs rp, rp+16, ...
+  int rp = rp0 + tid / 24;  // row pairs rp, rp+16, ...
   const uint8_t* src = g + (2 * rp) * RW + 8 * k;
   uint32_t* dst = HT + rp * HP + 4 * k;
   // the word in front of k == 0 and the word behind k == 23 only feed the unused columns j' = 0 and 95: those two

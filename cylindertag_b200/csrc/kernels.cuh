@@ -5,8 +5,11 @@
 namespace ctag {
 
 // K1 (front.cu): fused gray + 2x cubic decimation + adaptive threshold. `frames_dev` is u8, `channels` 1 or 3.
+// `ev_start` (optional) is recorded on the stream right in front of the kernel, behind the host-side preparation
+// (tensor maps), so that stage timings measure the kernel and not the host.
 int launch_front(const void* frames_dev, int n, const FrameGeom& geo, int channels, size_t pitch, size_t frame_stride,
-                 uint8_t* gray_out, size_t gray_fstride, uint8_t* bin_out, size_t bin_fstride, cudaStream_t stream);
+                 uint8_t* gray_out, size_t gray_fstride, uint8_t* bin_out, size_t bin_fstride, cudaStream_t stream,
+                 cudaEvent_t ev_start = nullptr);
 int front_smem_bytes(int channels);
 
 // front_generic.cu: the same stages for an adaptiveThresh window other than 5 (three plain kernels, half-res image in HBM).
