@@ -334,6 +334,20 @@ def main():
         e2e = {"value": a.batch * e2e_steps * world / float(t.item()), "unit": "frames/s",
                "h2d_bytes_per_step": int(a.batch * fstride), "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                "note": "pinned host frames -> ctag_detect_batch(is_device=0); wall clock around synchronous calls"}
+        # for context: the same bytes through a plain pinned-host -> device copy (nothing else running): how much of the
+        # end-to-end time is the PCIe transfer alone
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        frames.copy_(host, non_blocking=True)
+        torch.cuda.synchronize()
+        c0.record()
+        for _ in range(3):
+            frames.copy_(host, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        copy_ms = c0.elapsed_time(c1) / 3
+        e2e["h2d_copy_alone_ms_per_step"] = copy_ms
+        e2e["h2d_copy_alone_gbs"] = a.batch * fstride / copy_ms / 1e6
+        e2e["ms_per_step"] = 1000.0 * float(t.item()) / e2e_steps
 
     if rank == 0:
         # parity spot check of one frame against the oracle (outside every timed region)
@@ -367,7 +381,7 @@ def main():
         line = {"metric": "detect_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8/int32 dense, f32/f64 sparse", "data": "synthetic", "config": config,
-                "roofline": {"bound": "hbm", "kernel": f"front_kernel<{ch}> (" + ("gray + " if ch == 3 else "") + "cubic decimation + adaptive threshold)",
+                "roofline": {"bound": "hbm", "kernel": ("front_bgr_slide_kernel (gray + " if ch == 3 else "front_gray_slide_kernel (") + "cubic decimation + adaptive threshold)",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                              "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)", "traffic_detail": traffic_detail,
                              "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,

@@ -485,11 +485,17 @@ int ctag_detect_batch(ctag_detector* d, const void* frames, int n, int w, int h,
       Slot* s = &d->slot[d->next_enqueue];
       rc = ensure_stage(s, dfs * c);
       if (rc != CTAG_OK) return rc;
-      // one 2-D copy per frame keeps frame_stride != pitch*h inputs correct
-      for (int f = 0; f < c; ++f)
-        CTAG_CUDA_CHECK(cudaMemcpy2DAsync(s->d_stage + dfs * f, dpitch,
-                                          static_cast<const uint8_t*>(frames) + frame_stride * (queued + f), pitch,
-                                          (size_t)w * channels, h, cudaMemcpyHostToDevice, s->stream));
+      if (pitch == dpitch && frame_stride == dfs) {
+        // densely packed frames with a TMA-compatible pitch: one linear copy for the whole chunk
+        CTAG_CUDA_CHECK(cudaMemcpyAsync(s->d_stage, static_cast<const uint8_t*>(frames) + frame_stride * queued, dfs * c,
+                                        cudaMemcpyHostToDevice, s->stream));
+      } else {
+        // one 2-D copy per frame normalises the pitch and keeps frame_stride != pitch*h inputs correct
+        for (int f = 0; f < c; ++f)
+          CTAG_CUDA_CHECK(cudaMemcpy2DAsync(s->d_stage + dfs * f, dpitch,
+                                            static_cast<const uint8_t*>(frames) + frame_stride * (queued + f), pitch,
+                                            (size_t)w * channels, h, cudaMemcpyHostToDevice, s->stream));
+      }
       rc = enqueue_on_slot(d, s, s->d_stage, c, w, h, dpitch, dfs, channels, adaptive_thresh, corner_subpix, subpix_dist);
       if (rc != CTAG_OK) return rc;
       q_first[d->next_enqueue] = queued;

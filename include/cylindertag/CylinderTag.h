@@ -254,6 +254,28 @@ class CylinderTag {
     cornerList = out;  // markers_info = markers (CylinderTag.cpp:128)
   }
 
+  // Batched detection -- an extension: the reference walks a video frame by frame (main.cpp:48-60), the B200 library
+  // takes many frames per call (ctag_detect_batch).  `frames`: n images of cols x rows pixels in host memory, `step`
+  // bytes per row, `frame_stride` bytes from one frame to the next; channels 1 (gray) or 3 (BGR: the caller's cvtColor
+  // is done on the GPU).  out[f] is what detect() would assign for frame f, and is left EMPTY where detect() would have
+  // left its argument untouched (no corner / no feature); status (optional) receives the CTAG_FRAME_* code per frame.
+  void detectBatch(const uint8_t* frames, int n, int rows, int cols, size_t step, size_t frame_stride, int channels,
+                   std::vector<std::vector<MarkerInfo>>& out, int adaptiveThresh = 5, const bool cornerSubPix = false,
+                   int cornerSubPixDist = 3, std::vector<int>* status = nullptr) {
+    std::vector<ctag_marker> buf((size_t)n * kCap);
+    std::vector<int> count(n, 0);
+    std::vector<ctag_frame_info> info(n);
+    int rc = ctag_detect_batch(det_, frames, n, cols, rows, step, frame_stride, channels, 0, adaptiveThresh, cornerSubPix ? 1 : 0,
+                               cornerSubPixDist, buf.data(), kCap, count.data(), info.data());
+    if (rc != CTAG_OK) throw std::string("detectBatch, ") + ctag_strerror(rc) + ": " + ctag_last_error() + "\n";
+    out.assign(n, {});
+    if (status) status->assign(n, 0);
+    for (int f = 0; f < n; ++f) {
+      if (status) (*status)[f] = info[f].status;
+      for (int m = 0; m < count[f] && m < kCap; ++m) out[f].push_back(convert(buf[(size_t)f * kCap + m]));
+    }
+  }
+
 #ifdef CTAG_WITH_OPENCV
   void detect(const cv::Mat& img, std::vector<MarkerInfo>& cornerList, int adaptiveThresh = 5, const bool cornerSubPix = false,
               int cornerSubPixDist = 3) {

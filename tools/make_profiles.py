@@ -50,9 +50,9 @@ def launches():
            f"Same workload timed with CUDA events by the library, one batch at a time (`bench.py`, not under ncu), ms per 64-frame step: front {st['front']:.3f}, ccl {st['ccl']:.3f}, quad {st['quad']:.3f}, feature {st['feature']:.3f}, decode {st['decode']:.3f}; sum {sum(st.values()):.2f} ms.",
            f"Pipelined (4 batches in flight, one stream each): {d['ms_per_step']:.3f} ms/step = {d['value']:.0f} frames/s -- within a few % of the busy sum above: with four batches in flight the step time is set by how long the kernels keep SMs occupied, not by the critical path, so only instruction / efficiency cuts inside a kernel move it (tail-heavy kernels such as quad_fit overlap with the next batch's dense kernels). `bench.py --timeline` (ctag_stage_timeline_ms) shows the overlap per batch.",
            f"Front kernel: {d['roofline']['achieved']:.0f} GB/s algorithmic = {100 * d['roofline']['frac']:.1f} % of the measured 6552 GB/s.",
-           f"e2e (pinned host frames through ctag_detect_batch): {d['e2e']['value']:.0f} frames/s (PCIe bound, 1593 MB H2D per step = {d['e2e']['value'] / 64 * 1.5925:.1f} GB/s). CPU baseline: {d['cpu_baseline']['value']:.0f} frames/s on {d['cpu_baseline']['cores']} threads ({d['cpu_baseline']['sample']}).",
+           f"e2e (pinned host frames through ctag_detect_batch): {d['e2e']['value']:.0f} frames/s = {d['e2e'].get('ms_per_step', float('nan')):.2f} ms per step (PCIe bound: 1593 MB H2D per step; the same bytes through a plain pinned copy with nothing else running take {d['e2e'].get('h2d_copy_alone_ms_per_step', float('nan')):.2f} ms = {d['e2e'].get('h2d_copy_alone_gbs', float('nan')):.1f} GB/s). CPU baseline: {d['cpu_baseline']['value']:.0f} frames/s on {d['cpu_baseline']['cores']} threads ({d['cpu_baseline']['sample']}).",
            f"Warm single-frame latency (test.bmp through ctag_detect, host frame in, markers out): {d.get('single_frame', {}).get('median_ms', float('nan')):.2f} ms.", "",
-           "Round-1 trajectory of the pipelined step (same workload): 6.9 ms (first correct path) -> 1.78 ms -> 1.43 ms: front kernel 3 CTAs/SM + instruction diet + merged vertical/extrema phase (0.61 -> 0.51 ms), CCL runs + link deduplication (0.44 -> 0.23 ms), edges kernel occupancy / register-resident silhouettes / trace early-out and the fit kernel's lane refill + size-sorted work list (quad stage 1.38 -> 1.12 ms, fit instructions 136 M -> 79 M), refine ladder (0.37 -> 0.34 ms)."]
+           "Round-1 trajectory of the pipelined step (same workload): 6.9 ms (first correct path) -> 1.78 ms -> 1.43 ms -> 1.40 ms: front kernel 3 CTAs/SM + instruction diet + merged vertical/extrema phase (0.61 -> 0.51 ms), sliding tile columns + L2 prefetch (0.51 -> 0.487 ms), CCL runs + link deduplication (0.44 -> 0.23 ms), edges kernel occupancy / register-resident silhouettes / trace early-out and the fit kernel's lane refill + size-sorted work list (quad stage 1.38 -> 1.12 ms, fit instructions 136 M -> 79 M), refine ladder (0.37 -> 0.34 ms)."]
     open(os.path.join(P, "r1_launches_final.md"), "w").write("\n".join(md) + "\n")
 
 
@@ -79,17 +79,17 @@ def front():
             "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio"]
     rd, wr = tob(*g("dram__bytes_read.sum")), tob(*g("dram__bytes_write.sum"))
     alg = 4.25 * 3840 * 2160 * 64
-    md = ["# Round 1: `ncu --set full` capture of front_kernel<3> (final state), 64 4K BGR frames per launch", "",
-          "Command: `ncu --set full --clock-control none --import-source on -k regex:front_kernel -s 3 -c 1 -o prof python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --batch 64`",
+    md = ["# Round 1: `ncu --set full` capture of front_bgr_slide_kernel (final state), 64 4K BGR frames per launch", "",
+          "Command: `ncu --set full --clock-control none --import-source on -k regex:front_bgr -s 3 -c 1 -o prof python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --batch 64`",
           "(cold-cache single launch under the profiler; the bench number comes from CUDA events, not from here)", "", "| metric | value | unit |", "|---|---|---|"]
     md += [f"| {w} | {g(w)[0]} | {g(w)[1]} |" for w in want if w in h]
     md += ["", f"DRAM traffic per launch: {rd / 1e6:.1f} MB read + {wr / 1e6:.1f} MB written = {(rd + wr) / 1e6:.1f} MB; algorithmic bytes (3N read + N gray + N/4 binary, N = 3840x2160, 64 frames) = {alg / 1e6:.1f} MB -> traffic / algorithmic = {(rd + wr) / alg:.3f}.",
-           f"The staging regions overlap (192x102 full-res pixels loaded per 160x80 owned: 1.53x); L2 absorbs most of that, DRAM reads are {rd / (3 * 3840 * 2160 * 64):.2f}x the input bytes. Writes are slightly below the algorithmic figure because part of the last tiles' output is still in L2 when the kernel ends. No re-read problem to fix.", "",
-           "SASS evidence (cuobjdump -sass libctag_b200.so): `UTMALDG.3D` (TMA tile loads), `SYNCS.PHASECHK.TRANS64.TRYWAIT` (mbarrier), `IDP.2A.*.U16.U8` / `IDP.4A.U8.S8` (dp2a/dp4a stencil arithmetic), `VIMNMX3.U16x2` (column extrema).", "",
+           f"The staged regions overlap horizontally only (192 full-res columns loaded per 160 owned: 1.2x; vertically a CTA walks down its tile column and loads every row once); L2 absorbs most of that, DRAM reads are {rd / (3 * 3840 * 2160 * 64):.2f}x the input bytes. Writes are slightly below the algorithmic figure because part of the last tiles' output is still in L2 when the kernel ends. No re-read problem to fix.", "",
+           "SASS evidence (cuobjdump -sass libctag_b200.so): `UTMALDG.3D` (TMA tile loads), `UTMAPF.L2.3D` (TMA prefetch of the next tile's rows into L2), `SYNCS.PHASECHK.TRANS64.TRYWAIT` (mbarrier), `IDP.2A.*.U16.U8` / `IDP.4A.U8.S8` (dp2a/dp4a stencil arithmetic), `VIMNMX3.U16x2` (column extrema).", "",
            "Per-phase breakdown (SASS split at the CTA barriers, `tools/ncu_segments.py`; executed warp instructions, stall samples, shared-memory wavefronts vs ideal):", "", "```"]
     md += segs.strip().splitlines()
-    md += ["```", "", "seg 1-2 = phase A (BGR->gray through registers, then the gray tile into staging box 0), seg 3-4 = replicate-border patch (edge tiles only), seg 5 = horizontal taps, seg 6 = vertical taps + rounding + column extrema (merged), seg 7 = 5x5 tile extrema, seg 8 = 3x3 dilation + threshold, seg 9 = compare + store.", "",
-           "Reading: three CTAs per SM (shared memory 67.5 KB each, 54-56 registers per thread: both limits sit at 3). The kernel issues about two thirds of its slots; barrier and shared-memory (short scoreboard) stalls lead, no TMA wait is visible (the next tile is prefetched behind the tail phases and the other two CTAs cover the rest). The gray conversion is the largest phase (2 dp2a per pixel over the 1.53x halo region), then the two separable passes. Next levers: less halo (taller tiles) and fewer shared-memory round trips between phase A and the horizontal pass."]
+    md += ["```", "", "seg 1 = run / next-tile bookkeeping, seg 2 = reuse from the tile above (10 half-res rows, 2 rows of column extrema) + wait for the staged rows, seg 3 = BGR->gray of the 80 new rows + gray store, seg 4-5 = replicate-border patch (edge tiles only), seg 6 = horizontal taps, seg 7 = hand-over of the last 22 gray rows + vertical taps + rounding + column extrema of the 40 new half-res rows, seg 8 = 5x5 tile extrema, seg 9 = 3x3 dilation + threshold, seg 10 = compare + store.", "",
+           "Reading: three CTAs per SM (shared memory 74.4 KB each, 56 registers per thread: both limits sit at 3). Against the non-sliding kernel (320.5 M warp instructions, 0.523 ms) the gray conversion fell from 123 M to 80 M instructions (no vertical halo) and the vertical pass from 75 M to 71 M; the kernel issues about 60 % of its slots, barrier and shared-memory (short scoreboard) stalls lead. The wait for the staged rows (seg 2) is the one place where load latency shows (12 % of the stall samples, down from 19 % before the L2 prefetch): a CTA has one staging area, so its next load can only start once the horizontal pass has released it; the other two CTAs of the SM cover most of it. Next levers: the horizontal pass still runs over all 51 row pairs (its buffer aliases the staging area, so the 11 shared row pairs cannot be kept the way the gray-input kernel keeps them) and its 24-lane row mapping costs 1.65x the ideal shared-memory wavefronts."]
     open(os.path.join(P, "r1_front_kernel_ncu.md"), "w").write("\n".join(md) + "\n")
     json.dump({"4k": {"dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_total": rd + wr, "frames_per_launch": 64,
                       "source": "profiles/r1_front_kernel_ncu.md"}}, open(os.path.join(P, "front_traffic.json"), "w"), indent=1)
@@ -102,7 +102,7 @@ def variants():
     md = ["# Round 1: bench variants on one B200 (final state), `python bench.py --steps 60 --warmup 3 --no-cpu <variant>`", "",
           "All numbers: CUDA events, pipelined loop (4 batches in flight), parity spot check against the oracle = ok in every run.", "",
           "| variant | frames/s (device resident) | ms / step | front kernel ms / launch | front roofline frac | e2e frames/s (pinned host, H2D inside) |", "|---|---|---|---|---|---|",
-          row("4K BGR, batch 64 (default, BASELINE config 4/5; 100 steps)", d), row("4K gray, batch 64 (detect's own contract; 1.25 B/px)", vs[0]),
+          row("4K BGR, batch 64 (default, BASELINE config 4/5; 100 steps)", d), row("4K gray, batch 64 (detect's own contract; 1.25 B/px; sliding gray kernel, 4 CTAs/SM)", vs[0]),
           row("1080p BGR, batch 128 (BASELINE config 3)", vs[1]), row("1080p gray, batch 128", vs[2]), "", "Unoverlapped stage times (ms per step, batches one at a time):"]
     for name, v in (("4K BGR", d), ("4K gray", vs[0]), ("1080p BGR (128 frames)", vs[1]), ("1080p gray (128 frames)", vs[2])):
         md.append(f"* {name}: " + ", ".join(f"{k} {x:.3f}" for k, x in v["stages_ms_per_step_unoverlapped"].items()))
