@@ -196,11 +196,14 @@ __global__ void __launch_bounds__(front::NT, 3) front_kernel(const __grid_consta
 }
 
 // =====================================================================================================================
-// BGR input, sliding variant.  Vertically adjacent tiles share 22 of their 102 region rows (and 10 of their 50 half-res
-// rows).  A CTA therefore walks RUNS of consecutive tiles of one tile column top down and keeps the gray tile and the
-// half-res patch in shared memory between them: only the 80 new full-res rows are staged (TMA) and converted, only the
-// 40 new half-res rows go through the vertical pass.  The first tile of a run / of a column loads its 22 extra rows with
-// a second, 22-row tensor map.  Shared memory: [stage 3 x 192 x 80 | g | P | small], HT aliases the staging area
+// BGR input, sliding variant.  Vertically adjacent tiles share 22 of their 102 region rows (11 horizontal-pass row pairs,
+// 10 of their 50 half-res rows).  A CTA therefore walks RUNS of consecutive tiles of one tile column top down and keeps
+// what the tile below needs in shared memory: its 10 shared half-res rows, 2 rows of column extrema and the ONE
+// horizontal-pass row pair (50 -> 10) its first new half-res row reads.  Only the 80 new full-res rows are staged (TMA)
+// and converted, only the 40 new row pairs go through the horizontal and the vertical pass.  The first tile of a run / of
+// a column loads its 22 extra rows with a second, 22-row tensor map; a tile whose run goes on also writes the 11 gray
+// output rows that belong to the tile below (it has them, the tile below will not load them).
+// Shared memory: [stage 3 x 192 x 80 | g | P | small | keep], HT aliases the staging area
 // (74.4 KB per CTA, three CTAs per SM).
 namespace front {
 constexpr int SROWS = 80;            // rows staged per tile after the first
@@ -218,7 +221,8 @@ struct SlideLayout {
   static constexpr int cmx = small_ + 384 + 960;
   static constexpr int thr16 = small_ + 2304 + 128;
   static constexpr int mbar = small_ + 2304 + 128 + 640;
-  static constexpr int total = small_ + 2304 + 128 + 640 + 16;
+  static constexpr int keep = small_ + 2304 + 128 + 640 + 16;  // 2 x HP words: row pair 50 for the tile below
+  static constexpr int total = keep + 2 * HP * 4;
 };
 static_assert(H_BYTES <= 3 * SBOX, "HT must fit into the staging area");
 }  // namespace front
@@ -331,6 +335,7 @@ __global__ void __launch_bounds__(front::NT, 3)
   uint8_t* cmn = smem + L::cmn;
   uint8_t* cmx = smem + L::cmx;
   uint8_t* thr16 = smem + L::thr16;
+  uint32_t* keep = reinterpret_cast<uint32_t*>(smem + L::keep);
 
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
@@ -349,6 +354,7 @@ __global__ void __launch_bounds__(front::NT, 3)
     if (tid == 0) issue_rows_load(&tmap_top, mbar, stage_u32, fr, cx, cy, 0, OVR);
   }
   uint32_t loads = 0;  // completed-phase counter of the mbarrier (parity = loads & 1)
+  uint32_t kbuf = 0;   // keep buffer this tile writes (the other one holds what the tile above left)
 
   while (valid) {
     // ---- the tile after this one (the run continues one tile down / at the top of the next column, or the CTA's next
@@ -377,11 +383,13 @@ __global__ void __launch_bounds__(front::NT, 3)
     const int y0r = 2 * OH * cy - 11;  // full-res y of region row 0
     uint8_t* tile_base = gray_out + (size_t)fr * gray_fstride + (ptrdiff_t)y0r * geo.gpitch + x0r;
     asm volatile("" : "+l"(tile_base));  // keep the pointer live: recomputing the 64-bit products per store costs more
-    const int rlim = min(11 + 2 * OH, geo.h - y0r);
+    // gray output rows of this tile: region rows 11..90, plus rows 91..101 (rows 11..21 of the tile below) when the
+    // run goes on there
+    const int rlim = min((nvalid && !nfirst) ? RH : 11 + 2 * OH, geo.h - y0r);
 
     if (!first) {
       // Reuse from the tile above: its half-res rows 40..49 are rows 0..9 here, its column extrema of tile rows 8,9 are
-      // those of tile rows 0,1 (the gray rows were moved right after its horizontal pass).  Everybody has to be done
+      // those of tile rows 0,1 (its horizontal-pass row pair 50 waits in the keep buffer).  Everybody has to be done
       // with the previous tile's threshold phases first.
       __syncthreads();
       if (tid < 70) {  // 10 patch rows of PP = 112 bytes = 70 uint4
@@ -419,23 +427,16 @@ __global__ void __launch_bounds__(front::NT, 3)
       }
     }
 
-    phase_border(g, geo, cx, cy, x0r, y0r, tid);
-    // HT takes over the staging area
-    phase_horizontal(g, HT, tid);
+    phase_border(g, geo, cx, cy, x0r, y0r, tid, first ? 0 : OVR);
+    // HT takes over the staging area; only the new row pairs (11..50) unless this is a first tile
+    phase_horizontal(g, HT, tid, first ? 0 : OVR / 2);
     __syncthreads();
-    // the gray tile is dead: hand its last 22 rows (patched) to the tile below; rows 11..21 of that tile are owned by it
-    // and have not been written to the gray output yet (here they are rows 91..101, outside this tile's owned rows)
-    if (nvalid && !nfirst && tid < OVR * RW / 16) {
-      const uint4 v = reinterpret_cast<const uint4*>(g + SROWS * RW)[tid];
-      reinterpret_cast<uint4*>(g)[tid] = v;
-      const int row = tid / 12, gq = tid - row * 12;  // row of the tile below
-      if (row >= 11 && gq >= 1 && gq <= 10 && x0r + gq * 16 < geo.w && y0r + SROWS + row < geo.h)
-        *reinterpret_cast<uint4*>(tile_base + ((uint32_t)(SROWS + row) * (uint32_t)geo.gpitch + (uint32_t)gq * 16u)) = v;
-    }
 
     // vertical taps + rounding + column extrema for the NEW tile rows (all ten for a first tile)
     const bool edge_cta = (cx == 0) || (cy == 0) || (OW * cx + OW + 5 > geo.hw) || (OH * cy + OH + 5 > geo.hh);
-    phase_vertical_extrema(HT, P, cmn, cmx, geo, cx, cy, edge_cta, first ? 0 : 2, tid);
+    phase_vertical_extrema(HT, P, cmn, cmx, geo, cx, cy, edge_cta, first ? 0 : 2, tid, first ? nullptr : keep + (kbuf ^ 1) * HP,
+                           keep + kbuf * HP);
+    kbuf ^= 1;
     __syncthreads();
     // HT is dead, the staging area is free: load the next tile's rows behind the threshold phases
     if (tid == 0 && nvalid) {
@@ -457,11 +458,9 @@ __global__ void __launch_bounds__(front::NT, 3)
 
 // =====================================================================================================================
 // Gray input, sliding variant (detect()'s own contract: the caller hands over a gray frame).  Same walk as the BGR
-// kernel, but nothing is converted: TMA writes the 80 new rows straight into the gray tile, and because the
-// horizontal-pass buffer has its own storage here, its 11 overlapping row pairs are kept as well -- only the 40 new row
-// pairs go through the horizontal pass and only the 40 new half-res rows through the vertical pass; the gray tile is
-// dead after the horizontal pass, so the next tile's rows are loaded behind everything that follows.
-// Shared memory: [g | HT | P | small] = 46.8 KB per CTA, four CTAs per SM.
+// kernel, but nothing is converted: TMA writes the 80 new rows straight into the gray tile, which is dead after the
+// horizontal pass, so the next tile's rows are loaded behind everything that follows.
+// Shared memory: [g | HT | P | small | keep] = 47.5 KB per CTA, four CTAs per SM.
 namespace front {
 struct GraySlideLayout {
   static constexpr int g = 0;
@@ -474,9 +473,9 @@ struct GraySlideLayout {
   static constexpr int cmx = small_ + S_CMX;
   static constexpr int thr16 = small_ + S_THR16;
   static constexpr int mbar = small_ + S_MBAR;
-  static constexpr int total = small_ + S_BYTES;
+  static constexpr int keep = small_ + S_BYTES;  // 2 x HP words: row pair 50 for the tile below
+  static constexpr int total = keep + 2 * HP * 4;
 };
-constexpr int HKEEP = OVR / 2;  // 11 row pairs of HT shared with the tile above
 }  // namespace front
 
 // rows of the gray region of tile (fr, cx, cy) -> gray tile: all 102 (two boxes) for the first tile of a run, else the
@@ -516,6 +515,8 @@ __global__ void __launch_bounds__(front::NT, 4)
   uint8_t* cmn = smem + L::cmn;
   uint8_t* cmx = smem + L::cmx;
   uint8_t* thr16 = smem + L::thr16;
+  uint32_t* keep = reinterpret_cast<uint32_t*>(smem + L::keep);
+  uint32_t kbuf = 0;
 
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
@@ -559,8 +560,8 @@ __global__ void __launch_bounds__(front::NT, 4)
     const int x0r = 2 * OW * cx - 16, y0r = 2 * OH * cy - 11;
 
     if (!first) {
-      // from the tile above: half-res rows 40..49 -> 0..9, column extrema of tile rows 8,9 -> 0,1 (its HT row pairs
-      // 40..50 were moved to 0..10 behind its vertical pass).  Its threshold phases have to be over.
+      // from the tile above: half-res rows 40..49 -> 0..9, column extrema of tile rows 8,9 -> 0,1 (its HT row pair 50
+      // waits in the keep buffer).  Its threshold phases have to be over.
       __syncthreads();
       if (tid < 70) {
         reinterpret_cast<uint4*>(P)[tid] = reinterpret_cast<const uint4*>(P + 40 * PP)[tid];
@@ -575,7 +576,7 @@ __global__ void __launch_bounds__(front::NT, 4)
     ++loads;
 
     phase_border(g, geo, cx, cy, x0r, y0r, tid, first ? 0 : OVR);
-    phase_horizontal(g, HT, tid, first ? 0 : HKEEP);
+    phase_horizontal(g, HT, tid, first ? 0 : OVR / 2);
     __syncthreads();
     // the gray tile is dead: the next tile's rows arrive behind the rest of this one
     if (tid == 0 && nvalid) {
@@ -584,13 +585,10 @@ __global__ void __launch_bounds__(front::NT, 4)
     }
 
     const bool edge_cta = (cx == 0) || (cy == 0) || (OW * cx + OW + 5 > geo.hw) || (OH * cy + OH + 5 > geo.hh);
-    phase_vertical_extrema(HT, P, cmn, cmx, geo, cx, cy, edge_cta, first ? 0 : 2, tid);
+    phase_vertical_extrema(HT, P, cmn, cmx, geo, cx, cy, edge_cta, first ? 0 : 2, tid, first ? nullptr : keep + (kbuf ^ 1) * HP,
+                           keep + kbuf * HP);
+    kbuf ^= 1;
     __syncthreads();
-    // HT row pairs 40..50 are row pairs 0..10 of the tile below (threads that have no tile extrema to compute)
-    if (nvalid && !nfirst && tid >= NT - HKEEP * HP / 4) {
-      const int q = tid - (NT - HKEEP * HP / 4);
-      reinterpret_cast<uint4*>(HT)[q] = reinterpret_cast<const uint4*>(HT + (RH / 2 - HKEEP) * HP)[q];
-    }
     phase_tile_extrema(cmn, cmx, tmin, tmax, tid);
     __syncthreads();
     phase_threshold(tmin, tmax, thr16, geo, cx, cy, tid);

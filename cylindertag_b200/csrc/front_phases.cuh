@@ -146,8 +146,11 @@ __device__ __forceinline__ void phase_horizontal(const uint8_t* g, uint32_t* HT,
 //      registers the column extrema of the five rows of a threshold-tile row (first half of the 5x5 tile min/max,
 //      corner_detector.cpp:42-53).  One thread per (tile row ti >= ti0, word of four patch columns): it walks its five
 //      half-res rows top down, so every HT row is loaded once and reused for the next output row. ----------------------
+//      Sliding kernels: the last row pair a tile reads (50) is the first one the tile below reads (10); it is handed
+//      over through `keep_out` / `keep_in` (HP words each, two alternating buffers) because HT itself does not survive. --
 __device__ __forceinline__ void phase_vertical_extrema(const uint32_t* HT, uint8_t* P, uint8_t* cmn, uint8_t* cmx,
-                                                       const FrameGeom& geo, int cx, int cy, bool edge_cta, int ti0, int tid) {
+                                                       const FrameGeom& geo, int cx, int cy, bool edge_cta, int ti0, int tid,
+                                                       const uint32_t* keep_in = nullptr, uint32_t* keep_out = nullptr) {
   using namespace front;
   if (tid >= 24 * (CTY - ti0)) return;
   const uint32_t C01 = 0x000013FDu;  // (-3, 19) on bytes 0,1
@@ -165,7 +168,7 @@ __device__ __forceinline__ void phase_vertical_extrema(const uint32_t* HT, uint8
       if (xh >= 0 && xh < geo.hw) keepx |= 0xFFu << (8 * bb);
     }
   }
-  uint4 a = *reinterpret_cast<const uint4*>(src);
+  uint4 a = *reinterpret_cast<const uint4*>((keep_in && ti == ti0) ? keep_in + 4 * k : src);
   // byte-wise min/max through the native 16x2 three-input min/max on the even and odd bytes (the 8x4 video
   // intrinsics are emulated on sm_100)
   uint32_t ve[5], vo[5], xe[5], xo[5];
@@ -196,6 +199,7 @@ __device__ __forceinline__ void phase_vertical_extrema(const uint32_t* HT, uint8
     xo[dy] = __byte_perm(hi, 0u, 0x4341);
     a = b;
   }
+  if (keep_out && ti == CTY - 1) *reinterpret_cast<uint4*>(keep_out + 4 * k) = a;  // row pair 50
   const uint32_t mne = __vimin3_u16x2(__vimin3_u16x2(ve[0], ve[1], ve[2]), ve[3], ve[4]);
   const uint32_t mno = __vimin3_u16x2(__vimin3_u16x2(vo[0], vo[1], vo[2]), vo[3], vo[4]);
   const uint32_t mxe = __vimax3_u16x2(__vimax3_u16x2(xe[0], xe[1], xe[2]), xe[3], xe[4]);
