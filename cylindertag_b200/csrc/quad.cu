@@ -6,6 +6,7 @@
 // fit_core.cuh (shared with the host logic tests).
 #include "common.cuh"
 #include "kernels.cuh"
+#include <cstdlib>
 #include "quad_core.cuh"
 
 namespace ctag {
@@ -463,6 +464,14 @@ int quad_edge_warps(int sms) { return sms * kEdgeCtasPerSm * kEdgeWarps; }  // p
 int quad_exact_ctas(int sms) { return sms * 8; }
 void quad_build_pick_table(uint16_t* host_table, int max_count) { welsch_pick_table(host_table, max_count); }
 
+// CTAs per SM actually launched for the two persistent kernels (work-list driven: any grid size is correct).  Fewer
+// than the maximum leaves registers for the kernels of the other batches in flight.
+static int env_ctas(const char* name, int dflt, int maxv) {
+  const char* e = getenv(name);
+  const int v = e ? atoi(e) : dflt;
+  return v < 1 ? 1 : (v > maxv ? maxv : v);
+}
+
 int launch_quad(int n, const FrameGeom& g, const uint8_t* bin, size_t bin_fstride, const int* labels, const int* legal,
                 int legal_cap, const int* counters, int* prefix, int* qctl, uint8_t* scratch, int edge_warps, void* fits,
                 int fit_cap, int fit_per_frame, int* frame_fit, int* pool, int pool_cap, const uint16_t* pick_table, int table_max, void* results,
@@ -471,11 +480,15 @@ int launch_quad(int n, const FrameGeom& g, const uint8_t* bin, size_t bin_fstrid
                 int* launches) {
   QuadScratchLayout L = make_layout(g);
   quad_prefix_kernel<<<1, 32, 0, stream>>>(counters, n, prefix, qctl, frame_fit);
-  quad_edges_kernel<<<edge_warps / kEdgeWarps, 32 * kEdgeWarps, 0, stream>>>(
+  static const int edge_ctas = env_ctas("CTAG_EDGE_CTAS", kEdgeCtasPerSm, kEdgeCtasPerSm);
+  static const int fit_ctas = env_ctas("CTAG_FIT_CTAS", 8, 8);
+  int edge_grid = sms * edge_ctas;
+  if (edge_grid > edge_warps / kEdgeWarps) edge_grid = edge_warps / kEdgeWarps;
+  quad_edges_kernel<<<edge_grid, 32 * kEdgeWarps, 0, stream>>>(
       n, g, bin, bin_fstride, labels, legal, legal_cap, prefix, qctl, scratch, L, quad_status, static_cast<FitRec*>(fits),
       fit_cap, fit_per_frame, frame_fit, pool, pool_cap);
   quad_fitorder_kernel<<<1, 1024, 0, stream>>>(qctl, static_cast<const FitRec*>(fits), fit_cap, fit_order);
-  quad_fit_kernel<<<sms * 8, 128, 0, stream>>>(qctl, static_cast<const FitRec*>(fits), fit_cap, pool, pick_table, table_max,
+  quad_fit_kernel<<<sms * fit_ctas, 128, 0, stream>>>(qctl, static_cast<const FitRec*>(fits), fit_cap, pool, pick_table, table_max,
                                                 fit_order, static_cast<FitResult*>(results));
   quad_fitmerge_kernel<<<(4 * fit_cap + 127) / 128, 128, 0, stream>>>(qctl, fit_cap, static_cast<const FitResult*>(results),
                                                                      lines, exact_list);
