@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libctag_b200.so")
+LIB_PATH = os.environ.get("CTAG_LIB") or os.path.join(HERE, "lib", "libctag_b200.so")  # CTAG_LIB: A/B builds of the same ABI
 
 MAX_FEATURES = 20
 STAGE_NAMES = ("front", "ccl", "quad", "feature", "decode")

@@ -146,6 +146,17 @@ CT_HD void em_add(EdgeMoments& nextm, EdgeMoments& lastm, double bestx, double b
 // Along the normal it compares the pixels at offsets n+1 and n-1 for n = -win..win step 1/4: both belong to the one
 // ladder m = -(win+1)..(win+1) step 1/4, so every pixel is located and read once (n+1 = m, n-1 = m-2 = 8 steps back)
 // and kept in a 9-entry ring; the arithmetic per pixel and the order of the sums are the reference's.
+// float(v) * float(1/255) for a byte v without the conversion unit: 2^23 + v is exact in float, so is the subtraction.
+// (Measured on the refine kernel at equal register budget: -4 %.  Replacing the double -> int and float -> double
+// conversions by a round-toward-zero add / integer re-biasing as well was slower: +3 %.)
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ float lut255_byte(uint32_t v) {
+  return __fmul_rn(__fsub_rn(__uint_as_float(0x4B000000u | v), 8388608.0f), (float)(1.0 / 255));
+}
+#else
+CT_HD float lut255_byte(uint32_t v) { return lut255f((int)v); }
+#endif
+
 template <int WIN>
 CT_HD void edge_samples_w(const uint8_t* gray, int pitch, int cols, int rows, float ax, float ay, float bx, float by,
                           int first, int step, double nx, double ny, int nsamples, EdgeMoments& nextm, EdgeMoments& lastm) {
@@ -157,17 +168,18 @@ CT_HD void edge_samples_w(const uint8_t* gray, int pitch, int cols, int rows, fl
     double Mn = 0, Mcount = 0;
     float ring[9];
     bool okr[9];
+    double mb = -(double)(WIN + 1);  // m of the first pixel of the block: multiples of 0.25 are exact
 #pragma unroll 1
-    for (int blk = 0; blk < NM; blk += 9) {  // ring slot = i mod 9 is a compile-time constant inside the body
+    for (int blk = 0; blk < NM; blk += 9, mb += 2.25) {  // ring slot = i mod 9 is a compile-time constant inside the body
 #pragma unroll
       for (int j = 0; j < 9; ++j) {
         const int i = blk + j;
         if (i < NM) {
-          const double m = -(double)(WIN + 1) + 0.25 * i;
+          const double m = mb + 0.25 * j;
           const int x = (int)(x0 + m * nx);
           const int y = (int)(y0 + m * ny);
           const bool ok = !(x < 0 || x >= cols || y < 0 || y >= rows);
-          const float gv = ok ? lut255f(gray[(size_t)y * pitch + x]) : 0.f;
+          const float gv = ok ? lut255_byte(gray[(size_t)y * pitch + x]) : 0.f;
           if (i >= 8) {
             const double n = m - 1;
             const float g1 = gv, g2 = ring[(j + 1) % 9];
