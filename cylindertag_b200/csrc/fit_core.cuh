@@ -78,6 +78,14 @@ CT_HD void im_fit(const IntMoments& m, float* line) {
 // packed point: x | y << 16 (absolute half-res coordinates, both < 4096)
 CT_HD int pt_x(int p) { return p & 0xFFFF; }
 CT_HD int pt_y(int p) { return (p >> 16) & 0xFFFF; }
+// (float) of a packed coordinate (< 2^16).  On the device through the 2^23 trick (exact) instead of the conversion unit.
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ float pt_xf(int p) { return __fsub_rn(__uint_as_float(0x4B000000u | (uint32_t)(p & 0xFFFF)), 8388608.0f); }
+__device__ __forceinline__ float pt_yf(int p) { return __fsub_rn(__uint_as_float(0x4B000000u | ((uint32_t)p >> 16)), 8388608.0f); }
+#else
+CT_HD float pt_xf(int p) { return (float)pt_x(p); }
+CT_HD float pt_yf(int p) { return (float)pt_y(p); }
+#endif
 CT_HD int pt_pack(int x, int y) { return x | (y << 16); }
 
 CT_HD float welsch_exp(float a) { return exp_f(a); }
@@ -194,7 +202,7 @@ CT_HD void welsch_init(PtFn pt, const int* picked, int np, WelschState& st) {
   double x = 0, y = 0, x2 = 0, y2 = 0, xy = 0, w = 0;
   for (int a = 0; a < np; ++a) {
     int p = pt(picked[a]);
-    float px = (float)pt_x(p), py = (float)pt_y(p);
+    float px = pt_xf(p), py = pt_yf(p);
     x += px;
     y += py;
     x2 += px * px;
@@ -237,7 +245,7 @@ CT_HD bool welsch_step(PtFn pt, int count, WelschState& st, float* wcache, Visit
 #pragma unroll 4
   for (int j = 0; j < count; ++j) {
     int p = pt(j);
-    float x = (float)pt_x(p) - px0, y = (float)pt_y(p) - py0;
+    float x = pt_xf(p) - px0, y = pt_yf(p) - py0;
     float r = (float)fabs(nx * x + ny * y);
     err += r;
     float wr = welsch_exp(-r * r * c * c);
@@ -253,7 +261,7 @@ CT_HD bool welsch_step(PtFn pt, int count, WelschState& st, float* wcache, Visit
 #pragma unroll 4
   for (int j = 0; j < count; ++j) {
     int p = pt(j);
-    float fx = (float)pt_x(p), fy = (float)pt_y(p);
+    float fx = pt_xf(p), fy = pt_yf(p);
     float wr;
     if (cached) {
       wr = wcache[j];

@@ -279,6 +279,7 @@ __global__ void __launch_bounds__(1024) quad_fitorder_kernel(const int* __restri
 // a lane that handled one restart from start to end would idle most of the time.  Instead every lane keeps the state of
 // its current restart, all lanes advance by one iteration per trip, and a lane whose restart is over takes the next one
 // from the global counter right away.
+// (no minimum-blocks bound: 56 registers, eight CTAs per SM; forcing 12 or 16 CTAs per SM spills and is 13-20 % slower)
 __global__ void __launch_bounds__(128) quad_fit_kernel(int* __restrict__ qctl, const FitRec* __restrict__ fits,
                                                        int fit_cap, const int* __restrict__ pool,
                                                        const uint16_t* __restrict__ pick_table, int table_max,
