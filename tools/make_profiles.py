@@ -52,7 +52,7 @@ def launches():
            f"Front kernel: {d['roofline']['achieved']:.0f} GB/s algorithmic = {100 * d['roofline']['frac']:.1f} % of the measured 6552 GB/s.",
            f"e2e (pinned host frames through ctag_detect_batch): {d['e2e']['value']:.0f} frames/s = {d['e2e'].get('ms_per_step', float('nan')):.2f} ms per step (PCIe bound: 1593 MB H2D per step; the same bytes through a plain pinned copy with nothing else running take {d['e2e'].get('h2d_copy_alone_ms_per_step', float('nan')):.2f} ms = {d['e2e'].get('h2d_copy_alone_gbs', float('nan')):.1f} GB/s). CPU baseline: {d['cpu_baseline']['value']:.0f} frames/s on {d['cpu_baseline']['cores']} threads ({d['cpu_baseline']['sample']}).",
            f"Warm single-frame latency (test.bmp through ctag_detect, host frame in, markers out): {d.get('single_frame', {}).get('median_ms', float('nan')):.2f} ms.", "",
-           "Round-1 trajectory of the pipelined step (same workload): 6.9 ms (first correct path) -> 1.78 ms -> 1.43 ms -> 1.40 ms: front kernel 3 CTAs/SM + instruction diet + merged vertical/extrema phase (0.61 -> 0.51 ms), sliding tile columns + L2 prefetch (0.51 -> 0.487 ms), CCL runs + link deduplication (0.44 -> 0.23 ms), edges kernel occupancy / register-resident silhouettes / trace early-out and the fit kernel's lane refill + size-sorted work list (quad stage 1.38 -> 1.12 ms, fit instructions 136 M -> 79 M), refine ladder (0.37 -> 0.34 ms)."]
+           "Round-1 trajectory of the pipelined step (same workload): 6.9 ms (first correct path) -> 1.78 ms -> 1.43 ms -> 1.40 ms: front kernel 3 CTAs/SM + instruction diet + merged vertical/extrema phase (0.61 -> 0.51 ms), sliding tile columns + L2 prefetch + one-row-pair hand-over (0.51 -> 0.466 ms), CCL runs + link deduplication (0.44 -> 0.23 ms), edges kernel occupancy / register-resident silhouettes / trace early-out and the fit kernel's lane refill + size-sorted work list (quad stage 1.38 -> 1.12 ms, fit instructions 136 M -> 79 M), refine ladder (0.37 -> 0.34 ms)."]
     open(os.path.join(P, "r1_launches_final.md"), "w").write("\n".join(md) + "\n")
 
 
@@ -88,8 +88,8 @@ def front():
            "SASS evidence (cuobjdump -sass libctag_b200.so): `UTMALDG.3D` (TMA tile loads), `UTMAPF.L2.3D` (TMA prefetch of the next tile's rows into L2), `SYNCS.PHASECHK.TRANS64.TRYWAIT` (mbarrier), `IDP.2A.*.U16.U8` / `IDP.4A.U8.S8` (dp2a/dp4a stencil arithmetic), `VIMNMX3.U16x2` (column extrema).", "",
            "Per-phase breakdown (SASS split at the CTA barriers, `tools/ncu_segments.py`; executed warp instructions, stall samples, shared-memory wavefronts vs ideal):", "", "```"]
     md += segs.strip().splitlines()
-    md += ["```", "", "seg 1 = run / next-tile bookkeeping, seg 2 = reuse from the tile above (10 half-res rows, 2 rows of column extrema) + wait for the staged rows, seg 3 = BGR->gray of the 80 new rows + gray store, seg 4-5 = replicate-border patch (edge tiles only), seg 6 = horizontal taps, seg 7 = hand-over of the last 22 gray rows + vertical taps + rounding + column extrema of the 40 new half-res rows, seg 8 = 5x5 tile extrema, seg 9 = 3x3 dilation + threshold, seg 10 = compare + store.", "",
-           "Reading: three CTAs per SM (shared memory 74.4 KB each, 56 registers per thread: both limits sit at 3). Against the non-sliding kernel (320.5 M warp instructions, 0.523 ms) the gray conversion fell from 123 M to 80 M instructions (no vertical halo) and the vertical pass from 75 M to 71 M; the kernel issues about 60 % of its slots, barrier and shared-memory (short scoreboard) stalls lead. The wait for the staged rows (seg 2) is the one place where load latency shows (12 % of the stall samples, down from 19 % before the L2 prefetch): a CTA has one staging area, so its next load can only start once the horizontal pass has released it; the other two CTAs of the SM cover most of it. Next levers: the horizontal pass still runs over all 51 row pairs (its buffer aliases the staging area, so the 11 shared row pairs cannot be kept the way the gray-input kernel keeps them) and its 24-lane row mapping costs 1.65x the ideal shared-memory wavefronts."]
+    md += ["```", "", "seg 1 = run / next-tile bookkeeping, seg 2 = reuse from the tile above (10 half-res rows, 2 rows of column extrema) + wait for the staged rows, seg 3 = BGR->gray of the 80 new rows + gray store (incl. the 11 rows owned by the tile below when the run goes on), seg 4-5 = replicate-border patch (edge tiles only), seg 6 = horizontal taps on the 40 new row pairs, seg 7 = vertical taps + rounding + column extrema of the 40 new half-res rows (first row pair from the keep buffer), seg 8 = 5x5 tile extrema, seg 9 = 3x3 dilation + threshold, seg 10 = compare + store.", "",
+           "Reading: three CTAs per SM (shared memory 73.4 KB each, 56 registers per thread: both limits sit at 3). Against the non-sliding kernel (320.5 M warp instructions, 0.523 ms) the gray conversion fell from 123 M to 80 M instructions (no vertical halo), the horizontal pass from 63 M to 49 M (the tile below needs exactly one row pair of the tile above, handed over through a 2 x 384 B keep buffer) and the vertical pass from 75 M to 71 M; the kernel issues about 60 % of its slots, barrier and shared-memory (short scoreboard) stalls lead. The wait for the staged rows (seg 2) is the one place where load latency shows: a CTA has one staging area, so its next load can only start once the vertical pass has released it (the rows are prefetched into L2 meanwhile); the other two CTAs of the SM cover most of it. Next levers: the horizontal pass's 24-lane row mapping costs 1.65x the ideal shared-memory wavefronts, and phases D-F keep only 128-200 of the 384 threads busy between their barriers."]
     open(os.path.join(P, "r1_front_kernel_ncu.md"), "w").write("\n".join(md) + "\n")
     json.dump({"4k": {"dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_total": rd + wr, "frames_per_launch": 64,
                       "source": "profiles/r1_front_kernel_ncu.md"}}, open(os.path.join(P, "front_traffic.json"), "w"), indent=1)
