@@ -21,6 +21,9 @@ def last_json(path):
 def launches():
     shutil.copy(os.path.join(G, "launches_final.csv"), os.path.join(P, "r1_launches_final.csv"))
     shutil.copy(os.path.join(G, "bench_final.json"), os.path.join(P, "r1_bench_final.json"))
+    for n in (2, 4, 8):  # torchrun runs of the same bench, when they were made
+        if os.path.exists(os.path.join(G, f"bench{n}_final.json")):
+            shutil.copy(os.path.join(G, f"bench{n}_final.json"), os.path.join(P, f"r1_bench_final_{n}gpu.json"))
     rows = list(csv.reader(open(os.path.join(P, "r1_launches_final.csv"))))
     hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     h = rows[hi]
@@ -113,8 +116,8 @@ def variants():
            "Multi-GPU (torchrun, one rank per GPU, weak scaling, frames sharded, no data-path collective; max-over-ranks timing):", "",
            "| GPUs | frames/s (device resident) | ms / step | e2e frames/s | state |", "|---|---|---|---|---|",
            f"| 1 | {d['value']:,.0f} | {d['ms_per_step']:.3f} | {d['e2e']['value']:,.0f} | final |",
-           "| 2 | 86,013 | 1.488 | 4,125 | near-final build (1-GPU value was 43,943 then: 1.96x) |",
-           "| 4 | 141,410 | 1.810 | 8,113 | mid-round build (1-GPU value was 36,059 then: 3.92x) |", "",
+           *[f"| {v['n_gpus']} | {v['value']:,.0f} | {v['ms_per_step']:.3f} | {v['e2e']['value']:,.0f} | final ({v['value'] / d['value']:.2f}x / e2e {v['e2e']['value'] / d['e2e']['value']:.2f}x of one GPU) |"
+             for v in (last_json(os.path.join(G, n)) for n in ("bench2_final.json", "bench4_final.json") if os.path.exists(os.path.join(G, n)))], "",
            "Warm single-frame latency of `ctag_detect` (host gray frame in, markers out, wall clock, `tools/latency.py`): test.bmp 1920x1200 1.35 ms,",
            "synthetic 4K 1.19 ms (quad 0.29-0.66 ms and decode 0.20-0.24 ms dominate: single-lane / single-warp serial parts)."]
     open(os.path.join(P, "r1_bench_variants.md"), "w").write("\n".join(md) + "\n")
