@@ -67,3 +67,17 @@ def test_large_host_batch_uses_all_slots(detector, marker_path):
     worst, counts = _check(detector, frames, state, fs)
     assert worst <= 1e-3
     assert all(counts[i] == counts[i % 4] for i in range(18))
+
+
+def test_more_chunks_than_workspaces(detector, marker_path, monkeypatch):
+    """A host batch cut into more chunks than there are workspaces (what a 64-frame 4K batch does): chunks queue up
+    behind the in-flight ones and the results equal those of the default chunking, frame for frame."""
+    state, fs = o.load_marker_file(marker_path)
+    base = [synth.synthetic_frame(1000 + i, 1280, 720, state, 1)[0] for i in range(3)]
+    frames = np.stack([base[i % 3] for i in range(19)])
+    want_m, want_c, want_i = detector.detect_batch(frames, 5, True, 5, cap_per_frame=8)
+    monkeypatch.setenv("CTAG_CHUNK", "2")  # 10 chunks, the last one a single frame
+    got_m, got_c, got_i = detector.detect_batch(frames, 5, True, 5, cap_per_frame=8)
+    assert np.array_equal(got_c, want_c) and got_c.sum() >= 19
+    assert np.array_equal(got_i, want_i)
+    assert np.array_equal(got_m.view(np.uint8), want_m.view(np.uint8))
