@@ -256,6 +256,32 @@ __device__ __forceinline__ void run_tile_coords(const RunGrid& rg, int t, int& f
   fr = (int)q; cx = (int)c; cy = (int)r;
 }
 
+// The tile a CTA works on after (run, t): one tile down in the same run (`first` = false: the rows shared with the
+// tile above are still in shared memory), the top of the next tile column inside the run, or the first tile of the
+// CTA's next run (both `first` = true: nothing to reuse).  `valid` = false when the CTA has no more work.
+__device__ __forceinline__ void next_tile(const RunGrid& rg, int run, int t, int t_end, int fr, int cx, int cy, int& nrun, int& nt,
+                                          int& nt_end, int& nfr, int& ncx, int& ncy, bool& nvalid, bool& nfirst) {
+  nt = t + 1, nrun = run, nt_end = t_end;
+  nfr = fr, ncx = cx, ncy = cy + 1;
+  nvalid = true, nfirst = false;
+  if (nt < t_end) {
+    if (ncy == rg.tiles_y) {
+      ncy = 0;
+      nfirst = true;
+      if (++ncx == rg.tiles_x) ncx = 0, ++nfr;
+    }
+  } else {
+    nrun = run + gridDim.x;
+    nfirst = true;
+    nvalid = false;
+    if (nrun < rg.nruns) {
+      run_range(rg, nrun, nt, nt_end);
+      nvalid = nt < nt_end;
+      if (nvalid) run_tile_coords(rg, nt, nfr, ncx, ncy);
+    }
+  }
+}
+
 // rows [row0, row0 + nrows) of the region of tile (fr, cx, cy) -> staging area (three colour box slots of SBOX bytes)
 __device__ __forceinline__ void issue_rows_load(const CUtensorMap* tmap, uint32_t mbar, uint32_t dst, int fr, int cx, int cy,
                                                 int row0, int nrows) {
@@ -357,27 +383,10 @@ __global__ void __launch_bounds__(front::NT, 3)
   uint32_t kbuf = 0;   // keep buffer this tile writes (the other one holds what the tile above left)
 
   while (valid) {
-    // ---- the tile after this one (the run continues one tile down / at the top of the next column, or the CTA's next
-    //      run starts) ---------------------------------------------------------------------------------------------
-    int nt = t + 1, nrun = run, nt_end = t_end;
-    int nfr = fr, ncx = cx, ncy = cy + 1;
-    bool nvalid = true, nfirst = false;
-    if (nt < t_end) {
-      if (ncy == rg.tiles_y) {  // top of the next tile column: nothing to reuse
-        ncy = 0;
-        nfirst = true;
-        if (++ncx == rg.tiles_x) ncx = 0, ++nfr;
-      }
-    } else {
-      nrun = run + gridDim.x;
-      nfirst = true;
-      nvalid = false;
-      if (nrun < rg.nruns) {
-        run_range(rg, nrun, nt, nt_end);
-        nvalid = nt < nt_end;
-        if (nvalid) run_tile_coords(rg, nt, nfr, ncx, ncy);
-      }
-    }
+    // the tile after this one
+    int nt, nrun, nt_end, nfr, ncx, ncy;
+    bool nvalid, nfirst;
+    next_tile(rg, run, t, t_end, fr, cx, cy, nrun, nt, nt_end, nfr, ncx, ncy, nvalid, nfirst);
 
     const int x0r = 2 * OW * cx - 16;  // full-res x of region column 0
     const int y0r = 2 * OH * cy - 11;  // full-res y of region row 0
@@ -537,26 +546,10 @@ __global__ void __launch_bounds__(front::NT, 4)
   uint32_t loads = 0;  // completed-phase counter of the mbarrier (parity = loads & 1)
 
   while (valid) {
-    // the tile after this one (see front_bgr_slide_kernel)
-    int nt = t + 1, nrun = run, nt_end = t_end;
-    int nfr = fr, ncx = cx, ncy = cy + 1;
-    bool nvalid = true, nfirst = false;
-    if (nt < t_end) {
-      if (ncy == rg.tiles_y) {
-        ncy = 0;
-        nfirst = true;
-        if (++ncx == rg.tiles_x) ncx = 0, ++nfr;
-      }
-    } else {
-      nrun = run + gridDim.x;
-      nfirst = true;
-      nvalid = false;
-      if (nrun < rg.nruns) {
-        run_range(rg, nrun, nt, nt_end);
-        nvalid = nt < nt_end;
-        if (nvalid) run_tile_coords(rg, nt, nfr, ncx, ncy);
-      }
-    }
+    // the tile after this one
+    int nt, nrun, nt_end, nfr, ncx, ncy;
+    bool nvalid, nfirst;
+    next_tile(rg, run, t, t_end, fr, cx, cy, nrun, nt, nt_end, nfr, ncx, ncy, nvalid, nfirst);
     const int x0r = 2 * OW * cx - 16, y0r = 2 * OH * cy - 11;
 
     if (!first) {
