@@ -51,7 +51,7 @@ def launches():
     st = d["stages_ms_per_step_unoverlapped"]
     md += ["", f"Sum of the kernel durations {tot / 1000:.0f} us; sum of (duration x fraction of SMs busy) = {tb:.0f} us.", "",
            f"Same workload timed with CUDA events by the library, one batch at a time (`bench.py`, not under ncu), ms per 64-frame step: front {st['front']:.3f}, ccl {st['ccl']:.3f}, quad {st['quad']:.3f}, feature {st['feature']:.3f}, decode {st['decode']:.3f}; sum {sum(st.values()):.2f} ms.",
-           f"Pipelined (4 batches in flight, one stream each): {d['ms_per_step']:.3f} ms/step = {d['value']:.0f} frames/s -- within a few % of the busy sum above: with four batches in flight the step time is set by how long the kernels keep SMs occupied, not by the critical path, so only instruction / efficiency cuts inside a kernel move it (tail-heavy kernels such as quad_fit overlap with the next batch's dense kernels). `bench.py --timeline` (ctag_stage_timeline_ms) shows the overlap per batch.",
+           f"Pipelined ({d['pipelining']}): {d['ms_per_step']:.3f} ms/step = {d['value']:.0f} frames/s -- within a few % of the busy sum above: with several batches in flight the step time is set by how long the kernels keep SMs occupied, not by the critical path, so only instruction / efficiency cuts inside a kernel move it (tail-heavy kernels such as quad_fit overlap with the next batch's dense kernels). `bench.py --timeline` (ctag_stage_timeline_ms) shows the overlap per batch.",
            f"Front kernel: {d['roofline']['achieved']:.0f} GB/s algorithmic = {100 * d['roofline']['frac']:.1f} % of the measured 6552 GB/s.",
            f"e2e (pinned host frames through ctag_detect_batch): {d['e2e']['value']:.0f} frames/s = {d['e2e'].get('ms_per_step', float('nan')):.2f} ms per step (PCIe bound: 1593 MB H2D per step; the same bytes through a plain pinned copy with nothing else running take {d['e2e'].get('h2d_copy_alone_ms_per_step', float('nan')):.2f} ms = {d['e2e'].get('h2d_copy_alone_gbs', float('nan')):.1f} GB/s). CPU baseline: {d['cpu_baseline']['value']:.0f} frames/s on {d['cpu_baseline']['cores']} threads ({d['cpu_baseline']['sample']}).",
            f"Warm single-frame latency (test.bmp through ctag_detect, host frame in, markers out): {d.get('single_frame', {}).get('median_ms', float('nan')):.2f} ms.", "",
@@ -103,7 +103,7 @@ def variants():
     vs = [json.loads(l) for l in open(os.path.join(G, "variants.jsonl")) if l.strip()][-3:]
     row = lambda name, v: f"| {name} | {v['value']:,.0f} | {v['ms_per_step']:.3f} | {v['roofline']['kernel_ms_per_launch']:.3f} | {v['roofline']['frac']:.3f} | {v['e2e']['value']:,.0f} |"
     md = ["# Round 1: bench variants on one B200 (final state), `python bench.py --steps 60 --warmup 3 --no-cpu <variant>`", "",
-          "All numbers: CUDA events, pipelined loop (4 batches in flight), parity spot check against the oracle = ok in every run.", "",
+          "All numbers: CUDA events, pipelined loop (several batches in flight, one stream each), parity spot check against the oracle = ok in every run.", "",
           "| variant | frames/s (device resident) | ms / step | front kernel ms / launch | front roofline frac | e2e frames/s (pinned host, H2D inside) |", "|---|---|---|---|---|---|",
           row("4K BGR, batch 64 (default, BASELINE config 4/5; 100 steps)", d), row("4K gray, batch 64 (detect's own contract; 1.25 B/px; sliding gray kernel, 4 CTAs/SM)", vs[0]),
           row("1080p BGR, batch 128 (BASELINE config 3)", vs[1]), row("1080p gray, batch 128", vs[2]), "", "Unoverlapped stage times (ms per step, batches one at a time):"]
