@@ -1,5 +1,5 @@
 """Parity on rendered frames (BASELINE.json configs 3-5): 1080p single-marker frames, 4K multi-marker frames, generated
-15c3f / 18c4f codebooks, BGR input, and a batch large enough to exercise the multi-slot host pipeline."""
+15c3f / 18c4f codebooks, BGR input, and a batch large enough to exercise the chunked host pipeline."""
 import numpy as np
 import pytest
 
@@ -60,10 +60,10 @@ def test_generated_codebooks(cols, fsz):
     det.close()
 
 
-def test_large_host_batch_uses_all_slots(detector, marker_path):
+def test_large_host_batch_is_chunked(detector, marker_path):
     state, fs = o.load_marker_file(marker_path)
     base = [synth.synthetic_frame(1000 + i, 1280, 720, state, 1)[0] for i in range(4)]
-    frames = np.stack([base[i % 4] for i in range(18)])  # 18 frames -> 4 chunks over the workspaces
+    frames = np.stack([base[i % 4] for i in range(18)])  # 18 frames -> 4 chunks, three in flight
     worst, counts = _check(detector, frames, state, fs)
     assert worst <= 1e-3
     assert all(counts[i] == counts[i % 4] for i in range(18))
