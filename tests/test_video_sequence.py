@@ -4,9 +4,10 @@ by seeded homographies / blur / noise (cylindertag_b200.synth.video_sequence, de
 DESIGN.md.  The caller loop is main.cpp:48-60: per frame detect(gray, 5, true, 5) -> estimatePose, outputs cleared
 between frames.
 
-CPU part: the generator is deterministic and the C++ oracle port agrees with the cv2 oracle on sequence frames.
-GPU part: every frame of the sequence against the C++ port, a subset stage by stage against the cv2 oracle, poses
-against the pose oracle."""
+CPU part: the generator is deterministic; the C++ oracle port agrees with the cv2 oracle on sequence frames (live on
+three frames, against the frozen oracle results of tests/golden/sequence_detect.npz on all 120).
+GPU part: every frame of the sequence against the frozen oracle results and against the C++ port, a subset stage by
+stage against the live cv2 oracle, poses against the pose oracle."""
 import os
 
 import numpy as np
@@ -27,6 +28,43 @@ COUNT_KEYS = ("n_labels", "n_legal", "n_quads", "n_features", "n_groups", "n_mar
 @pytest.fixture(scope="module")
 def dictionary(marker_path):
     return o.load_marker_file(marker_path)
+
+
+@pytest.fixture(scope="module")
+def golden_sequence():
+    """cv2-oracle results on all 120 frames (tests/golden/make_golden_sequence.py)."""
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sequence_detect.npz"))
+
+
+def _assert_matches_golden(gold, counts6, n_markers, markers, tol, ctx):
+    """counts6: [frame][6] stage counts, markers[f][k]: ctag_marker records of the implementation under test."""
+    total = 0
+    for f in range(N_FRAMES):
+        if gold["flagged"][f]:
+            continue
+        assert list(counts6[f]) == list(gold["counts"][f]), f"{ctx} frame {f}"
+        a, b = int(gold["marker_start"][f]), int(gold["marker_start"][f + 1])
+        assert int(n_markers[f]) == b - a, f"{ctx} frame {f}"
+        for k in range(b - a):
+            g = markers[f][k]
+            nf = int(gold["n_features"][a + k])
+            assert int(g["marker_id"]) == int(gold["marker_id"][a + k]) and int(g["inverse"]) == int(gold["inverse"][a + k])
+            assert int(g["n_features"]) == nf, (ctx, f, k)
+            for name in ("feature_pos", "feature_id", "id_left", "id_right"):
+                npos = nf if name != "feature_pos" else int((gold["feature_pos"][a + k] >= 0).sum())
+                assert list(g[name][:npos]) == list(gold[name][a + k][:npos]), (ctx, f, k, name)
+            assert np.abs(g["corners"][:nf] - gold["corners"][a + k][:nf]).max() <= tol, (ctx, f, k)
+            total += 1
+    return total
+
+
+def test_cpu_port_matches_golden_on_all_frames(test_gray, dictionary, golden_sequence):
+    """Every frame of the sequence: the C++ port against the frozen cv2-oracle results."""
+    state, fs = dictionary
+    seq = synth.video_sequence(test_gray, N_FRAMES, SEED)
+    counts, markers = cpu.detect_batch(seq, state, fs, True, 5, threads=os.cpu_count() or 1, cap=32)
+    total = _assert_matches_golden(golden_sequence, counts[:, :6], counts[:, 5], markers, 1e-6, "cpu_ref")
+    assert total == int(golden_sequence["marker_start"][-1]) >= 4 * N_FRAMES
 
 
 def test_sequence_is_deterministic_and_sliceable(test_gray):
@@ -70,6 +108,16 @@ def test_full_sequence_matches_cpu_port(detector, test_gray, dictionary):
                 assert list(g[name][:nf]) == list(w[name][:nf]), (f, k, name)
             assert np.abs(g["corners"][:nf] - w["corners"][:nf]).max() <= 1e-3, (f, k)
     assert decoded >= 4 * N_FRAMES  # five markers in the photo, a warped frame loses one now and then
+
+
+@pytest.mark.gpu
+def test_full_sequence_matches_golden(detector, test_gray, golden_sequence):
+    """Every frame of the sequence: the CUDA path against the frozen cv2-oracle results."""
+    seq = synth.video_sequence(test_gray, N_FRAMES, SEED)
+    markers, counts, info = detector.detect_batch(seq, 5, True, 5, cap_per_frame=32)
+    counts6 = np.stack([info[k] for k in COUNT_KEYS], axis=1)
+    total = _assert_matches_golden(golden_sequence, counts6, counts, markers, 1e-3, "gpu")
+    assert total == int(golden_sequence["marker_start"][-1])
 
 
 @pytest.mark.gpu
