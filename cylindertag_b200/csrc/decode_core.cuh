@@ -143,10 +143,11 @@ CT_HD int c_mod(int a, int b) { return a % b; }  // C semantics (sign of the div
 // Scratch for one frame.
 struct DecodeScratch {
   int* father;      // [100]
-  uint8_t* link;    // [100]
+  uint8_t* link;    // 16 bytes, 4-byte aligned: link bit mask of the feature being joined (up to 128 features)
   int* group_of;    // [100] group index of every feature
   int* order;       // [100] feature indices of the current group, sorted
   int* cover;       // [2 * rows * cols] coverage table of match_dictionary
+  ctag_marker* mk;  // working record of the current group (shared memory on the GPU: zeroed and stored by all lanes)
 };
 
 // Whole tail of detect() for one frame.  Returns the number of decoded markers written
@@ -157,15 +158,26 @@ CT_HD int organize_and_decode(const FeatureRec* feats, int nf, const int* state,
   // ---- union-find over linked feature pairs (:977-991) ----
   for (int i = ln.id; i < nf; i += ln.n) sc.father[i] = i;
   w_sync();
+  // links of feature i to the features behind it as a bit mask (a feature links to a few neighbours only), then lane 0
+  // joins them in ascending j like the reference's inner loop
+  uint32_t* lmask = reinterpret_cast<uint32_t*>(sc.link);  // 4 words: up to 128 features
+  for (int w = ln.id; w < 4; w += ln.n) lmask[w] = 0u;
+  w_sync();
   for (int i = 0; i < nf - 1; ++i) {
-    for (int j = i + 1 + ln.id; j < nf; j += ln.n) sc.link[j] = feature_link(feats[i], feats[j]) ? 1 : 0;
+    for (int j = i + 1 + ln.id; j < nf; j += ln.n)
+      if (feature_link(feats[i], feats[j])) bit_or(&lmask[j >> 5], 1u << (j & 31));
     w_sync();
     if (ln.id == 0) {
-      for (int j = i + 1; j < nf; ++j)
-        if (sc.link[j]) {
+      for (int w = (i + 1) >> 5; w < 4 && 32 * w < nf; ++w) {
+        uint32_t m = lmask[w];
+        lmask[w] = 0u;
+        while (m) {
+          const int j = 32 * w + popc32((m & (0u - m)) - 1u);  // lowest set bit
+          m &= m - 1u;
           int a = uf_find_c(sc.father, i), b = uf_find_c(sc.father, j);
           if (a != b) sc.father[b] = a;
         }
+      }
     }
     w_sync();
   }
@@ -201,15 +213,17 @@ CT_HD int organize_and_decode(const FeatureRec* feats, int nf, const int* state,
   w_sync();
   ngroups = w_bcast_i(ngroups, 0);
   for (int g = 0; g < ngroups; ++g) {
-    // per-group working record (lane 0 fills it)
-    ctag_marker mk;
+    // per-group working record (lane 0 fills it); unused slots of the record are zero
+    ctag_marker& mk = *sc.mk;
+    constexpr int kMkWords = (int)(sizeof(ctag_marker) / 4);
+    {
+      int* z = reinterpret_cast<int*>(&mk);
+      for (int q = ln.id; q < kMkWords; q += ln.n) z[q] = 0;
+    }
+    w_sync();
     int m = 0, pos_now = 0, legal = 0, decode_ok = 0;
     int code[20];
     if (ln.id == 0) {
-      {  // unused slots of the record are zero, not stack garbage
-        int* z = reinterpret_cast<int*>(&mk);
-        for (int q = 0; q < (int)(sizeof(ctag_marker) / 4); ++q) z[q] = 0;
-      }
       // members in feature order
       for (int i = 0; i < nf; ++i)
         if (sc.group_of[i] == g) sc.order[m++] = i;
@@ -299,15 +313,27 @@ CT_HD int organize_and_decode(const FeatureRec* feats, int nf, const int* state,
         int dir = t / (srows * scols), rc = t - dir * srows * scols;
         int i = rc / scols, j = rc - i * scols;
         int cov = 0;
-        for (int k = 0; k <= pos_now; ++k) {
-          int ck = cd[k];
-          if (dir == 0) {
-            if (state[i * scols + (j + k) % scols] == ck) ++cov;
-          } else {
-            // a contiguous cv::Mat read with a possibly negative column offset; reads before the buffer never match
-            int idx = i * scols + c_mod(j - k + scols, scols);
-            int inv = (7 - ck / 8) + (7 - ck % 8) * 8;
+        const int* row = state + i * scols;
+        if (dir == 0) {
+          // state(i, (j + k) % cols): the column walks right and wraps
+          int col = j;
+          for (int k = 0; k <= pos_now; ++k) {
+            if (row[col] == cd[k]) ++cov;
+            if (++col == scols) col = 0;
+          }
+        } else {
+          // inverse reading: state read at the flat offset i * cols + (j - k + cols) % cols with C's remainder, i.e. a
+          // contiguous cv::Mat read whose column offset turns negative once k > j + cols (then it walks 0, -1, ...,
+          // -(cols - 1), 0, ... into the previous row); reads before the buffer never match.  a = j - k + cols.
+          int a = j + scols, col = j;
+          for (int k = 0; k <= pos_now; ++k) {
+            const int ck = cd[k];
+            const int inv = (7 - ck / 8) + (7 - ck % 8) * 8;
+            const int idx = i * scols + col;
             if (idx >= 0 && state[idx] == inv) ++cov;
+            --a;
+            if (a >= 0) col = col == 0 ? scols - 1 : col - 1;
+            else col = col == -(scols - 1) ? 0 : col - 1;
           }
         }
         sc.cover[t] = cov;
@@ -340,6 +366,7 @@ CT_HD int organize_and_decode(const FeatureRec* feats, int nf, const int* state,
         // the record that set the global maximum: the lane whose chunk raised the running maximum to maxc
         tbest = w_min_i((first != 0x7fffffff && run == maxc && lmax == maxc) ? first : 0x7fffffff);
       }
+      int store_at = -1;
       if (ln.id == 0) {
         int pi = 0, pj = 0, direc = 1;
         if (maxc > -1 && tbest != 0x7fffffff) {
@@ -364,9 +391,16 @@ CT_HD int organize_and_decode(const FeatureRec* feats, int nf, const int* state,
                   mk.corners[k][q + 4][d] = tswap;
                 }
           }
-          if (nout < out_cap) out[nout] = mk;
+          if (nout < out_cap) store_at = nout;
           ++nout;
         }
+      }
+      w_sync();
+      store_at = w_bcast_i(store_at, 0);
+      if (store_at >= 0) {
+        const int* src = reinterpret_cast<const int*>(&mk);
+        int* dst = reinterpret_cast<int*>(out + store_at);
+        for (int q = ln.id; q < kMkWords; q += ln.n) dst[q] = src[q];
       }
       w_sync();
     }

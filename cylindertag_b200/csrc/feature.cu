@@ -157,6 +157,8 @@ __global__ void __launch_bounds__(32) decode_kernel(const FeatureRec* __restrict
   sc.order = smem_i + 256;
   sc.link = reinterpret_cast<uint8_t*>(smem_i + 384);
   sc.cover = smem_i + 384 + 32;
+  __shared__ ctag_marker s_mk;
+  sc.mk = &s_mk;
   const int nf = fstate[fr * 4 + 2];
   int ngroups = 0, flagged = 0, stale = 0, nm = 0;
   if (nf > 0)

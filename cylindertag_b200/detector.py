@@ -94,7 +94,7 @@ class Detector:
         self._pending.append(n)
 
     def collect(self, cap_per_frame=16):
-        """Results of the oldest enqueued batch (up to two batches may be in flight)."""
+        """Results of the oldest enqueued batch (up to max_in_flight() batches may be pending)."""
         n = self._pending.pop(0) if getattr(self, "_pending", None) else self._n
         out = np.zeros((n, cap_per_frame), C.MARKER_DTYPE)
         cnt = np.zeros(n, np.int32)

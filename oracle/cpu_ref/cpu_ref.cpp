@@ -264,7 +264,8 @@ void detect_gray(const std::vector<uint8_t>& gray, int w, int h, const int* stat
   }
   std::vector<int> father(128), group_of(128), order(128), cover(2 * (size_t)srows * scols + 32);
   std::vector<uint8_t> link(128);
-  DecodeScratch ds{father.data(), link.data(), group_of.data(), order.data(), cover.data()};
+  ctag_marker work_mk;
+  DecodeScratch ds{father.data(), link.data(), group_of.data(), order.data(), cover.data(), &work_mk};
   R.markers.resize(50);
   int flagged = 0, stale = 0;
   R.n_markers = organize_and_decode(feats.data(), R.n_features, state, srows, scols, fsz, Lanes{0, 1}, ds, R.markers.data(), 50, 0,

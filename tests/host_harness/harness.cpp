@@ -130,7 +130,8 @@ int hh_organize_decode(const FeatureRec* feats, int nf, const int32_t* state, in
                        int cap, int32_t* info /* n_groups, flagged, stale */) {
   std::vector<int> father(128), group_of(128), order(128), cover(2 * rows * cols + 32);
   std::vector<uint8_t> link(128);
-  DecodeScratch sc{father.data(), link.data(), group_of.data(), order.data(), cover.data()};
+  ctag_marker work_mk;
+  DecodeScratch sc{father.data(), link.data(), group_of.data(), order.data(), cover.data(), &work_mk};
   return organize_and_decode(feats, nf, state, rows, cols, fsz, Lanes{0, 1}, sc, out, cap, 0, &info[0], &info[1], &info[2]);
 }
 
