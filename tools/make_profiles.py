@@ -38,7 +38,7 @@ def launches():
     tot = sum(mean(v["gpu__time_duration.sum"]) for v in agg.values())
     d = last_json(os.path.join(P, "r1_bench_final.json"))
     md = ["# Round 1, final state: ncu launch list + bench (4K BGR, batch 64, 6 markers/frame)", "",
-          "Command: `ncu --metrics gpu__time_duration.sum,sm__cycles_active.avg,sm__cycles_elapsed.max,sm__inst_executed.sum --clock-control none -s 85 -c 68 --csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu`",
+          "Command: `ncu --metrics gpu__time_duration.sum,sm__cycles_active.avg,sm__cycles_elapsed.max,sm__inst_executed.sum --clock-control none -s 117 -c 100 --csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu`",
           "(per-launch times are cold-cache and serialised: compare shares, not absolutes; raw csv: r1_launches_final.csv; 16 kernels per batch)", "",
           "| kernel | launches | avg us | share of summed time | SMs busy (active / elapsed cycles) | busy us | warp instructions (M) |", "|---|---|---|---|---|---|---|"]
     tb = 0
@@ -55,7 +55,7 @@ def launches():
            f"Front kernel: {d['roofline']['achieved']:.0f} GB/s algorithmic = {100 * d['roofline']['frac']:.1f} % of the measured 6552 GB/s.",
            f"e2e (pinned host frames through ctag_detect_batch): {d['e2e']['value']:.0f} frames/s = {d['e2e'].get('ms_per_step', float('nan')):.2f} ms per step (PCIe bound: 1593 MB H2D per step; the same bytes through a plain pinned copy with nothing else running take {d['e2e'].get('h2d_copy_alone_ms_per_step', float('nan')):.2f} ms = {d['e2e'].get('h2d_copy_alone_gbs', float('nan')):.1f} GB/s). CPU baseline: {d['cpu_baseline']['value']:.0f} frames/s on {d['cpu_baseline']['cores']} threads ({d['cpu_baseline']['sample']}).",
            f"Warm single-frame latency (test.bmp through ctag_detect, host frame in, markers out): {d.get('single_frame', {}).get('median_ms', float('nan')):.2f} ms.", "",
-           "Round-1 trajectory of the pipelined step (same workload): 6.9 ms (first correct path) -> 1.78 ms -> 1.43 ms -> 1.40 ms: front kernel 3 CTAs/SM + instruction diet + merged vertical/extrema phase (0.61 -> 0.51 ms), sliding tile columns + L2 prefetch + one-row-pair hand-over (0.51 -> 0.466 ms), CCL runs + link deduplication (0.44 -> 0.23 ms), edges kernel occupancy / register-resident silhouettes / trace early-out and the fit kernel's lane refill + size-sorted work list (quad stage 1.38 -> 1.12 ms, fit instructions 136 M -> 79 M), refine ladder (0.37 -> 0.34 ms)."]
+           "Round-1 trajectory of the pipelined step (same workload): 6.9 ms (first correct path) -> 1.78 ms -> 1.43 ms -> 1.39 ms: front kernel 3 CTAs/SM + instruction diet + merged vertical/extrema phase (0.61 -> 0.51 ms), sliding tile columns + L2 prefetch + one-row-pair hand-over (0.51 -> 0.466 ms), CCL runs + link deduplication (0.44 -> 0.23 ms), edges kernel occupancy / register-resident silhouettes / trace early-out and the fit kernel's lane refill + size-sorted work list (quad stage 1.38 -> 1.12 ms, fit instructions 136 M -> 79 M), refine ladder (0.37 -> 0.34 ms), decode kernel without divisions / local-memory record (0.25 -> 0.19 ms)."]
     open(os.path.join(P, "r1_launches_final.md"), "w").write("\n".join(md) + "\n")
 
 
