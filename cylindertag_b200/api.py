@@ -130,11 +130,9 @@ class CylinderTag:
         return out
 
     def loadCamera(self, path) -> CamInfo:
-        """CylinderTag.cpp:192-196 (cv::FileStorage: cameraMatrix, distCoeffs, both dt: f)."""
-        import cv2
-        fs = cv2.FileStorage(str(path), cv2.FILE_STORAGE_READ)
-        cam = CamInfo(fs.getNode("cameraMatrix").mat(), fs.getNode("distCoeffs").mat())
-        fs.release()
+        """CylinderTag.cpp:192-196 (cv::FileStorage: cameraMatrix, distCoeffs, both dt: f).  The OpenCV YAML 1.0 matrices
+        are parsed here (no OpenCV in the detection modules); dt: f values are float32 like FileStorage returns them."""
+        cam = CamInfo(_read_opencv_matrix(path, "cameraMatrix"), _read_opencv_matrix(path, "distCoeffs"))
         return cam
 
     # ---- Marker Localization (CylinderTag.cpp:198-209, pose_estimation.cpp:50-143) ----
@@ -174,6 +172,26 @@ class CylinderTag:
             if rc != C.OK:
                 raise RuntimeError("drawAxis, " + C.strerror(rc))
         return out
+
+
+def _read_opencv_matrix(path, name):
+    """One `name: !!opencv-matrix` node of an OpenCV YAML 1.0 file -> ndarray (rows x cols; dt f -> float32, d ->
+    float64, i -> int32).  A missing node gives an empty array, like an empty FileNode."""
+    import re
+    try:
+        text = open(path).read()
+    except OSError:
+        return np.zeros((0, 0), np.float32)  # cv::FileStorage on a missing file: loadCamera does not check
+    m = re.search(r"^%s\s*:\s*!!opencv-matrix\s*\n(.*?)data\s*:\s*\[(.*?)\]" % re.escape(name), text, re.S | re.M)
+    if not m:
+        return np.zeros((0, 0), np.float32)
+    head = m.group(1)
+    rows = int(re.search(r"rows\s*:\s*(\d+)", head).group(1))
+    cols = int(re.search(r"cols\s*:\s*(\d+)", head).group(1))
+    dt = re.search(r"dt\s*:\s*\"?(\w+)", head).group(1)
+    vals = [float(v) for v in m.group(2).replace("\n", " ").split(",") if v.strip()]
+    dtype = {"f": np.float32, "d": np.float64, "i": np.int32}.get(dt[-1], np.float64)
+    return np.array(vals, np.float64).astype(dtype).reshape(rows, cols)
 
 
 def select_pose_points(mk: MarkerInfo, model: ModelInfo):

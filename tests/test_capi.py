@@ -80,3 +80,36 @@ def test_product_package_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt, os.path.join(dirpath, f)
+
+
+def test_detection_modules_do_not_need_opencv():
+    """cv2 is the ORACLE's library.  In the product package only synth.py (input synthesis for tests / bench) may use
+    it; the detector, the mirror class and the C ABI binding must not."""
+    pkg = os.path.join(ROOT, "cylindertag_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py") and f != "synth.py":
+            assert "cv2" not in open(os.path.join(pkg, f)).read(), f
+
+
+def test_camera_loader_matches_filestorage(tmp_path):
+    """CylinderTag.loadCamera parses OpenCV YAML 1.0 itself: same matrices as cv::FileStorage (CylinderTag.cpp:192-196)."""
+    import cv2
+    import numpy as np
+    from cylindertag_b200.api import CylinderTag, _read_opencv_matrix
+    path = os.path.join(ROOT, "tests", "golden", "data", "cameraParams.yml")
+    fs = cv2.FileStorage(path, cv2.FILE_STORAGE_READ)
+    tag = CylinderTag.__new__(CylinderTag)  # the loader is host code: no detector needed
+    cam = tag.loadCamera(path)
+    for got, name in ((cam.Intrinsic, "cameraMatrix"), (cam.distCoeffs, "distCoeffs")):
+        want = fs.getNode(name).mat()
+        assert got.dtype == want.dtype and np.array_equal(got, want), name
+    # a written-by-OpenCV file with another dt / layout, and a missing node
+    out = str(tmp_path / "cam.yml")
+    w = cv2.FileStorage(out, cv2.FILE_STORAGE_WRITE)
+    K = np.array([[2200.5, 0, 960], [0, 2201.25, 540], [0, 0, 1]], np.float64)
+    w.write("cameraMatrix", K)
+    w.write("distCoeffs", np.zeros((5, 1), np.float32))
+    w.release()
+    assert np.array_equal(_read_opencv_matrix(out, "cameraMatrix"), K)
+    assert _read_opencv_matrix(out, "distCoeffs").shape == (5, 1)
+    assert _read_opencv_matrix(out, "nothing").size == 0
