@@ -1,12 +1,17 @@
 // imageio.h -- minimal frame ingest for programs that use the mirror class without OpenCV:
 // uncompressed BMP (8-bit palettised gray, 24-bit BGR, 32-bit BGRA; bottom-up or top-down) and binary PGM/PPM.
 // Stands in for cv::imread at main.cpp:29 for the formats the reference's sample data uses (test.bmp).
+// With CTAG_WITH_ZLIB defined (link -lz) it also reads non-interlaced 8-bit PNG (gray, gray+alpha, RGB, RGBA, palette).
 #pragma once
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <string>
 #include <vector>
+
+#ifdef CTAG_WITH_ZLIB
+#include <zlib.h>
+#endif
 
 #include "CylinderTag.h"
 
@@ -24,6 +29,91 @@ inline uint32_t rd32(const uint8_t* p) { return p[0] | (p[1] << 8) | (p[2] << 16
 inline uint16_t rd16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
 }  // namespace detail
 
+#ifdef CTAG_WITH_ZLIB
+namespace detail {
+inline uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | (p[1] << 16) | (p[2] << 8) | p[3]; }
+inline int paeth(int a, int b, int c) {
+  const int p = a + b - c, pa = p > a ? p - a : a - p, pb = p > b ? p - b : b - p, pc = p > c ? p - c : c - p;
+  return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+}  // namespace detail
+
+// PNG (ISO/IEC 15948): 8-bit, non-interlaced.  Colour images come back as B,G,R like cv::imread; alpha is dropped.
+inline Image read_png(const std::vector<uint8_t>& buf) {
+  Image img;
+  static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+  if (buf.size() < 33 || std::memcmp(buf.data(), sig, 8) != 0) return img;
+  uint32_t w = 0, h = 0;
+  int depth = 0, ctype = -1, interlace = 0;
+  std::vector<uint8_t> idat, pal;
+  for (size_t pos = 8; pos + 12 <= buf.size();) {
+    const uint32_t len = detail::be32(&buf[pos]);
+    if (pos + 12 + (size_t)len > buf.size()) return img;
+    const uint8_t* type = &buf[pos + 4];
+    const uint8_t* d = &buf[pos + 8];
+    if (!std::memcmp(type, "IHDR", 4) && len >= 13) {
+      w = detail::be32(d), h = detail::be32(d + 4), depth = d[8], ctype = d[9], interlace = d[12];
+    } else if (!std::memcmp(type, "PLTE", 4)) {
+      pal.assign(d, d + len);
+    } else if (!std::memcmp(type, "IDAT", 4)) {
+      idat.insert(idat.end(), d, d + len);
+    } else if (!std::memcmp(type, "IEND", 4)) {
+      break;
+    }
+    pos += 12 + (size_t)len;
+  }
+  int spp = 0;  // samples per pixel
+  switch (ctype) {
+    case 0: spp = 1; break;
+    case 2: spp = 3; break;
+    case 3: spp = 1; break;
+    case 4: spp = 2; break;
+    case 6: spp = 4; break;
+    default: return img;
+  }
+  if (depth != 8 || interlace != 0 || w == 0 || h == 0 || w > 65535 || h > 65535 || idat.empty()) return img;
+  const size_t stride = (size_t)w * spp;
+  std::vector<uint8_t> raw((stride + 1) * h);
+  uLongf out_len = (uLongf)raw.size();
+  if (uncompress(raw.data(), &out_len, idat.data(), (uLong)idat.size()) != Z_OK || out_len != raw.size()) return img;
+  std::vector<uint8_t> prev(stride, 0), cur(stride);
+  const bool colour = ctype == 2 || ctype == 6 || ctype == 3;
+  img.rows = (int)h, img.cols = (int)w, img.channels = colour ? 3 : 1;
+  img.data.resize((size_t)h * w * img.channels);
+  for (uint32_t y = 0; y < h; ++y) {
+    const uint8_t* line = &raw[(stride + 1) * y];
+    const int filter = line[0];
+    for (size_t x = 0; x < stride; ++x) {
+      const int a = x >= (size_t)spp ? cur[x - spp] : 0, b = prev[x], c = x >= (size_t)spp ? prev[x - spp] : 0;
+      int v = line[1 + x];
+      switch (filter) {
+        case 0: break;
+        case 1: v += a; break;
+        case 2: v += b; break;
+        case 3: v += (a + b) >> 1; break;
+        case 4: v += detail::paeth(a, b, c); break;
+        default: return Image();
+      }
+      cur[x] = (uint8_t)v;
+    }
+    uint8_t* dst = &img.data[(size_t)y * w * img.channels];
+    for (uint32_t x = 0; x < w; ++x) {
+      const uint8_t* s = &cur[(size_t)x * spp];
+      if (ctype == 0 || ctype == 4) {
+        dst[x] = s[0];
+      } else if (ctype == 3) {
+        if ((size_t)3 * s[0] + 2 >= pal.size()) return Image();
+        dst[3 * x] = pal[3 * s[0] + 2], dst[3 * x + 1] = pal[3 * s[0] + 1], dst[3 * x + 2] = pal[3 * s[0]];
+      } else {
+        dst[3 * x] = s[2], dst[3 * x + 1] = s[1], dst[3 * x + 2] = s[0];
+      }
+    }
+    prev.swap(cur);
+  }
+  return img;
+}
+#endif  // CTAG_WITH_ZLIB
+
 // Returns an empty image on any error (like cv::imread).
 inline Image imread(const std::string& path) {
   Image img;
@@ -34,6 +124,9 @@ inline Image imread(const std::string& path) {
   size_t n;
   while ((n = std::fread(tmp, 1, sizeof(tmp), f)) > 0) buf.insert(buf.end(), tmp, tmp + n);
   std::fclose(f);
+#ifdef CTAG_WITH_ZLIB
+  if (buf.size() >= 8 && buf[0] == 0x89 && buf[1] == 'P' && buf[2] == 'N' && buf[3] == 'G') return read_png(buf);
+#endif
   if (buf.size() >= 54 && buf[0] == 'B' && buf[1] == 'M') {
     const uint32_t off = detail::rd32(&buf[10]), hdr = detail::rd32(&buf[14]);
     if (hdr < 40) return img;
