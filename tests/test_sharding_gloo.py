@@ -80,3 +80,48 @@ def test_gather_world2_equals_single(n_frames):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(res)
+
+
+def _seq_worker(rank, world, port, n_frames, q):
+    """Real detection records through the sharding path: each rank runs the C++ oracle port (the CPU stand-in for its
+    GPU) on ITS block of the config-2 sequence; rank 0 compares the gathered list with a single-process run."""
+    import cv2
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from cylindertag_b200 import synth
+    from cylindertag_b200.sharding import frame_shard, gather_detections
+    from oracle import ctag_oracle as o
+    from oracle.cpu_ref import api as cpu
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    data = os.path.join(ROOT, "tests", "golden", "data")
+    gray = cv2.imread(os.path.join(data, "test_gray.png"), cv2.IMREAD_UNCHANGED)
+    state, fs = o.load_marker_file(os.path.join(data, "CTag_2f12c.marker"))
+    s, e = frame_shard(n_frames, rank, world)
+    frames = synth.video_sequence(gray, 120, 2024, first=s, count=e - s)
+    counts, markers = cpu.detect_batch(frames, state, fs, True, 5, threads=2, cap=8)
+    allm, allc = gather_detections(markers, counts[:, 5].copy(), n_frames, dist)
+    if rank == 0:
+        whole = synth.video_sequence(gray, 120, 2024, first=0, count=n_frames)
+        c1, m1 = cpu.detect_batch(whole, state, fs, True, 5, threads=2, cap=8)
+        q.put(bool(np.array_equal(allc, c1[:, 5]) and allm.tobytes() == m1.tobytes() and int(allc.sum()) >= 4 * n_frames))
+    else:
+        q.put(allm is None)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_sequence_equals_single_process():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_seq_worker, args=(r, 2, port, 5, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(res)
