@@ -10,9 +10,12 @@
 // outside the image; replicate borders are patched afterwards).  The half-res gray image, the float image and the
 // tile extrema never touch HBM.
 //
-// Persistent CTAs (as many as fit per SM) walk the tile list with a stride; the TMA load of a CTA's NEXT tile is issued
-// as soon as the staging buffer of the current one is free (after the gray conversion for BGR input, at the top of the
-// iteration for gray input, which double-buffers), so the load latency hides behind the stencil phases.
+// Three families of kernels share the stencil / threshold phases of front_phases.cuh:
+//   front_bgr_slide_kernel / front_gray_slide_kernel   the production kernels: persistent CTAs walk RUNS of tiles down a
+//       tile column and keep what vertically adjacent tiles share in shared memory (see the comments in front of them)
+//   front_kernel<C>   the same phases on independent tiles taken with a stride (whole 192x102 region staged per tile;
+//       the TMA load of a CTA's next tile is issued as soon as the staging buffer is free); kept for A/B runs
+//       (CTAG_FRONT_NOSLIDE=1)
 //
 // HBM traffic per frame (N = w*h): BGR input 3N read + N gray write + N/4 binary write; gray input N + N/4.
 #include "common.cuh"
