@@ -186,3 +186,17 @@ def test_speculative_expand_equals_sequential():
             continue
         lib.hh_expand_both(H.vp(arr), n, init, end, H.vp(out))
         assert out[0] == out[2] and out[1] == out[3], (trial, n, init, end, out)
+
+
+@pytest.mark.parametrize("cols,fsz", [(15, 3), (18, 4)])
+def test_generated_codebooks_all_stages(cols, fsz):
+    """BASELINE config 4's other dictionaries (15 columns / 3-feature windows, 18 / 4): the decode core's coverage walk
+    runs with other row lengths than the shipped 12."""
+    from cylindertag_b200 import synth
+    state = synth.generate_codebook(cols, fsz, 30, seed=7)
+    decoded = 0
+    for seed in (3000, 3001):
+        frame, specs = synth.synthetic_frame(seed, 1920, 1080, state, 2)
+        d = check_frame(frame, state, fsz)
+        decoded += len(d.markers)
+    assert decoded >= 2
