@@ -113,3 +113,17 @@ def test_camera_loader_matches_filestorage(tmp_path):
     assert np.array_equal(_read_opencv_matrix(out, "cameraMatrix"), K)
     assert _read_opencv_matrix(out, "distCoeffs").shape == (5, 1)
     assert _read_opencv_matrix(out, "nothing").size == 0
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    """No CPU fallback behind the binding: with the shared library absent, loading raises (in a fresh interpreter, with
+    CTAG_LIB pointing at a path that does not exist)."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from cylindertag_b200 import _capi\n"
+            "try:\n    _capi.load()\nexcept ImportError as e:\n    print('ImportError', 'no CPU fallback' in str(e))\n"
+            "else:\n    print('loaded')\n") % ROOT
+    env = dict(os.environ, CTAG_LIB=str(tmp_path / "absent" / "libctag_b200.so"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120).stdout
+    assert out.strip() == "ImportError True"
