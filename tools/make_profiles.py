@@ -106,7 +106,12 @@ def variants():
           "All numbers: CUDA events, pipelined loop (several batches in flight, one stream each), parity spot check against the oracle = ok in every run.", "",
           "| variant | frames/s (device resident) | ms / step | front kernel ms / launch | front roofline frac | e2e frames/s (pinned host, H2D inside) |", "|---|---|---|---|---|---|",
           row("4K BGR, batch 64 (default, BASELINE config 4/5; 100 steps)", d), row("4K gray, batch 64 (detect's own contract; 1.25 B/px; sliding gray kernel, 4 CTAs/SM)", vs[0]),
-          row("1080p BGR, batch 128 (BASELINE config 3)", vs[1]), row("1080p gray, batch 128", vs[2]), "", "Unoverlapped stage times (ms per step, batches one at a time):"]
+          row("1080p BGR, batch 128, six markers per frame", vs[1]), row("1080p gray, batch 128, six markers per frame", vs[2])]
+    c3 = os.path.join(G, "bench_1080p_b256_m1.json")
+    if os.path.exists(c3):  # BASELINE config 3 to the letter: 256 frames, ONE rendered marker each
+        shutil.copy(c3, os.path.join(P, "r1_bench_config3_1080p_b256.json"))
+        md.append(row("1080p BGR, batch 256, one marker per frame (BASELINE config 3 as written)", last_json(c3)))
+    md += ["", "Unoverlapped stage times (ms per step, batches one at a time):"]
     for name, v in (("4K BGR", d), ("4K gray", vs[0]), ("1080p BGR (128 frames)", vs[1]), ("1080p gray (128 frames)", vs[2])):
         md.append(f"* {name}: " + ", ".join(f"{k} {x:.3f}" for k, x in v["stages_ms_per_step_unoverlapped"].items()))
     md += ["", "Reading: with gray input the fused front end is bound by its stencil arithmetic and shared-memory traffic, not by HBM",
