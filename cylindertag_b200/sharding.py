@@ -24,8 +24,8 @@ def owner_of(frame: int, n_frames: int, world: int) -> int:
 
 def gather_detections(markers: np.ndarray, counts: np.ndarray, n_frames: int, dist=None, device="cpu"):
     """Gathers per-rank results (markers [n_local, cap], counts [n_local]) to rank 0 in frame order.
-    Returns (markers [n_frames, cap], counts [n_frames]) on rank 0 and (None, None) elsewhere.  With dist=None (single
-    process) it is the identity."""
+    Returns (markers [n_frames, cap], counts [n_frames]) on rank 0 and (None, None) elsewhere; the `frame` field of the
+    gathered records is rewritten to the global frame index.  With dist=None (single process) it is the identity."""
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
         return markers, counts
     import torch
@@ -53,4 +53,8 @@ def gather_detections(markers: np.ndarray, counts: np.ndarray, n_frames: int, di
         if k:
             all_m[s:e] = b[:k, :cap * rec].copy().view(markers.dtype).reshape(k, cap)
             all_c[s:e] = b[:k, cap * rec:].copy().view(np.int32).reshape(k)
+    # ctag_marker::frame is the index inside the batch a rank ran; in the gathered list it is the global frame index
+    if "frame" in (markers.dtype.names or ()):
+        for f in range(n_frames):
+            all_m["frame"][f, :min(int(all_c[f]), cap)] = f
     return all_m, all_c

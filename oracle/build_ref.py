@@ -48,7 +48,7 @@ def build_ref(force=False):
     jobs = []
     for src in [os.path.join(REFERENCE, s) for s in REF_SOURCES] + [os.path.join(SHIM, s) for s in SHIM_SOURCES]:
         obj = os.path.join(OUT, os.path.basename(src) + ".o")
-        cmd = ["g++"] + CXXFLAGS + ["-I", SHIM, "-I", REFERENCE, "-c", src, "-o", obj]
+        cmd = ["g++"] + CXXFLAGS + ["-I", SHIM, "-I", REFERENCE, "-I", os.path.join(HERE, "..", "include"), "-c", src, "-o", obj]
         jobs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in jobs:

@@ -50,7 +50,7 @@ def load():
         lib.ref_load_model_camera.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p]
         lib.ref_estimate_pose.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         lib.ref_detect_batch_mt.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 8 + \
-            [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+            [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         lib.shim_set_backend.argtypes = [ctypes.c_void_p]
         _lib = lib
     return _lib
@@ -95,6 +95,7 @@ class RefDump:
     status: str              # ok | no_corner | no_feature
     flagged: bool
     markers: list = field(default_factory=list)
+    n_groups: int = 0
 
     @property
     def binary(self):
@@ -143,7 +144,7 @@ class RefDetector:
         rc = lib.ref_detect(self._h, _vp(g), w, h, g.strides[0], int(adaptive_thresh), int(bool(subpix)), int(dist), int(bool(reset_ids)))
         if rc < 0:
             raise RuntimeError("reference detect failed: " + lib.ref_last_error(self._h).decode(errors="replace"))
-        c = np.zeros(8, np.int32)
+        c = np.zeros(12, np.int32)
         lib.ref_counts(self._h, _vp(c))
         labels = np.zeros((h // 2, w // 2), np.int32)
         comps = np.zeros((max(int(c[1]), 1), 5), np.int32)
@@ -173,7 +174,7 @@ class RefDetector:
             a += n
             p += npos
         return RefDump(int(c[0]), labels, comps[:int(c[1])], quads[:int(c[2])], fc[:nf], fcen[:nf], fang[:nf],
-                       ("ok", "no_corner", "no_feature")[int(c[5])], bool(c[6]), markers)
+                       ("ok", "no_corner", "no_feature")[int(c[5])], bool(c[6]), markers, int(c[8]))
 
     def load_model_camera(self, model_path, camera_path):
         if self._lib.ref_load_model_camera(self._h, os.fsencode(model_path), os.fsencode(camera_path)) != 0:
@@ -189,26 +190,73 @@ class RefDetector:
         return [(int(ids[i]), rt[i, :3].copy(), rt[i, 3:].copy()) for i in range(n)]
 
 
-def detect_batch_mt(frames, state, feature_size, adaptive_thresh=5, subpix=True, dist=5, threads=1, ids_cap=16):
+def inverse_flag(state, marker_id, feature_pos, feature_id):
+    """pos_with_ID::inverse is not kept in MarkerInfo (header/corner_detector.h:16-22); it follows from the output.
+    featurePos lists (y + direc * i) mod cols for the occupied code slots i in ascending order
+    (corner_detector.cpp:1317-1321), so consecutive entries step forwards (direc = 1) or backwards (direc = -1, the
+    inverse reading).  Fallback for a single occupied slot: a legal state never equals its inverse reading (its two
+    digits lie in the same half, the inverse swaps halves), so a matching feature tells the direction.
+    Returns 0 / 1, or -1 if undecidable."""
+    cols = state.shape[1]
+    pos = [p for p in feature_pos if p >= 0]
+    steps = [(b - a) % cols for a, b in zip(pos, pos[1:])]
+    fwd = sum(1 for s in steps if 0 < s < cols / 2)
+    inv = sum(1 for s in steps if s > cols / 2)
+    if fwd != inv:
+        return int(inv > fwd)
+    if len(pos) != len(feature_id):
+        return -1
+    fwd = inv = 0
+    for p, c in zip(pos, feature_id):
+        if c < 0:
+            continue
+        s = int(state[marker_id, p])
+        fwd += s == c
+        inv += s == (7 - c // 8) + (7 - c % 8) * 8
+    return -1 if fwd == inv else int(inv > fwd)
+
+
+def detect_batch_mt(frames, state, feature_size, adaptive_thresh=5, subpix=True, dist=5, threads=1, cap=32):
     """main.cpp's per-frame loop (cvtColor for BGR input, then detect) over a batch, one CylinderTag per host thread.
-    Returns (marker count per frame, marker ids per frame padded with -1)."""
+    Returns (counts [n][8]: n_labels, n_legal, n_quads, n_features, n_groups, n_markers, status, flagged;
+             markers [n][cap] in the ctag_marker record layout, `inverse` derived from the dictionary)."""
+    from cylindertag_b200 import _capi as C
     fr = np.ascontiguousarray(frames, np.uint8)
     ch = 1 if fr.ndim == 3 else 3
     n, h, w = fr.shape[:3]
     st = np.ascontiguousarray(state, np.int32)
-    counts = np.zeros(n, np.int32)
-    ids = np.full((n, ids_cap), -1, np.int32)
+    nmk = np.zeros(n, np.int32)
+    counts = np.zeros((n, 8), np.int32)
+    markers = np.zeros((n, cap), C.MARKER_DTYPE)
     rc = load().ref_detect_batch_mt(_vp(st), st.shape[0], st.shape[1], int(feature_size), _vp(fr), n, w, h, ch, int(adaptive_thresh),
-                                    int(bool(subpix)), int(dist), int(threads), _vp(counts), _vp(ids), ids_cap)
+                                    int(bool(subpix)), int(dist), int(threads), _vp(nmk), None, 0, _vp(counts), _vp(markers), cap)
     if rc != 0:
         raise RuntimeError("reference batch detect failed")
-    return counts, ids
+    for f in range(n):
+        for k in range(min(int(nmk[f]), cap)):
+            m = markers[f, k]
+            nf = min(int(m["n_features"]), len(m["feature_id"]))
+            m["inverse"] = inverse_flag(st, int(m["marker_id"]), m["feature_pos"].tolist(), m["feature_id"][:nf].tolist())
+    return counts, markers
+
+
+def detect_batch(frames, state, fs, subpix=True, dist=5, threads=1, cap=32):
+    """detect_batch_mt with adaptiveThresh = 5 (the demo's call, main.cpp:57)."""
+    return detect_batch_mt(frames, state, fs, 5, subpix, dist, threads, cap)
 
 
 def detect_batch_bgr(frames, state, fs, adaptive_thresh, subpix, dist, threads):
     """bench.py's CPU arm: total markers found."""
-    counts, _ = detect_batch_mt(frames, state, fs, adaptive_thresh, subpix, dist, threads)
-    return int(counts.sum())
+    fr = np.ascontiguousarray(frames, np.uint8)
+    ch = 1 if fr.ndim == 3 else 3
+    n, h, w = fr.shape[:3]
+    st = np.ascontiguousarray(state, np.int32)
+    nmk = np.zeros(n, np.int32)
+    rc = load().ref_detect_batch_mt(_vp(st), st.shape[0], st.shape[1], int(fs), _vp(fr), n, w, h, ch, int(adaptive_thresh),
+                                    int(bool(subpix)), int(dist), int(threads), _vp(nmk), None, 0, None, None, 0)
+    if rc != 0:
+        raise RuntimeError("reference batch detect failed")
+    return int(nmk.sum())
 
 
 # ---- cv2 backend ---------------------------------------------------------------------------------------------------

@@ -28,6 +28,8 @@
 
 #include <pthread.h>
 
+#include "ctag.h"  // the product's public C header: only for the POD ctag_marker layout the batch leg fills
+
 #include <opencv2/core.hpp>
 #include "ceres/ceres.h"
 #include "ceres/rotation.h"
@@ -162,7 +164,8 @@ __attribute__((visibility("default"))) int ref_detect(void* hp, const unsigned c
     return a.rc;
 }
 
-// counts[8]: n_labels (incl. background), n_legal, n_quads, n_features, n_markers, status, flagged, total features in markers
+// counts[9]: n_labels (incl. background), n_legal, n_quads, n_features, n_markers, status, flagged, total features in
+// markers, n_groups (markerOrganization's cnt)
 __attribute__((visibility("default"))) void ref_counts(void* hp, int* c) {
     RefHandle* h = (RefHandle*)hp;
     c[0] = h->tag->detector.nccomp_area;
@@ -175,6 +178,7 @@ __attribute__((visibility("default"))) void ref_counts(void* hp, int* c) {
     int t = 0;
     for (const auto& m : h->markers) t += (int)m.cornerLists.size();
     c[7] = t;
+    c[8] = h->untouched ? 0 : h->tag->detector.cnt;
 }
 
 // label image of connectedComponentLabeling (corner_detector.cpp:82), half_h x half_w int32
@@ -293,7 +297,29 @@ struct BatchArgs {
     const int* state; int rows, cols, fs;
     const unsigned char* frames; int n, w, h, channels, win, subpix, dist, tid, nthreads;
     int* marker_counts; int* marker_ids; int ids_cap; int rc;
+    int* counts8; ctag_marker* records; int rec_cap;
 };
+
+// MarkerInfo -> POD record (features beyond CTAG_MAX_FEATURES are dropped; n_features keeps the true count)
+static void fill_record(const MarkerInfo& m, int frame, ctag_marker* r) {
+    std::memset(r, 0, sizeof(*r));
+    r->marker_id = m.markerID;
+    r->n_features = (int)m.cornerLists.size();
+    r->inverse = -1;  // not recorded by the reference; oracle/ref_api.py derives it from the dictionary
+    r->frame = frame;
+    for (int k = 0; k < CTAG_MAX_FEATURES; k++) r->feature_pos[k] = -1;
+    for (size_t k = 0; k < m.featurePos.size() && k < CTAG_MAX_FEATURES; k++) r->feature_pos[k] = m.featurePos[k];
+    for (size_t k = 0; k < m.cornerLists.size() && k < CTAG_MAX_FEATURES; k++) {
+        r->feature_id[k] = m.feature_ID[k];
+        r->id_left[k] = m.feature_ID_left[k];
+        r->id_right[k] = m.feature_ID_right[k];
+        r->cr_left[k] = m.cr_left[k];
+        r->cr_right[k] = m.cr_right[k];
+        r->edge_length[k] = m.edge_length[k];
+        r->center[k][0] = m.feature_center[k].x; r->center[k][1] = m.feature_center[k].y;
+        for (int c = 0; c < 8; c++) { r->corners[k][c][0] = m.cornerLists[k][c].x; r->corners[k][c][1] = m.cornerLists[k][c].y; }
+    }
+}
 
 static void* batch_worker(void* p) {
     BatchArgs* a = (BatchArgs*)p;
@@ -309,7 +335,19 @@ static void* batch_worker(void* p) {
             if (a->channels == 3) cv::cvtColor(frame, gray, cv::COLOR_BGR2GRAY); else gray = frame;
             markers.clear();
             tag.detector.ID_left = 0; tag.detector.ID_right = 0;
+            MarkerInfo sentinel; sentinel.markerID = SENTINEL_ID;
+            markers.assign(1, sentinel);
             tag.detect(gray, markers, a->win, a->subpix != 0, a->dist);
+            const bool untouched = markers.size() == 1 && markers[0].markerID == SENTINEL_ID;
+            if (untouched) markers.clear();
+            if (a->counts8) {
+                int* c = a->counts8 + 8 * (size_t)f;
+                c[0] = tag.detector.nccomp_area; c[1] = (int)tag.quadAreas_labeled.size(); c[2] = (int)tag.corners.size();
+                c[3] = (int)tag.features.size(); c[4] = untouched ? 0 : tag.detector.cnt; c[5] = (int)markers.size();
+                c[6] = !untouched ? 0 : tag.corners.empty() ? 1 : 2;
+                c[7] = tag.corners.size() > 1000 || tag.features.size() > 100;
+            }
+            if (a->records) for (int k = 0; k < (int)markers.size() && k < a->rec_cap; k++) fill_record(markers[k], f, a->records + (size_t)f * a->rec_cap + k);
             a->marker_counts[f] = (int)markers.size();
             if (a->marker_ids) for (int k = 0; k < a->ids_cap; k++) a->marker_ids[(size_t)f * a->ids_cap + k] = k < (int)markers.size() ? markers[k].markerID : -1;
         }
@@ -319,7 +357,8 @@ static void* batch_worker(void* p) {
 
 __attribute__((visibility("default"))) int ref_detect_batch_mt(const int* state, int rows, int cols, int fs, const unsigned char* frames, int n, int w, int h,
                                                                int channels, int adaptive_thresh, int subpix, int subpix_dist, int threads,
-                                                               int* marker_counts, int* marker_ids, int ids_cap) {
+                                                               int* marker_counts, int* marker_ids, int ids_cap, int* counts8,
+                                                               void* records, int rec_cap) {
     if (threads < 1) threads = 1;
     if (threads > n) threads = n > 0 ? n : 1;
     // "No corner detected!" goes to cout from every thread; silence the shared stream for the duration of the batch
@@ -330,7 +369,8 @@ __attribute__((visibility("default"))) int ref_detect_batch_mt(const int* state,
     pthread_attr_init(&at);
     pthread_attr_setstacksize(&at, (size_t)256 << 20);
     for (int t = 0; t < threads; t++) {
-        args[t] = BatchArgs{state, rows, cols, fs, frames, n, w, h, channels, adaptive_thresh, subpix, subpix_dist, t, threads, marker_counts, marker_ids, ids_cap, 0};
+        args[t] = BatchArgs{state, rows, cols, fs, frames, n, w, h, channels, adaptive_thresh, subpix, subpix_dist, t, threads, marker_counts, marker_ids, ids_cap, 0,
+                            counts8, (ctag_marker*)records, rec_cap};
         pthread_create(&tids[t], &at, batch_worker, &args[t]);
     }
     int rc = 0;
@@ -338,6 +378,74 @@ __attribute__((visibility("default"))) int ref_detect_batch_mt(const int* state,
     pthread_attr_destroy(&at);
     std::cout.rdbuf(old);
     return rc;
+}
+
+// ---- direct access to the stand-in's primitives, for the known-answer tests against cv2 (tests/test_ref_pinning.py) --
+__attribute__((visibility("default"))) int shim_resize_cubic_u8(const unsigned char* src, int sw, int sh, unsigned char* dst, int dw, int dh) {
+    try {
+        cv::Mat s(sh, sw, CV_8UC1, (void*)src), d;
+        cv::resize(s, d, cv::Size(dw, dh), 0.5, 0.5, cv::INTER_CUBIC);
+        for (int i = 0; i < dh; i++) std::memcpy(dst + (size_t)i * dw, d.ptr<unsigned char>(i), dw);
+    } catch (...) { return -1; }
+    return 0;
+}
+__attribute__((visibility("default"))) int shim_ccl(const unsigned char* img, int w, int h, int* labels, int* stats, int stats_cap) {
+    try {
+        cv::Mat s(h, w, CV_8UC1, (void*)img), lab, st, cen;
+        int n = cv::connectedComponentsWithStats(s, lab, st, cen, 8, CV_32S, cv::CCL_BBDT);
+        for (int i = 0; i < h; i++) std::memcpy(labels + (size_t)i * w, lab.ptr<int>(i), sizeof(int) * w);
+        for (int l = 0; l < n && l < stats_cap; l++) std::memcpy(stats + 5 * l, st.ptr<int>(l), 5 * sizeof(int));
+        return n;
+    } catch (...) { return -1; }
+}
+__attribute__((visibility("default"))) int shim_fit_line(const int* xy, int n, int dist, float* line4) {
+    try {
+        std::vector<cv::Point> pts(n);
+        for (int i = 0; i < n; i++) pts[i] = cv::Point(xy[2 * i], xy[2 * i + 1]);
+        std::vector<float> line;
+        cv::fitLine(pts, line, dist, 0, 0.01, 0.01);
+        for (int k = 0; k < 4; k++) line4[k] = line[k];
+    } catch (...) { return -1; }
+    return 0;
+}
+__attribute__((visibility("default"))) float shim_fast_atan2(float y, float x) { return cv::fastAtan2(y, x); }
+__attribute__((visibility("default"))) int shim_solve2x2(const float* a4, const float* b2, float* x2, double* det) {
+    cv::Mat A(2, 2, CV_32FC1), B(2, 1, CV_32FC1), X(2, 1, CV_32FC1);
+    A.at<float>(0, 0) = a4[0]; A.at<float>(0, 1) = a4[1]; A.at<float>(1, 0) = a4[2]; A.at<float>(1, 1) = a4[3];
+    B.at<float>(0, 0) = b2[0]; B.at<float>(1, 0) = b2[1];
+    *det = cv::determinant(A);
+    if (*det == 0) return 1;
+    cv::solve(A, B, X);
+    x2[0] = X.at<float>(0, 0); x2[1] = X.at<float>(1, 0);
+    return 0;
+}
+__attribute__((visibility("default"))) int shim_convert_u8_f32(const unsigned char* src, int n, double alpha, float* dst) {
+    cv::Mat s(1, n, CV_8UC1, (void*)src), d;
+    s.convertTo(d, CV_32FC1, alpha);
+    std::memcpy(dst, d.ptr<float>(0), sizeof(float) * n);
+    return 0;
+}
+__attribute__((visibility("default"))) int shim_bgr2gray(const unsigned char* bgr, int w, int h, unsigned char* gray) {
+    cv::Mat s(h, w, CV_8UC3, (void*)bgr), d;
+    cv::cvtColor(s, d, cv::COLOR_BGR2GRAY);
+    for (int i = 0; i < h; i++) std::memcpy(gray + (size_t)i * w, d.ptr<unsigned char>(i), w);
+    return 0;
+}
+__attribute__((visibility("default"))) int shim_undistort_project(const float* xy, const float* xyz, int n, const float* K9, const float* D5,
+                                                                  const double* rvec, const double* tvec, float* und_xy, float* proj_xy) {
+    try {
+        cv::Mat K(3, 3, CV_32FC1), D(5, 1, CV_32FC1), r(3, 1, CV_64FC1), t(3, 1, CV_64FC1);
+        for (int i = 0; i < 9; i++) K.at<float>(i / 3, i % 3) = K9[i];
+        for (int i = 0; i < 5; i++) D.at<float>(i, 0) = D5[i];
+        for (int i = 0; i < 3; i++) { r.at<double>(i, 0) = rvec[i]; t.at<double>(i, 0) = tvec[i]; }
+        std::vector<cv::Point2f> p(n), u, q;
+        std::vector<cv::Point3f> o(n);
+        for (int i = 0; i < n; i++) { p[i] = cv::Point2f(xy[2 * i], xy[2 * i + 1]); o[i] = cv::Point3f(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]); }
+        cv::undistortPoints(p, u, K, D, cv::noArray(), K);
+        cv::projectPoints(o, r, t, K, D, q);
+        for (int i = 0; i < n; i++) { und_xy[2 * i] = u[i].x; und_xy[2 * i + 1] = u[i].y; proj_xy[2 * i] = q[i].x; proj_xy[2 * i + 1] = q[i].y; }
+    } catch (...) { return -1; }
+    return 0;
 }
 
 }  // extern "C"

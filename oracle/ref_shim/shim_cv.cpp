@@ -85,9 +85,12 @@ void cvtColor(const Mat& src, Mat& dst, int code) {
 // resize, INTER_CUBIC, 8UC1 (CylinderTag.cpp:79).  Restates imgproc/resize.cpp's generic path for that case:
 // per destination column/row the source position ((d + 0.5) * scale - 0.5) in float, Keys' bicubic weights with
 // A = -0.75 in float, rounded to 11-bit fixed point (cvRound), replicate border; horizontal pass in exact int32;
-// vertical pass: the vectorised body (VResizeCubicVec_32s8u, 8 columns at a time in the SSE baseline build of the
-// Python wheel) evaluates S0*b0 + (S1*b1 + (S2*b2 + S3*b3)) in binary32 with b = beta * 2^-22 and rounds half to even,
-// the scalar tail uses the integer form (v + 2^21) >> 22.
+// vertical pass (VResizeCubicVec_32s8u): S0*b0 + (S1*b1 + (S2*b2 + S3*b3)) in binary32 with b = beta * 2^-22, rounded
+// half to even.  cv2 4.13 gives this float form on every column, also where the width is not a multiple of the vector
+// length (the integer form (v + 2^21) >> 22 differs on ties; measured, tests/test_ref_pinning.py).
+// Non-integer scales (odd source sizes): this restatement equals cv2 with cv::setUseOptimized(false); with CPU dispatch
+// on, the library's own result differs by 1 DN on ~5 % of the pixels, i.e. OpenCV itself has no single answer there,
+// which is why every config and the product's C ABI keep to even sizes (exact 2x, identical either way).
 static inline void cubic_coeffs(float x, float* c) {
     const float A = -0.75f;
     c[0] = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
@@ -133,7 +136,6 @@ static void resize_cubic_u8_native(const uchar* src, int sw, int sh, size_t sste
             D[dx] = v;
         }
     }
-    const int vec_w = dw - dw % 8;
     for (int dy = 0; dy < dh; dy++) {
         const int* S[4];
         for (int k = 0; k < 4; k++) {
@@ -145,18 +147,12 @@ static void resize_cubic_u8_native(const uchar* src, int sw, int sh, size_t sste
         const float scale = 1.f / (2048 * 2048);
         const float b0 = b[0] * scale, b1 = b[1] * scale, b2 = b[2] * scale, b3 = b[3] * scale;
         uchar* D = dst + (size_t)dy * dstep;
-        int x = 0;
-        for (; x < vec_w; x++) {
+        for (int x = 0; x < dw; x++) {
             float t = (float)S[3][x] * b3;  // built with -ffp-contract=off: every step rounds to binary32
             t = (float)S[2][x] * b2 + t;
             t = (float)S[1][x] * b1 + t;
             t = (float)S[0][x] * b0 + t;
             int r = cvRound(t);
-            D[x] = (uchar)(r < 0 ? 0 : r > 255 ? 255 : r);
-        }
-        for (; x < dw; x++) {
-            int v = S[0][x] * b[0] + S[1][x] * b[1] + S[2][x] * b[2] + S[3][x] * b[3];
-            int r = (v + (1 << 21)) >> 22;
             D[x] = (uchar)(r < 0 ? 0 : r > 255 ? 255 : r);
         }
     }

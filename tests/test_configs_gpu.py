@@ -1,0 +1,141 @@
+"""BASELINE.json configs 1-4 AS WRITTEN, CUDA path through the C ABI against results frozen from the
+reference's own code (tests/golden/ref_*.npz, made by tests/golden/make_golden_ref.py from oracle/_ref =
+corner_detector.cpp + CylinderTag.cpp compiled unmodified).  Per frame: the binary image (CRC), the legal component
+list, the quad candidate set, the feature list, every marker field.  Bars: integers exact, coordinates <= 1e-3 px.
+
+  config 1  test.bmp, detect(gray, 5, true, 5) + estimatePose (<= 1e-4 rad / 1e-4 |t|)
+  config 2  120-frame sequence (substitute for the missing test.avi)
+  config 3  256 frames 1920x1080 BGR, one 2f12c marker each, seeds 1000..1255
+  config 4  3840x2160 BGR, 4-8 markers per frame, 8 frames per codebook: 2f12c, 15c3f, 18c4f (default_rng(7))
+Frames are re-rendered here from their seeds; the goldens hold results only."""
+import ctypes
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from cylindertag_b200 import Detector, synth
+from tests import configs
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DATA = os.path.join(GOLDEN, "data")
+TOL = 1e-3
+INFO_KEYS = ("n_labels", "n_legal", "n_quads", "n_features", "n_groups", "n_markers", "status", "flagged")
+
+
+def check_against_golden(det, frames, gold, first=0, sub=8, ctx=""):
+    """frames: [n,h,w] gray or [n,h,w,3] BGR, frame i = golden frame first + i.  Runs them in sub-batches small enough to
+    stay one chunk, so the stage dumps of every frame can be read back.  Returns (markers checked, worst corner error)."""
+    worst, checked = 0.0, 0
+    for s in range(0, len(frames), sub):
+        part = frames[s:s + sub]
+        markers, counts, info = det.detect_batch(part, 5, True, 5, cap_per_frame=32)
+        for i in range(len(part)):
+            f = first + s + i
+            c = f"{ctx} frame {f}"
+            want = gold["counts"][f]
+            if want[7]:
+                assert int(info["flagged"][i]) == 1, c
+                continue
+            assert [int(info[k][i]) for k in INFO_KEYS] == list(want), c
+            assert zlib.crc32(np.ascontiguousarray(det.debug_binary(i)).tobytes()) == int(gold["binary_crc"][f]), c + ": binary image"
+            comps = det.debug_components(i)
+            assert np.array_equal(comps[:, 1:], gold["comps"][gold["comp_start"][f]:gold["comp_start"][f + 1]]), c + ": components"
+            _, quads = det.debug_quads(i)
+            gq = gold["quads"][gold["quad_start"][f]:gold["quad_start"][f + 1]]
+            assert quads.shape == gq.shape and np.abs(quads - gq).max(initial=0) <= TOL, c + ": quad candidates"
+            if want[6] == 0:
+                cor = det.debug_features(i)[0]
+                gf = gold["feats"][gold["feat_start"][f]:gold["feat_start"][f + 1]]
+                assert cor.shape == gf.shape and np.abs(cor - gf).max(initial=0) <= TOL, c + ": features"
+            a, b = int(gold["marker_start"][f]), int(gold["marker_start"][f + 1])
+            assert int(counts[i]) == b - a, c
+            for k in range(b - a):
+                g = markers[i][k]
+                nf = int(gold["n_features"][a + k])
+                assert (int(g["marker_id"]), int(g["inverse"]), int(g["n_features"])) == \
+                       (int(gold["marker_id"][a + k]), int(gold["inverse"][a + k]), nf), (c, k)
+                npos = int((gold["feature_pos"][a + k] >= 0).sum())
+                assert list(g["feature_pos"][:npos]) == list(gold["feature_pos"][a + k][:npos]), (c, k)
+                for name in ("feature_id", "id_left", "id_right"):
+                    assert list(g[name][:nf]) == list(gold[name][a + k][:nf]), (c, k, name)
+                err = float(np.abs(g["corners"][:nf] - gold["corners"][a + k][:nf]).max())
+                worst = max(worst, err)
+                assert err <= TOL, (c, k, err)
+                assert np.abs(g["center"][:nf] - gold["center"][a + k][:nf]).max() <= TOL, (c, k)
+                assert np.allclose(g["cr_left"][:nf], gold["cr_left"][a + k][:nf], rtol=1e-4, atol=1e-4), (c, k)
+                assert np.allclose(g["cr_right"][:nf], gold["cr_right"][a + k][:nf], rtol=1e-4, atol=1e-4), (c, k)
+                assert np.allclose(g["edge_length"][:nf], gold["edge_length"][a + k][:nf], rtol=1e-5, atol=TOL), (c, k)
+                checked += 1
+    return checked, worst
+
+
+def test_config1_testbmp_every_stage_and_pose(detector, test_gray, marker_path):
+    from cylindertag_b200 import CylinderTag
+    gold = np.load(os.path.join(GOLDEN, "ref_testbmp.npz"))
+    checked, worst = check_against_golden(detector, test_gray[None], gold, ctx="test.bmp")
+    assert checked == 5 and worst <= TOL
+    # the binary image itself, not only its checksum
+    want = np.unpackbits(gold["labels_packed"])[:600 * 960].reshape(600, 960) * 255
+    assert np.array_equal(detector.debug_binary(0), want)
+    # without refinement (cornerSubPix = false): the features are the lifted half-resolution quads
+    detector.detect_batch(test_gray[None], 5, False, 3)
+    assert np.abs(detector.debug_features(0)[0] - gold["feats_unrefined"]).max() <= TOL
+    # main.cpp:39-40: detect -> estimatePose on the mirror class; poses of the compiled pose_estimation.cpp
+    tag = CylinderTag(marker_path)
+    models = tag.loadModel(os.path.join(DATA, "CTag_2f12c.model"))
+    cam = tag.loadCamera(os.path.join(DATA, "cameraParams.yml"))
+    markers = []
+    tag.detect(test_gray, markers, 5, True, 5)
+    poses = tag.estimatePose(test_gray, markers, models, cam, False)
+    assert [p.markerID for p in poses] == list(gold["pose_model_index"])
+    for p, r, t in zip(poses, gold["pose_rvec"], gold["pose_tvec"]):
+        assert np.abs(p.rvec - r).max() <= 1e-4 and np.abs(p.tvec - t).max() <= 1e-4 * np.linalg.norm(t)
+
+
+def test_config2_sequence_all_120_frames(detector, test_gray):
+    gold = np.load(os.path.join(GOLDEN, "ref_sequence.npz"))
+    seq = synth.video_sequence(test_gray, 120, 2024)
+    checked, worst = check_against_golden(detector, seq, gold, sub=12, ctx="sequence")
+    assert checked == int(gold["marker_start"][-1]) >= 4 * 120 and worst <= TOL
+
+
+def test_config3_all_256_frames_1080p_bgr(detector):
+    gold = np.load(os.path.join(GOLDEN, "ref_config3.npz"))
+    checked = 0
+    worst = 0.0
+    for first in range(0, configs.CONFIG3_FRAMES, 64):
+        frames = np.stack(configs.render_many([(3, None, i) for i in range(first, first + 64)]))
+        c, w = check_against_golden(detector, frames, gold, first=first, sub=16, ctx="config 3")
+        checked += c
+        worst = max(worst, w)
+    assert checked == int(gold["marker_start"][-1]) and checked >= 0.9 * configs.CONFIG3_FRAMES and worst <= TOL
+
+
+def test_config3_as_one_256_frame_batch(detector):
+    """The same 256 frames as ONE host batch (chunked pipeline): results only (the stage dumps cover one chunk)."""
+    gold = np.load(os.path.join(GOLDEN, "ref_config3.npz"))
+    frames = np.stack(configs.render_many([(3, None, i) for i in range(configs.CONFIG3_FRAMES)]))
+    markers, counts, info = detector.detect_batch(frames, 5, True, 5, cap_per_frame=8)
+    for f in range(configs.CONFIG3_FRAMES):
+        assert [int(info[k][f]) for k in INFO_KEYS] == list(gold["counts"][f]), f
+        a, b = int(gold["marker_start"][f]), int(gold["marker_start"][f + 1])
+        assert int(counts[f]) == b - a
+        for k in range(b - a):
+            nf = int(gold["n_features"][a + k])
+            assert int(markers[f][k]["marker_id"]) == int(gold["marker_id"][a + k]) and int(markers[f][k]["frame"]) == f
+            assert np.abs(markers[f][k]["corners"][:nf] - gold["corners"][a + k][:nf]).max() <= TOL
+
+
+@pytest.mark.parametrize("name", list(configs.CODEBOOKS))
+def test_config4_4k_bgr_4_to_8_markers(name):
+    gold = np.load(os.path.join(GOLDEN, f"ref_config4_{name}.npz"))
+    state, fs = configs.codebook(name)
+    assert np.array_equal(state, gold["dictionary"]) and fs == int(gold["feature_size"])
+    det = Detector(state=state, feature_size=fs)
+    frames = np.stack(configs.render_many([(4, name, i) for i in range(configs.CONFIG4_FRAMES)]))
+    checked, worst = check_against_golden(det, frames, gold, sub=4, ctx=f"config 4 {name}")
+    det.close()
+    assert checked == int(gold["marker_start"][-1]) >= 2 * configs.CONFIG4_FRAMES and worst <= TOL

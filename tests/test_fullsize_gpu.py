@@ -1,12 +1,13 @@
-"""BASELINE.json's full size (4K BGR frames, six markers each): the CUDA path against the C++ oracle port
-(oracle/cpu_ref, itself pinned to the cv2 oracle in tests/test_cpu_ref.py) on every frame of a multi-chunk batch, plus
-size-independent properties: a frame's result does not depend on its position in the batch or on the batch around it."""
+"""BASELINE.json's full size (4K BGR frames, six markers each): the CUDA path against the reference's own code
+(oracle/_ref: corner_detector.cpp + CylinderTag.cpp compiled unmodified, run here on the host cores through
+ref_detect_batch_mt) on every frame of a multi-chunk batch, plus size-independent properties: a frame's result does not
+depend on its position in the batch or on the batch around it."""
 import numpy as np
 import pytest
 
 from cylindertag_b200 import synth
 from oracle import ctag_oracle as o
-from oracle.cpu_ref import api as cpu
+from oracle import ref_api as cpu
 
 pytestmark = pytest.mark.gpu
 
@@ -17,7 +18,7 @@ def frames_4k(marker_path):
     return state, fs, np.stack([synth.synthetic_frame(2100 + i, 3840, 2160, state, 6, channels=3)[0] for i in range(8)])
 
 
-def test_4k_bgr_batch_matches_cpu_port(detector, frames_4k):
+def test_4k_bgr_batch_matches_compiled_reference(detector, frames_4k):
     state, fs, frames = frames_4k
     batch = np.concatenate([frames, frames[::-1]])  # 16 frames: chunked over all workspaces, each frame twice
     markers, counts, info = detector.detect_batch(batch, 5, True, 5, cap_per_frame=32)

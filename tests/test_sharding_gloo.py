@@ -91,7 +91,7 @@ def _seq_worker(rank, world, port, n_frames, q):
     from cylindertag_b200 import synth
     from cylindertag_b200.sharding import frame_shard, gather_detections
     from oracle import ctag_oracle as o
-    from oracle.cpu_ref import api as cpu
+    from oracle import ref_api as cpu
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)

@@ -4,10 +4,11 @@ by seeded homographies / blur / noise (cylindertag_b200.synth.video_sequence, de
 DESIGN.md.  The caller loop is main.cpp:48-60: per frame detect(gray, 5, true, 5) -> estimatePose, outputs cleared
 between frames.
 
-CPU part: the generator is deterministic; the C++ oracle port agrees with the cv2 oracle on sequence frames (live on
-three frames, against the frozen oracle results of tests/golden/sequence_detect.npz on all 120).
-GPU part: every frame of the sequence against the frozen oracle results and against the C++ port, a subset stage by
-stage against the live cv2 oracle, poses against the pose oracle."""
+CPU part: the generator is deterministic; the compiled reference (oracle/_ref) agrees with the cv2 oracle on sequence
+frames (live on three frames, against the frozen oracle results of tests/golden/sequence_detect.npz on all 120).
+GPU part: every frame of the sequence against the frozen results (tests/golden/ref_sequence.npz, made by the compiled
+reference, and sequence_detect.npz, made by the cv2 oracle) and against the compiled reference run live, a subset stage
+by stage against the live cv2 oracle, poses against the pose oracle."""
 import os
 
 import numpy as np
@@ -16,7 +17,7 @@ import pytest
 from cylindertag_b200 import synth
 from oracle import ctag_oracle as o
 from oracle import pose_oracle as po
-from oracle.cpu_ref import api as cpu
+from oracle import ref_api as cpu
 from tests.parity import assert_frame_matches, assert_markers_match
 
 DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "data")
@@ -58,12 +59,12 @@ def _assert_matches_golden(gold, counts6, n_markers, markers, tol, ctx):
     return total
 
 
-def test_cpu_port_matches_golden_on_all_frames(test_gray, dictionary, golden_sequence):
-    """Every frame of the sequence: the C++ port against the frozen cv2-oracle results."""
+def test_compiled_reference_matches_oracle_golden_on_all_frames(test_gray, dictionary, golden_sequence):
+    """Every frame of the sequence: the reference's own code against the frozen cv2-oracle results."""
     state, fs = dictionary
     seq = synth.video_sequence(test_gray, N_FRAMES, SEED)
     counts, markers = cpu.detect_batch(seq, state, fs, True, 5, threads=os.cpu_count() or 1, cap=32)
-    total = _assert_matches_golden(golden_sequence, counts[:, :6], counts[:, 5], markers, 1e-6, "cpu_ref")
+    total = _assert_matches_golden(golden_sequence, counts[:, :6], counts[:, 5], markers, 1e-6, "oracle/_ref")
     assert total == int(golden_sequence["marker_start"][-1]) >= 4 * N_FRAMES
 
 
@@ -77,7 +78,7 @@ def test_sequence_is_deterministic_and_sliceable(test_gray):
     assert [int(f.astype(np.uint64).sum() % 1000003) for f in a] == GOLDEN_SUMS
 
 
-def test_cpu_port_matches_oracle_on_sequence_frames(test_gray, dictionary):
+def test_compiled_reference_matches_oracle_on_sequence_frames(test_gray, dictionary):
     state, fs = dictionary
     frames = synth.video_sequence(test_gray, N_FRAMES, SEED, first=0, count=3)
     counts, markers = cpu.detect_batch(frames, state, fs, True, 5, threads=3)
@@ -89,7 +90,7 @@ def test_cpu_port_matches_oracle_on_sequence_frames(test_gray, dictionary):
 
 
 @pytest.mark.gpu
-def test_full_sequence_matches_cpu_port(detector, test_gray, dictionary):
+def test_full_sequence_matches_compiled_reference(detector, test_gray, dictionary):
     state, fs = dictionary
     seq = synth.video_sequence(test_gray, N_FRAMES, SEED)
     markers, counts, info = detector.detect_batch(seq, 5, True, 5, cap_per_frame=32)
