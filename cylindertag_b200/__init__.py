@@ -6,8 +6,8 @@ needs the built library and a B200.
 """
 from . import _capi
 from ._capi import CtagError
-from .detector import Detector
+from .detector import Detector, detect_batch_multi
 from .api import CamInfo, CylinderTag, MarkerInfo, ModelInfo, PoseInfo
 
-__all__ = ["CylinderTag", "Detector", "MarkerInfo", "ModelInfo", "CamInfo", "PoseInfo", "CtagError", "_capi"]
+__all__ = ["CylinderTag", "Detector", "detect_batch_multi", "MarkerInfo", "ModelInfo", "CamInfo", "PoseInfo", "CtagError", "_capi"]
 __version__ = "0.1"

@@ -62,6 +62,8 @@ SIGNATURES = {
     "ctag_create": (_I, [ctypes.POINTER(_P), _P, _I, _I, _I, _I]),
     "ctag_create_from_file": (_I, [ctypes.POINTER(_P), ctypes.c_char_p, _I]),
     "ctag_destroy": (None, [_P]),
+    "ctag_set_option": (_I, [_P, ctypes.c_char_p, _I]),
+    "ctag_detect_batch_multi": (_I, [_P, _I, _P, _I, _I, _I, ctypes.c_size_t, ctypes.c_size_t, _I, _I, _I, _I, _P, _I, _P, _P]),
     "ctag_get_dictionary": (_I, [_P, ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_I), _P, _I]),
     "ctag_detect": (_I, [_P, _P, _I, _I, _SZ, _I, _I, _I, _P, _I, ctypes.POINTER(_I), ctypes.POINTER(_I)]),
     "ctag_detect_batch": (_I, [_P, _P, _I, _I, _I, _SZ, _SZ, _I, _I, _I, _I, _I, _P, _I, _P, _P]),

@@ -152,8 +152,7 @@ class CylinderTag:
         h, w = gray.shape
         out = np.empty((h, w, 3), np.uint8)
         rc = lib.ctag_gray_to_3ch(gray.ctypes.data, w, h, gray.strides[0], out.ctypes.data, out.strides[0])
-        if rc != C.OK:
-            raise RuntimeError("drawAxis, " + C.strerror(rc))
+        C.check(rc, "drawAxis")
         K = np.ascontiguousarray(camera.Intrinsic, np.float32).reshape(9)
         D = np.ascontiguousarray(camera.distCoeffs, np.float32).reshape(-1)
         for i, pose in enumerate(poses):
@@ -169,8 +168,7 @@ class CylinderTag:
             rc = lib.ctag_draw_axis(out.ctypes.data, w, h, out.strides[0], rec.ctypes.data, corners3.ctypes.data,
                                     corners3.shape[0], base.ctypes.data, axis.ctypes.data, K.ctypes.data, D.ctypes.data,
                                     int(D.size), rvec.ctypes.data, tvec.ctypes.data, int(axisLength))
-            if rc != C.OK:
-                raise RuntimeError("drawAxis, " + C.strerror(rc))
+            C.check(rc, "drawAxis")
         return out
 
 

@@ -11,6 +11,7 @@
 
 #include <fstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -112,7 +113,24 @@ struct ctag_detector {
   int last = -1;  // slot of the most recently collected batch (debug getters, stage times)
   float stage_ms[CTAG_STAGE_COUNT] = {0, 0, 0, 0, 0};
   int last_launches = 0;
+  int debug_fail_chunk = -1;  // fault injection for the tests: fail the host pipeline when this chunk index is reached
+  int chunk_frames = 0;  // frames per chunk of a host batch; 0 = automatic (CTAG_CHUNK at creation, ctag_set_option later)
 };
+
+// Brings the slot queue back to "nothing in flight" after a failure in the middle of a pipelined call: waits for
+// whatever was queued on the slot streams (the staging buffers they read stay alive), then resets the ring.  Without
+// this a transient error (out of memory while growing a staging buffer, a failed copy) would leave in_flight > 0 and
+// every later call on the handle would be refused.
+static void drain_slots(ctag_detector* d) {
+  for (int i = 0; i < kMaxSlots; ++i) {
+    Slot& s = d->slot[i];
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    s.busy = false;
+  }
+  cudaGetLastError();  // clear a non-sticky error so that the next call starts clean
+  d->next_enqueue = d->next_collect = 0;
+  d->in_flight = 0;
+}
 
 static int select_device(int cuda_device, int* chosen, int* sms) {
   int count = 0;
@@ -351,6 +369,79 @@ static int check_args(ctag_detector* d, const void* frames, int n, int w, int h,
   return CTAG_OK;
 }
 
+// Host frames: cut the batch into chunks and rotate the slots, so that the H2D copy of chunk c+1 (its own stream)
+// overlaps the kernels of chunk c.  The 2-D copy normalises any host pitch to a 16-byte multiple (TMA).
+static int detect_batch_host(ctag_detector* d, const void* frames, int n, int w, int h, size_t pitch, size_t frame_stride,
+                             int channels, int adaptive_thresh, int corner_subpix, int subpix_dist, ctag_marker* out,
+                             int cap_per_frame, int* n_out, ctag_frame_info* info) {
+  int rc = CTAG_OK;
+  const size_t dpitch = (size_t)round_up(w * channels, 16);
+  const size_t dfs = dpitch * h;
+  // Small batches stay whole (the debug getters then see all frames).  Larger ones go in chunks of about 192 MiB (8 4K
+  // BGR frames), at most a quarter of the batch: what cannot be hidden behind the copies is the processing of the LAST
+  // chunk, and the sparse stages' latency barely shrinks with the chunk, so small chunks end sooner (64 4K BGR frames:
+  // 30.7 ms with 16-frame chunks, 30.0 ms with 8; the bare copy takes 28.6 ms).  ctag_set_option("chunk_frames") overrides.
+  int chunk = n;
+  if (n >= 8) {
+    const size_t target = (size_t)192 << 20;
+    chunk = (int)((target + dfs - 1) / dfs);
+    if (chunk > (n + 3) / 4) chunk = (n + 3) / 4;
+    if (chunk < 1) chunk = 1;
+  }
+  if (d->chunk_frames > 0) chunk = d->chunk_frames < n ? d->chunk_frames : n;
+  int done = 0, queued = 0;
+  int q_first[kMaxSlots], q_count[kMaxSlots];
+  while (done < n) {
+    // at most three chunks in flight: copies queued on more streams share the copy engine and every chunk arrives later
+    // (64 4K BGR frames: 29.8 ms with 3 or 4, 31.2 ms with 6)
+    while (queued < n && d->in_flight < (kSlots < 3 ? kSlots : 3)) {
+      const int c = n - queued < chunk ? n - queued : chunk;
+      Slot* s = &d->slot[d->next_enqueue];
+      if (d->debug_fail_chunk >= 0 && queued / chunk == d->debug_fail_chunk) {
+        d->debug_fail_chunk = -1;  // one shot
+        set_last_error_text("injected failure (debug_fail_chunk)");
+        return CTAG_ERR_CUDA;
+      }
+      rc = ensure_stage(s, dfs * c);
+      if (rc != CTAG_OK) return rc;
+      if (pitch == dpitch && frame_stride == dfs) {
+        // densely packed frames with a TMA-compatible pitch: one linear copy for the whole chunk
+        CTAG_CUDA_CHECK(cudaMemcpyAsync(s->d_stage, static_cast<const uint8_t*>(frames) + frame_stride * queued, dfs * c,
+                                        cudaMemcpyHostToDevice, s->stream));
+      } else {
+        // one 2-D copy per frame normalises the pitch and keeps frame_stride != pitch*h inputs correct
+        for (int f = 0; f < c; ++f)
+          CTAG_CUDA_CHECK(cudaMemcpy2DAsync(s->d_stage + dfs * f, dpitch,
+                                            static_cast<const uint8_t*>(frames) + frame_stride * (queued + f), pitch,
+                                            (size_t)w * channels, h, cudaMemcpyHostToDevice, s->stream));
+      }
+      rc = enqueue_on_slot(d, s, s->d_stage, c, w, h, dpitch, dfs, channels, adaptive_thresh, corner_subpix, subpix_dist);
+      if (rc != CTAG_OK) return rc;
+      q_first[d->next_enqueue] = queued;
+      q_count[d->next_enqueue] = c;
+      d->next_enqueue = (d->next_enqueue + 1) % kSlots;
+      d->in_flight += 1;
+      queued += c;
+    }
+    const int si = d->next_collect;
+    Slot* s = &d->slot[si];
+    const int first = q_first[si], c = q_count[si];
+    d->last = si;
+    d->next_collect = (d->next_collect + 1) % kSlots;
+    d->in_flight -= 1;
+    rc = collect_slot(d, s, out ? out + (size_t)first * cap_per_frame : nullptr, cap_per_frame, n_out ? n_out + first : nullptr,
+                      info ? info + first : nullptr);
+    if (rc != CTAG_OK) return rc;
+    if (out)
+      for (int f = 0; f < c; ++f) {
+        const int nm = s->h_summary[12 * f + 10];  // markers stored for the frame (n_out may be NULL)
+        for (int k = 0; k < nm && k < cap_per_frame; ++k) out[(size_t)(first + f) * cap_per_frame + k].frame = first + f;
+      }
+    done += c;
+  }
+  return CTAG_OK;
+}
+
 extern "C" {
 
 int ctag_create(ctag_detector** out, const int32_t* state, int rows, int cols, int feature_size, int cuda_device) {
@@ -369,6 +460,7 @@ int ctag_create(ctag_detector** out, const int32_t* state, int rows, int cols, i
   d->rows = rows;
   d->cols = cols;
   d->feature_size = feature_size;
+  if (const char* e = getenv("CTAG_CHUNK")) d->chunk_frames = atoi(e) > 0 ? atoi(e) : 0;  // read once, at creation
   // initial subsets of cv::fitLine's 20 restarts for every point count up to kPickTableMax (fit_core.cuh)
   std::vector<uint16_t> table((size_t)kPickTableMax * 200);
   quad_build_pick_table(table.data(), kPickTableMax);
@@ -418,6 +510,21 @@ void ctag_destroy(ctag_detector* d) {
   cudaFree(d->d_state);
   cudaFree(d->d_pick_table);
   delete d;
+}
+
+int ctag_set_option(ctag_detector* d, const char* key, int value) {
+  if (!d || !key) return CTAG_ERR_ARG;
+  if (d->in_flight != 0) return CTAG_ERR_ARG;
+  if (!strcmp(key, "chunk_frames")) {
+    if (value < 0) return CTAG_ERR_ARG;
+    d->chunk_frames = value;
+    return CTAG_OK;
+  }
+  if (!strcmp(key, "debug_fail_chunk")) {
+    d->debug_fail_chunk = value;
+    return CTAG_OK;
+  }
+  return CTAG_ERR_ARG;
 }
 
 int ctag_get_dictionary(const ctag_detector* d, int* rows, int* cols, int* feature_size, int32_t* state_out, int cap) {
@@ -471,72 +578,40 @@ int ctag_detect_batch(ctag_detector* d, const void* frames, int n, int w, int h,
     if (rc != CTAG_OK) return rc;
     return ctag_detect_batch_collect(d, out, cap_per_frame, n_out, info);
   }
-  // Host frames: cut the batch into chunks and alternate the two slots, so that the H2D copy of chunk c+1 (its own
-  // stream) overlaps the kernels of chunk c.  The 2-D copy normalises any host pitch to a 16-byte multiple (TMA).
   CTAG_CUDA_CHECK(cudaSetDevice(d->device));
   if (pitch < (size_t)w * channels) return CTAG_ERR_ARG;
-  const size_t dpitch = (size_t)round_up(w * channels, 16);
-  const size_t dfs = dpitch * h;
-  // Small batches stay whole (the debug getters then see all frames).  Larger ones go in chunks of about 192 MiB (8 4K
-  // BGR frames), at most a quarter of the batch: what cannot be hidden behind the copies is the processing of the LAST
-  // chunk, and the sparse stages' latency barely shrinks with the chunk, so small chunks end sooner (64 4K BGR frames:
-  // 30.7 ms with 16-frame chunks, 30.0 ms with 8; the bare copy takes 28.6 ms).  CTAG_CHUNK overrides.
-  int chunk = n;
-  if (n >= 8) {
-    const size_t target = (size_t)192 << 20;
-    chunk = (int)((target + dfs - 1) / dfs);
-    if (chunk > (n + 3) / 4) chunk = (n + 3) / 4;
-    if (chunk < 1) chunk = 1;
+  rc = detect_batch_host(d, frames, n, w, h, pitch, frame_stride, channels, adaptive_thresh, corner_subpix, subpix_dist, out,
+                         cap_per_frame, n_out, info);
+  if (rc != CTAG_OK) drain_slots(d);  // the handle stays usable after a failed call
+  return rc;
+}
+
+int ctag_detect_batch_multi(ctag_detector* const* dets, int n_det, const void* frames, int n, int w, int h, size_t pitch,
+                            size_t frame_stride, int channels, int adaptive_thresh, int corner_subpix, int subpix_dist,
+                            ctag_marker* out, int cap_per_frame, int* n_out, ctag_frame_info* info) {
+  if (!dets || n_det <= 0 || !frames || n <= 0) return CTAG_ERR_ARG;
+  for (int g = 0; g < n_det; ++g)
+    if (!dets[g]) return CTAG_ERR_ARG;
+  if (frame_stride == 0) frame_stride = pitch * (size_t)h;
+  std::vector<int> rcs(n_det, CTAG_OK);
+  std::vector<std::thread> threads;
+  // contiguous blocks, frame f -> detector floor(f * n_det / n) (video locality); one host thread per detector
+  for (int g = 0; g < n_det; ++g) {
+    const int first = (int)((long long)n * g / n_det), last = (int)((long long)n * (g + 1) / n_det);
+    if (last <= first) continue;
+    threads.emplace_back([=, &rcs]() {
+      rcs[g] = ctag_detect_batch(dets[g], static_cast<const uint8_t*>(frames) + frame_stride * first, last - first, w, h, pitch,
+                                 frame_stride, channels, 0, adaptive_thresh, corner_subpix, subpix_dist,
+                                 out ? out + (size_t)first * cap_per_frame : nullptr, cap_per_frame, n_out ? n_out + first : nullptr,
+                                 info ? info + first : nullptr);
+      if (rcs[g] == CTAG_OK && out && n_out)
+        for (int f = first; f < last; ++f)
+          for (int k = 0; k < n_out[f] && k < cap_per_frame; ++k) out[(size_t)f * cap_per_frame + k].frame = f;
+    });
   }
-  if (const char* e = getenv("CTAG_CHUNK")) {
-    const int v = atoi(e);
-    if (v > 0) chunk = v < n ? v : n;
-  }
-  int done = 0, queued = 0;
-  int q_first[kMaxSlots], q_count[kMaxSlots];
-  while (done < n) {
-    // at most three chunks in flight: copies queued on more streams share the copy engine and every chunk arrives later
-    // (64 4K BGR frames: 29.8 ms with 3 or 4, 31.2 ms with 6)
-    while (queued < n && d->in_flight < (kSlots < 3 ? kSlots : 3)) {
-      const int c = n - queued < chunk ? n - queued : chunk;
-      Slot* s = &d->slot[d->next_enqueue];
-      rc = ensure_stage(s, dfs * c);
-      if (rc != CTAG_OK) return rc;
-      if (pitch == dpitch && frame_stride == dfs) {
-        // densely packed frames with a TMA-compatible pitch: one linear copy for the whole chunk
-        CTAG_CUDA_CHECK(cudaMemcpyAsync(s->d_stage, static_cast<const uint8_t*>(frames) + frame_stride * queued, dfs * c,
-                                        cudaMemcpyHostToDevice, s->stream));
-      } else {
-        // one 2-D copy per frame normalises the pitch and keeps frame_stride != pitch*h inputs correct
-        for (int f = 0; f < c; ++f)
-          CTAG_CUDA_CHECK(cudaMemcpy2DAsync(s->d_stage + dfs * f, dpitch,
-                                            static_cast<const uint8_t*>(frames) + frame_stride * (queued + f), pitch,
-                                            (size_t)w * channels, h, cudaMemcpyHostToDevice, s->stream));
-      }
-      rc = enqueue_on_slot(d, s, s->d_stage, c, w, h, dpitch, dfs, channels, adaptive_thresh, corner_subpix, subpix_dist);
-      if (rc != CTAG_OK) return rc;
-      q_first[d->next_enqueue] = queued;
-      q_count[d->next_enqueue] = c;
-      d->next_enqueue = (d->next_enqueue + 1) % kSlots;
-      d->in_flight += 1;
-      queued += c;
-    }
-    const int si = d->next_collect;
-    Slot* s = &d->slot[si];
-    const int first = q_first[si], c = q_count[si];
-    d->last = si;
-    d->next_collect = (d->next_collect + 1) % kSlots;
-    d->in_flight -= 1;
-    rc = collect_slot(d, s, out ? out + (size_t)first * cap_per_frame : nullptr, cap_per_frame, n_out ? n_out + first : nullptr,
-                      info ? info + first : nullptr);
-    if (rc != CTAG_OK) return rc;
-    if (out)
-      for (int f = 0; f < c; ++f) {
-        const int nm = n_out ? n_out[first + f] : 0;
-        for (int k = 0; k < nm && k < cap_per_frame; ++k) out[(size_t)(first + f) * cap_per_frame + k].frame = first + f;
-      }
-    done += c;
-  }
+  for (auto& t : threads) t.join();
+  for (int g = 0; g < n_det; ++g)
+    if (rcs[g] != CTAG_OK) return rcs[g];
   return CTAG_OK;
 }
 

@@ -733,7 +733,8 @@ int launch_front(const void* frames_dev, int n, const FrameGeom& geo, int channe
     set_last_error_text("cuTensorMapEncodeTiled failed");
     return CTAG_ERR_CUDA;
   }
-  if (!getenv("CTAG_FRONT_NOSLIDE")) {
+  static const bool noslide = getenv("CTAG_FRONT_NOSLIDE") != nullptr;  // A/B switch, read once per process
+  if (!noslide) {
     CUtensorMap tmap_main, tmap_top;
     cuuint32_t box_main[3] = {(cuuint32_t)RW, (cuuint32_t)SROWS, 1}, box_top[3] = {(cuuint32_t)RW, (cuuint32_t)OVR, 1};
     if (enc(&tmap_main, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(frames_dev), dims, strides, box_main, estr,

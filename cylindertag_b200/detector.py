@@ -50,6 +50,10 @@ class Detector:
         C.check(self._lib.ctag_get_dictionary(self._h, None, None, None, _ptr(out), out.size), "ctag_get_dictionary")
         return out
 
+    def set_option(self, key, value):
+        """ctag_set_option: "chunk_frames" (frames per chunk of a host batch, 0 = automatic), "debug_fail_chunk"."""
+        C.check(self._lib.ctag_set_option(self._h, key.encode(), int(value)), "ctag_set_option")
+
     # ---- detection ------------------------------------------------------------------------------------------
     def detect_batch(self, frames, adaptive_thresh=5, corner_subpix=False, subpix_dist=3, cap_per_frame=16):
         """frames: host uint8 array [n,h,w] (gray) or [n,h,w,3] (BGR).  Returns (markers, counts, info) numpy
@@ -157,3 +161,25 @@ class Detector:
         C.check(self._lib.ctag_debug_get_features(self._h, frame, _ptr(cor), _ptr(cen), _ptr(ang), _ptr(qp), cap, ctypes.byref(n)), "ctag_debug_get_features")
         k = n.value
         return cor[:k], cen[:k], ang[:k], qp[:k]
+
+
+def detect_batch_multi(detectors, frames, adaptive_thresh=5, corner_subpix=False, subpix_dist=3, cap_per_frame=16):
+    """ctag_detect_batch_multi: one host batch sharded over several detectors (one per GPU, contiguous frame blocks, one
+    host thread each inside the library).  Returns (markers, counts, info) indexed by the global frame number."""
+    fr = np.ascontiguousarray(frames, dtype=np.uint8)
+    if fr.ndim == 3:
+        n, h, w = fr.shape
+        ch = 1
+    elif fr.ndim == 4 and fr.shape[3] == 3:
+        n, h, w, ch = fr.shape
+    else:
+        raise ValueError("frames must be [n,h,w] or [n,h,w,3] uint8")
+    lib = C.load()
+    handles = (ctypes.c_void_p * len(detectors))(*[d._h for d in detectors])
+    out = np.zeros((n, cap_per_frame), C.MARKER_DTYPE)
+    cnt = np.zeros(n, np.int32)
+    info = np.zeros(n, C.INFO_DTYPE)
+    C.check(lib.ctag_detect_batch_multi(handles, len(detectors), _ptr(fr), n, w, h, w * ch, 0, ch, int(adaptive_thresh),
+                                        int(bool(corner_subpix)), int(subpix_dist), _ptr(out), cap_per_frame, _ptr(cnt), _ptr(info)),
+            "ctag_detect_batch_multi")
+    return out, cnt, info

@@ -102,6 +102,13 @@ CTAG_API int ctag_create_from_file(ctag_detector** out, const char* marker_path,
 
 CTAG_API void ctag_destroy(ctag_detector* det);
 
+/* Tuning knobs of one detector (the defaults are the measured best; environment variables of the same meaning are
+ * read ONCE, when the detector is created).  Keys: "chunk_frames" -- frames per chunk of a host batch in
+ * ctag_detect_batch(is_device=0), 0 = automatic (about 192 MiB of frames, at most a quarter of the batch).
+ * "debug_fail_chunk" -- fault injection for the tests: the next host batch fails with CTAG_ERR_CUDA when it reaches
+ * that chunk index (one shot; -1 = off).  Not allowed while batches are pending.  Unknown key: CTAG_ERR_ARG. */
+CTAG_API int ctag_set_option(ctag_detector* det, const char* key, int value);
+
 /* Dictionary accessors (state matrix the detector holds, header/CylinderTag.h:44-45). */
 CTAG_API int ctag_get_dictionary(const ctag_detector* det, int* rows, int* cols, int* feature_size, int32_t* state_out, int cap);
 
@@ -120,10 +127,26 @@ CTAG_API int ctag_detect(ctag_detector* det, const uint8_t* gray, int w, int h, 
  * pitch       : bytes between rows; frame_stride: bytes between frames (0 -> pitch*h)
  * out         : host array of n*cap_per_frame markers, frame f's markers start at out[f*cap_per_frame]
  * n_out       : host array of n counts; info (optional): host array of n ctag_frame_info
- * Device inputs must be 16-byte aligned with pitch % 16 == 0 (TMA requirement). */
+ * Device inputs must be 16-byte aligned with pitch % 16 == 0 (TMA requirement).
+ * w and h must be even: the reference's resize (CylinderTag.cpp:79) is an exact 2x bicubic decimation only then; for odd
+ * sizes cv::resize's own output depends on the library's CPU dispatch (tests/test_ref_pinning.py), so there is no single
+ * reference answer to be bit-exact with -- such frames are refused with CTAG_ERR_ARG.
+ * A call that fails half way (out of memory, a failed copy) leaves the detector usable: pending work is drained and the
+ * next call starts clean.  out, n_out and info may each be NULL. */
 CTAG_API int ctag_detect_batch(ctag_detector* det, const void* frames, int n, int w, int h, size_t pitch, size_t frame_stride,
                       int channels, int is_device, int adaptive_thresh, int corner_subpix, int subpix_dist,
                       ctag_marker* out, int cap_per_frame, int* n_out, ctag_frame_info* info);
+
+/* The same call sharded over several detectors -- one per CUDA device, created with ctag_create(..., cuda_device = g) --
+ * for the video loop of main.cpp:52-60 on a multi-GPU box.  Frames are independent (detect() clears its
+ * state per call, CylinderTag.cpp:73-76), so the batch is cut into contiguous blocks, frame f -> detector
+ * floor(f * n_det / n); each block runs ctag_detect_batch(is_device = 0) on its own host thread and there is no exchange
+ * between devices.  `frames` is a HOST pointer; out / n_out / info are indexed by the global frame number and
+ * ctag_marker::frame is the global index, i.e. the result equals the single-detector call on the whole batch.
+ * n_out is required when out is given.  Returns the first non-OK block status. */
+CTAG_API int ctag_detect_batch_multi(ctag_detector* const* dets, int n_det, const void* frames, int n, int w, int h,
+                                     size_t pitch, size_t frame_stride, int channels, int adaptive_thresh, int corner_subpix,
+                                     int subpix_dist, ctag_marker* out, int cap_per_frame, int* n_out, ctag_frame_info* info);
 
 /* Asynchronous pair for device-resident throughput runs: enqueue the whole detect path for a batch, then collect.
  * Up to ctag_max_in_flight() batches may be enqueued before the first collect (each has its own workspace and CUDA

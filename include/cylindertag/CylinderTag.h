@@ -236,6 +236,8 @@ class CylinderTag {
   // Marker Detector (CylinderTag.cpp:67-128). `img` is 8-bit single channel.
   void detect(const ImageView& img, std::vector<MarkerInfo>& cornerList, int adaptiveThresh = 5, const bool cornerSubPix = false,
               int cornerSubPixDist = 3) {
+    // the reference's cvtColor(img, imgMark, COLOR_GRAY2RGB) (CylinderTag.cpp:70) asserts on anything but one channel
+    if (img.channels != 1) throw std::string("detect, the image must be 8-bit single-channel (convert BGR frames first, main.cpp:54, or use detectBatch with channels = 3)\n");
     std::vector<ctag_marker> buf(kCap);
     int n = 0, status = 0;
     int rc = ctag_detect(det_, img.data, img.cols, img.rows, img.step, adaptiveThresh, cornerSubPix ? 1 : 0, cornerSubPixDist,

@@ -3,6 +3,7 @@
 // Stands in for cv::imread at main.cpp:29 for the formats the reference's sample data uses (test.bmp).
 // With CTAG_WITH_ZLIB defined (link -lz) it also reads non-interlaced 8-bit PNG (gray, gray+alpha, RGB, RGBA, palette).
 #pragma once
+#include <climits>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -128,21 +129,26 @@ inline Image imread(const std::string& path) {
   if (buf.size() >= 8 && buf[0] == 0x89 && buf[1] == 'P' && buf[2] == 'N' && buf[3] == 'G') return read_png(buf);
 #endif
   if (buf.size() >= 54 && buf[0] == 'B' && buf[1] == 'M') {
-    const uint32_t off = detail::rd32(&buf[10]), hdr = detail::rd32(&buf[14]);
-    if (hdr < 40) return img;
+    // every size below comes from the file: all arithmetic in 64 bits, every offset checked before it is used
+    const uint64_t off = detail::rd32(&buf[10]), hdr = detail::rd32(&buf[14]);
+    if (hdr < 40 || 14 + hdr > buf.size()) return img;
     const int32_t w = (int32_t)detail::rd32(&buf[18]), hs = (int32_t)detail::rd32(&buf[22]);
     const int bpp = detail::rd16(&buf[28]);
     const uint32_t comp = detail::rd32(&buf[30]);
-    if (w <= 0 || hs == 0 || (comp != 0 && !(comp == 3 && bpp == 32)) || (bpp != 8 && bpp != 24 && bpp != 32)) return img;
+    if (w <= 0 || w > 65535 || hs == 0 || hs == INT32_MIN || hs > 65535 || hs < -65535) return img;
+    if ((comp != 0 && !(comp == 3 && bpp == 32)) || (bpp != 8 && bpp != 24 && bpp != 32)) return img;
     const int h = hs < 0 ? -hs : hs;
-    const size_t stride = (((size_t)w * bpp + 31) / 32) * 4;
-    if (off + stride * h > buf.size()) return img;
+    const uint64_t stride = (((uint64_t)w * bpp + 31) / 32) * 4;
+    if (off < 14 + hdr || off > buf.size() || stride * (uint64_t)h > buf.size() - off) return img;
     const uint8_t* pal = &buf[14 + hdr];
+    uint8_t pal_full[256 * 4] = {0};  // indices beyond the stored palette read black instead of whatever follows in the file
     bool gray_palette = bpp == 8;
     if (bpp == 8) {
       uint32_t ncol = detail::rd32(&buf[46]);
       if (ncol == 0 || ncol > 256) ncol = 256;
-      if (14 + hdr + 4 * (size_t)ncol > buf.size()) return img;
+      if (14 + hdr + 4 * (uint64_t)ncol > buf.size()) return img;
+      std::memcpy(pal_full, pal, 4 * (size_t)ncol);
+      pal = pal_full;
       for (uint32_t c = 0; c < ncol && gray_palette; ++c) gray_palette = pal[4 * c] == pal[4 * c + 1] && pal[4 * c] == pal[4 * c + 2];
     }
     img.rows = h, img.cols = w, img.channels = (bpp == 8 && gray_palette) ? 1 : 3;

@@ -1,62 +1,3 @@
-"""The synthetic workloads of BASELINE.json configs 3-5 as SURVEY 8(d) writes them, in one place for the golden
-generator (tests/golden/make_golden_ref.py), the parity tests and bench.py.
-
-config 3: 256 frames 1920x1080 BGR, one 2f12c marker each, frame i from default_rng(1000 + i)
-config 4: 3840x2160 BGR, 4..8 markers per frame (4 + i % 5), seeds 2000 + i, three codebooks: 2f12c (shipped) and
-          15c3f / 18c4f generated with default_rng(7) (30 rows each; one detector holds one dictionary,
-          header/CylinderTag.h:44)
-config 5: the ring of 64 distinct config-4 2f12c frames (seeds 2000..2063)."""
-import functools
-import os
-
-import numpy as np
-
-from cylindertag_b200 import synth
-
-DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "data")
-CODEBOOKS = {"2f12c": None, "15c3f": (15, 3), "18c4f": (18, 4)}
-CONFIG3_FRAMES = 256
-CONFIG4_FRAMES = 8
-
-
-@functools.lru_cache(maxsize=None)
-def codebook(name):
-    """(state, feature_size) of a config-4 codebook."""
-    if name == "2f12c":
-        toks = open(os.path.join(DATA, "CTag_2f12c.marker")).read().split()
-        n, cols, fs = int(toks[0]), int(toks[1]), int(toks[2])
-        return np.array([int(t) for t in toks[3:3 + n * cols]], np.int32).reshape(n, cols), fs
-    cols, fs = CODEBOOKS[name]
-    return synth.generate_codebook(cols, fs, 30, seed=7), fs
-
-
-def config3_frame(i):
-    """Frame i of config 3 (BGR u8 1080x1920x3)."""
-    state, _ = codebook("2f12c")
-    return synth.synthetic_frame(1000 + i, 1920, 1080, state, 1, channels=3)[0]
-
-
-def config4_markers(i):
-    return 4 + i % 5
-
-
-def config4_frame(name, i, w=3840, h=2160):
-    """Frame i of the config-4 run with codebook `name`: (BGR frame, rendered dictionary rows)."""
-    state, _ = codebook(name)
-    frame, specs = synth.synthetic_frame(2000 + i, w, h, state, config4_markers(i), channels=3)
-    return frame, [row for row, _ in specs]
-
-
-def _job(args):
-    kind, name, i = args
-    return config3_frame(i) if kind == 3 else config4_frame(name, i)[0]
-
-
-def render_many(jobs, workers=None):
-    """jobs: [(3, None, i) | (4, codebook, i)] -> list of frames, rendered by a process pool (the renderer is numpy)."""
-    workers = workers or min(len(jobs), os.cpu_count() or 1)
-    if workers <= 1 or len(jobs) <= 1:
-        return [_job(j) for j in jobs]
-    import multiprocessing as mp
-    with mp.get_context("fork").Pool(workers) as pool:
-        return pool.map(_job, jobs, chunksize=1)
+"""The BASELINE.json workloads live in the package (cylindertag_b200/workloads.py); re-exported for the tests."""
+from cylindertag_b200.workloads import *  # noqa: F401,F403
+from cylindertag_b200.workloads import CODEBOOKS, CONFIG3_FRAMES, CONFIG4_FRAMES, CONFIG5_DISTINCT, codebook, config3_frame, config4_frame, config4_markers, config5_frame, render_many  # noqa: F401

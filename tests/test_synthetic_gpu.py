@@ -69,15 +69,69 @@ def test_large_host_batch_is_chunked(detector, marker_path):
     assert all(counts[i] == counts[i % 4] for i in range(18))
 
 
-def test_more_chunks_than_workspaces(detector, marker_path, monkeypatch):
+def test_more_chunks_than_workspaces(detector, marker_path):
     """A host batch cut into more chunks than there are workspaces (what a 64-frame 4K batch does): chunks queue up
     behind the in-flight ones and the results equal those of the default chunking, frame for frame."""
     state, fs = o.load_marker_file(marker_path)
     base = [synth.synthetic_frame(1000 + i, 1280, 720, state, 1)[0] for i in range(3)]
     frames = np.stack([base[i % 3] for i in range(19)])
     want_m, want_c, want_i = detector.detect_batch(frames, 5, True, 5, cap_per_frame=8)
-    monkeypatch.setenv("CTAG_CHUNK", "2")  # 10 chunks, the last one a single frame
-    got_m, got_c, got_i = detector.detect_batch(frames, 5, True, 5, cap_per_frame=8)
+    detector.set_option("chunk_frames", 2)  # 10 chunks, the last one a single frame
+    try:
+        got_m, got_c, got_i = detector.detect_batch(frames, 5, True, 5, cap_per_frame=8)
+    finally:
+        detector.set_option("chunk_frames", 0)
     assert np.array_equal(got_c, want_c) and got_c.sum() >= 19
     assert np.array_equal(got_i, want_i)
     assert np.array_equal(got_m.view(np.uint8), want_m.view(np.uint8))
+
+
+def test_failed_host_batch_leaves_the_detector_usable(detector, marker_path):
+    """A failure in the middle of the chunked host pipeline (injected: the third chunk) must not wedge the handle: pending
+    chunks are drained and the next call gives the same result as before."""
+    from cylindertag_b200 import CtagError
+    state, fs = o.load_marker_file(marker_path)
+    base = [synth.synthetic_frame(1000 + i, 1280, 720, state, 1)[0] for i in range(3)]
+    frames = np.stack([base[i % 3] for i in range(19)])
+    want_m, want_c, _ = detector.detect_batch(frames, 5, True, 5, cap_per_frame=8)
+    detector.set_option("chunk_frames", 2)
+    detector.set_option("debug_fail_chunk", 2)
+    try:
+        with pytest.raises(CtagError):
+            detector.detect_batch(frames, 5, True, 5, cap_per_frame=8)
+        got_m, got_c, _ = detector.detect_batch(frames, 5, True, 5, cap_per_frame=8)  # same handle, next call
+    finally:
+        detector.set_option("chunk_frames", 0)
+    assert np.array_equal(got_c, want_c) and np.array_equal(got_m.view(np.uint8), want_m.view(np.uint8))
+
+
+def test_batch_without_count_array_still_numbers_its_frames(detector, marker_path):
+    """n_out == NULL is allowed by ctag.h; the records of a chunked batch still carry the batch-global frame index."""
+    import ctypes
+    from cylindertag_b200 import _capi as C
+    state, fs = o.load_marker_file(marker_path)
+    base = [synth.synthetic_frame(1000 + i, 1280, 720, state, 1)[0] for i in range(3)]
+    frames = np.ascontiguousarray(np.stack([base[i % 3] for i in range(12)]))
+    out = np.zeros((12, 4), C.MARKER_DTYPE)
+    rc = C.load().ctag_detect_batch(detector._h, frames.ctypes.data_as(ctypes.c_void_p), 12, 1280, 720, 1280, 0, 1, 0, 5, 1, 5,
+                                    out.ctypes.data_as(ctypes.c_void_p), 4, None, None)
+    assert rc == 0
+    assert [int(out[f][0]["frame"]) for f in range(12)] == list(range(12)) and all(int(out[f][0]["n_features"]) >= 2 for f in range(12))
+
+
+def test_multi_detector_call_equals_single_detector(marker_path):
+    """ctag_detect_batch_multi (one detector per GPU, one host thread each) against the single call; with one
+    GPU in the box the detectors share the device, which exercises the same sharding / threading / index code."""
+    import torch
+    from cylindertag_b200 import detect_batch_multi
+    state, fs = o.load_marker_file(marker_path)
+    ngpu = max(1, torch.cuda.device_count())
+    dets = [Detector(state=state, feature_size=fs, device=g % ngpu) for g in range(max(2, min(ngpu, 4)))]
+    base = [synth.synthetic_frame(1000 + i, 1280, 720, state, 1)[0] for i in range(5)]
+    frames = np.stack([base[i % 5] for i in range(23)])
+    want_m, want_c, want_i = dets[0].detect_batch(frames, 5, True, 5, cap_per_frame=8)
+    got_m, got_c, got_i = detect_batch_multi(dets, frames, 5, True, 5, cap_per_frame=8)
+    assert np.array_equal(got_c, want_c) and got_c.sum() >= 23 and np.array_equal(got_i, want_i)
+    assert np.array_equal(got_m.view(np.uint8), want_m.view(np.uint8))
+    for d in dets:
+        d.close()
