@@ -404,6 +404,7 @@ def main():
         sustained = {"seconds": ms2 / 1000.0, "steps": steps2, "value": n * steps2 * world / (ms2 / 1000.0), "unit": "frames/s", "clocks": c2}
 
     stage_acc = run.stage_times(max(3, min(a.steps, 10)))
+    quad_counters = det.debug_quad_counters()
 
     # ---- end to end through the host-buffer C-ABI call (H2D + detect + D2H inside the timed region) ----
     e2e = None
@@ -512,7 +513,7 @@ def main():
                                           "ceiling_frames_per_s_per_gpu": peak * 1e9 / (5.5 * w * h),
                                           "note": "whole detect path per GPU against the S1+S2 dense traffic of BASELINE.md 4 at the measured HBM peak"},
                 "stages_ms_per_step_unoverlapped": stage_acc, "pipelining": f"{depth} batches in flight, one stream each",
-                "gpu_launches": launches, "markers_decoded_per_step": n_markers / max(steps_done, 1), "parity_check": parity,
+                "quad_fit_work": quad_counters, "gpu_launches": launches, "markers_decoded_per_step": n_markers / max(steps_done, 1), "parity_check": parity,
                 "clocks": clocks, "timed_region_s": ms_max / 1000.0}
         if sustained:
             line["sustained"] = sustained

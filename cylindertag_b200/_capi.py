@@ -81,6 +81,7 @@ SIGNATURES = {
     "ctag_stream": (_P, [_P]),
     "ctag_debug_get_gray": (_I, [_P, _I, _P, _SZ]),
     "ctag_debug_get_binary": (_I, [_P, _I, _P, _SZ]),
+    "ctag_debug_get_quad_counters": (_I, [_P, _P]),
     "ctag_debug_get_components": (_I, [_P, _I, _P, _I, ctypes.POINTER(_I)]),
     "ctag_debug_get_quads": (_I, [_P, _I, _P, _P, _I, ctypes.POINTER(_I)]),
     "ctag_debug_get_features": (_I, [_P, _I, _P, _P, _P, _P, _I, ctypes.POINTER(_I)]),

@@ -82,6 +82,8 @@ struct Slot {
   int *d_prefix = nullptr, *d_qctl = nullptr, *d_quad_status = nullptr, *d_quad_comp = nullptr, *d_n_quads = nullptr,
       *d_exact_list = nullptr, *d_fit_order = nullptr, *d_frame_fit = nullptr, *d_pool = nullptr;
   float *d_quad_corners = nullptr, *d_quads = nullptr, *d_lines = nullptr;
+  void *d_tails = nullptr;
+  int tail_cap = 0;
   void *d_fits = nullptr, *d_traj = nullptr, *d_fit_results = nullptr, *d_geom = nullptr, *d_feats = nullptr;
   int edge_warps = 0, exact_ctas = 0, fit_cap = 0, fit_per_frame = 0, pool_cap = 0;
   int *d_fstate = nullptr, *d_packed_count = nullptr, *d_summary = nullptr;
@@ -211,7 +213,7 @@ static int ensure_workspace(ctag_detector* d, Slot* s, int n, int w, int h) {
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_legal, (size_t)s->legal_cap * 6 * cap));
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_counters, (size_t)4 * cap));
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_prefix, (size_t)cap + 1));
-  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_qctl, 8));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_qctl, 16));
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_quad_status, (size_t)s->legal_cap * cap));
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_quad_corners, (size_t)s->legal_cap * 8 * cap));
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_quads, (size_t)kQuadCap * 8 * cap));
@@ -243,6 +245,8 @@ static int ensure_workspace(ctag_detector* d, Slot* s, int n, int w, int h) {
   const long long per_frame_pts = (long long)g.hw * g.hh;
   s->pool_cap = (int)(per_frame_pts * cap < 0x7fffffff ? per_frame_pts * cap : 0x7fffffff);
   CTAG_CUDA_CHECK(slot_alloc_bytes(s, &s->d_fits, quad_fitrec_bytes() * s->fit_cap));
+  s->tail_cap = quad_tail_cap(d->sms);
+  CTAG_CUDA_CHECK(slot_alloc_bytes(s, &s->d_tails, quad_tailrec_bytes() * s->tail_cap));
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_lines, (size_t)16 * s->fit_cap));
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_pool, (size_t)s->pool_cap));
   s->cap_frames = cap;
@@ -303,7 +307,7 @@ static int enqueue_on_slot(ctag_detector* d, Slot* s, const void* frames_dev, in
   CTAG_CUDA_CHECK(cudaEventRecord(s->ev[2], st));
   rc = launch_quad(n, s->geo, s->d_bin, s->bin_fstride, s->d_labels, s->d_legal, s->legal_cap, s->d_counters, s->d_prefix,
                    s->d_qctl, s->d_quad_scratch, s->edge_warps, s->d_fits, s->fit_cap, s->fit_per_frame, s->d_frame_fit, s->d_pool, s->pool_cap,
-                   d->d_pick_table, kPickTableMax, s->d_fit_results, s->d_exact_list, s->d_fit_order, s->d_traj, s->exact_ctas, d->sms,
+                   d->d_pick_table, kPickTableMax, s->d_fit_results, s->d_exact_list, s->d_fit_order, s->d_tails, s->tail_cap, s->d_traj, s->exact_ctas, d->sms,
                    s->d_lines, s->d_quad_status, s->d_quad_corners, kQuadCap, s->d_quads, s->d_quad_comp, s->d_n_quads, st,
                    &s->launches);
   if (rc != CTAG_OK) return rc;
@@ -665,6 +669,14 @@ int ctag_debug_get_binary(ctag_detector* d, int frame, uint8_t* out, size_t out_
   CTAG_CUDA_CHECK(cudaSetDevice(d->device));
   CTAG_CUDA_CHECK(cudaMemcpy2D(out, out_pitch, s->d_bin + s->bin_fstride * frame, s->geo.bpitch, s->geo.hw, s->geo.hh,
                                cudaMemcpyDeviceToHost));
+  return CTAG_OK;
+}
+
+int ctag_debug_get_quad_counters(ctag_detector* d, int32_t* out16) {
+  Slot* s = last_slot(d, 0);
+  if (!s || !out16) return CTAG_ERR_ARG;
+  CTAG_CUDA_CHECK(cudaSetDevice(d->device));
+  CTAG_CUDA_CHECK(cudaMemcpy(out16, s->d_qctl, sizeof(int32_t) * 16, cudaMemcpyDeviceToHost));
   return CTAG_OK;
 }
 

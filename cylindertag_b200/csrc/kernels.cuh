@@ -28,6 +28,8 @@ int launch_ccl(const uint8_t* bin, size_t bin_fstride, int n, const FrameGeom& g
 // selection -> ordered compaction.
 size_t quad_scratch_bytes_per_warp(const FrameGeom& g);
 size_t quad_fitrec_bytes();
+size_t quad_tailrec_bytes();
+int quad_tail_cap(int sms);
 size_t quad_fitresult_bytes();
 size_t quad_traj_bytes_per_cta();
 int quad_edge_warps(int sms);
@@ -36,7 +38,7 @@ void quad_build_pick_table(uint16_t* host_table, int max_count);
 int launch_quad(int n, const FrameGeom& g, const uint8_t* bin, size_t bin_fstride, const int* labels, const int* legal,
                 int legal_cap, const int* counters, int* prefix, int* qctl, uint8_t* scratch, int edge_warps, void* fits,
                 int fit_cap, int fit_per_frame, int* frame_fit, int* pool, int pool_cap, const uint16_t* pick_table, int table_max, void* results,
-                int* exact_list, int* fit_order, void* traj, int exact_ctas, int sms, float* lines, int* quad_status,
+                int* exact_list, int* fit_order, void* tails, int tail_cap, void* traj, int exact_ctas, int sms, float* lines, int* quad_status,
                 float* quad_corners, int quad_cap, float* quads, int* quad_comp, int* n_quads, cudaStream_t stream,
                 int* launches);
 

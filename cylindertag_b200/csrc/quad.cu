@@ -53,7 +53,21 @@ static QuadScratchLayout make_layout(const FrameGeom& g) {
 size_t quad_scratch_bytes_per_warp(const FrameGeom& g) { return make_layout(g).total; }  // per persistent CTA
 
 // control words of the quad stage (device ints)
-enum { QC_WORK_EDGES = 0, QC_EXACT_COUNT = 1, QC_FIT_COUNT = 2, QC_POOL_CURSOR = 3, QC_OVERFLOW = 4, QC_WORK_FIT = 5, QC_WORDS = 8 };
+enum { QC_WORK_EDGES = 0, QC_EXACT_COUNT = 1, QC_FIT_COUNT = 2, QC_POOL_CURSOR = 3, QC_OVERFLOW = 4, QC_WORK_FIT = 5,
+       QC_UNITS_G32 = 6, QC_TAIL_COUNT = 7, QC_WORK_G32 = 8, QC_FIT_FALLBACKS = 10, QC_WORDS = 16 };
+
+// Restarts of clusters with more than kGroup32Min points are fitted by a whole warp each (quad_fitwarp_kernel), the rest
+// by one lane each (quad_fit_kernel); once the work list has run dry the lane kernel parks its stragglers in a tail list
+// and the warp kernel finishes them, one restart per warp.
+constexpr int kGroup32Min = 256;
+constexpr int kTailLanes = 4;  // a warp parks its restarts when the list is dry and at most this many lanes are busy
+
+// A restart handed from the lane kernel to the warp kernel between two reweighting passes.
+struct TailRec {
+  float line[4], prev[4], best_line[4];
+  double best_err;
+  int i, nvis, t, count, sub_eps, pool_index;
+};
 
 // Component that reached four edges: what the line fits and the corner selection need.
 struct FitRec {
@@ -230,7 +244,7 @@ __device__ __forceinline__ int load_picks(const uint16_t* __restrict__ table, in
 
 // Fit edges sorted by point count, largest first (counting sort, one CTA): the lanes of a warp then walk clusters of
 // similar size, and the long restarts start first instead of forming the tail of the fit kernel.
-__global__ void __launch_bounds__(1024) quad_fitorder_kernel(const int* __restrict__ qctl, const FitRec* __restrict__ fits,
+__global__ void __launch_bounds__(1024) quad_fitorder_kernel(int* __restrict__ qctl, const FitRec* __restrict__ fits,
                                                               int fit_cap, int* __restrict__ order) {
   __shared__ int hist[1024];
   __shared__ int wsum[32];
@@ -268,10 +282,189 @@ __global__ void __launch_bounds__(1024) quad_fitorder_kernel(const int* __restri
   __syncthreads();
   hist[tid] = wsum[warp] + inc - v;
   __syncthreads();
+  // the sorted list starts with the largest clusters: their 20 restarts each are the work units of
+  // quad_fitwarp_kernel, the lane-per-restart kernel starts behind them
+  if (tid == 0) {
+    const int u32 = 20 * hist[1023 - kGroup32Min];
+    qctl[QC_UNITS_G32] = u32;  // work units [0, u32): one restart per warp (quad_fitwarp_kernel)
+    qctl[QC_WORK_G32] = 0;
+    qctl[QC_TAIL_COUNT] = 0;
+    qctl[QC_WORK_FIT] = u32;   // [u32, 80 * nfit): one restart per lane (quad_fit_kernel)
+  }
+  __syncthreads();
   for (int e = tid; e < nedge; e += 1024) {
     const FitRec* fr = fits + (e >> 2);
     const int cnt = fr->cl_off[(e & 3) + 1] - fr->cl_off[e & 3];
     order[atomicAdd(&hist[1023 - (cnt < 1023 ? cnt : 1023)], 1)] = e;
+  }
+}
+
+// ---- larger clusters: one restart per GROUP of G lanes ---------------------------------------------------------------
+// A lane that walks a 100-point cluster through 30 reweighting passes alone needs about 600k cycles and is the tail of
+// the whole quad stage, so the restarts of larger clusters are spread over G = 8 or 32 lanes: residuals, weights and
+// products per point in parallel, the sums by shuffle.  cv::fitLine accumulates its sums sequentially in double, and the
+// result has to stay bit-identical, so a parallel sum is only accepted when it is provably EXACT: every term is a
+// non-negative float, hence a multiple of ulp(smallest non-zero term) >= t_min * 2^-24, and every partial sum in any order
+// is a multiple of that quantum bounded by the total S; with S <= 2^28 * t_min all of them fit the 53-bit significand,
+// no addition rounds, and any summation order gives the same double.  An iteration in which one of its eight sums
+// fails that test (a point on the line to within float noise next to far outliers) is redone by the scalar routine,
+// redundantly on every lane of the group (counted in QC_FIT_FALLBACKS).
+struct GroupSum {
+  double s;
+  float tmin;  // smallest non-zero term
+};
+__device__ __forceinline__ void gsum_add(GroupSum& a, float t) {
+  a.s += t;
+  if (t > 0.f && t < a.tmin) a.tmin = t;
+}
+template <int G>
+__device__ __forceinline__ bool gsum_reduce(GroupSum& a) {  // every lane of the group gets the total; true = provably exact
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) {
+    a.s += __shfl_xor_sync(0xffffffffu, a.s, o);
+    a.tmin = fminf(a.tmin, __shfl_xor_sync(0xffffffffu, a.tmin, o));
+  }
+  return a.s <= 268435456.0 * (double)a.tmin;  // 2^28 * t_min (an all-zero sum has tmin = inf and is exact)
+}
+
+// One reweighting pass of the group's restart (welsch_step, fit_core.cuh, with the point loops dealt over the lanes).
+// Called by ALL lanes of the warp (the reductions are warp-wide shuffles); groups without work pass have = false.
+// Returns false when the restart is over.
+template <int G, int CACHE>
+__device__ __forceinline__ bool welsch_step_group(PoolPts pt, int count, bool have, WelschState& st, WelschBest& best, int gl,
+                                                  int* __restrict__ fallbacks) {
+  float* line = st.line;
+  float* prev = st.prev;
+  bool run = have && st.i < 30;
+  if (run && st.i > 0) {
+    double t = line[0] * prev[0] + line[1] * prev[1];
+    t = t > -1. ? t : -1.;
+    t = t < 1. ? t : 1.;
+    if (fabs(acos(t)) < 0.01f) {
+      float dx = (float)fabs(line[2] - prev[2]);
+      float dy = (float)fabs(line[3] - prev[3]);
+      float d = dx > dy ? dx : dy;
+      if (d < 0.01f) run = false;
+    }
+  }
+  const int n = run ? count : 0;
+  const float c = 1 / 2.9846f;
+  const float px0 = line[2], py0 = line[3], nx = line[1], ny = -line[0];
+  const float kInf = __int_as_float(0x7f800000);
+  float wloc[CACHE];
+  const bool cached = count <= G * CACHE;
+  GroupSum s_err{0., kInf}, s_w{0., kInf};
+  for (int j = gl, m = 0; j < n; j += G, ++m) {
+    const int p = pt(j);
+    const float x = pt_xf(p) - px0, y = pt_yf(p) - py0;
+    const float r = (float)fabs(nx * x + ny * y);
+    const float wr = welsch_exp(-r * r * c * c);
+    if (cached) wloc[m] = wr;
+    gsum_add(s_err, r);
+    gsum_add(s_w, wr);
+  }
+  bool exact = gsum_reduce<G>(s_err);
+  exact &= gsum_reduce<G>(s_w);
+  const double sum_w = s_w.s;
+  const bool norm = fabs(sum_w) > 1.1920928955078125e-07;
+  const double inv = norm ? 1. / sum_w : 0.;
+  GroupSum sx{0., kInf}, sy{0., kInf}, sxx{0., kInf}, syy{0., kInf}, sxy{0., kInf}, sw{0., kInf};
+  if (exact) {
+    for (int j = gl, m = 0; j < n; j += G, ++m) {
+      const int p = pt(j);
+      const float fx = pt_xf(p), fy = pt_yf(p);
+      float wr;
+      if (cached) {
+        wr = wloc[m];
+      } else {
+        const float xx = fx - px0, yy = fy - py0;
+        const float r = (float)fabs(nx * xx + ny * yy);
+        wr = welsch_exp(-r * r * c * c);
+      }
+      const float w = norm ? (float)(wr * inv) : 1.f;
+      gsum_add(sx, w * fx);
+      gsum_add(sy, w * fy);
+      gsum_add(sxx, w * fx * fx);
+      gsum_add(syy, w * fy * fy);
+      gsum_add(sxy, w * fx * fy);
+      gsum_add(sw, w);
+    }
+  }
+  exact &= gsum_reduce<G>(sx);
+  exact &= gsum_reduce<G>(sy);
+  exact &= gsum_reduce<G>(sxx);
+  exact &= gsum_reduce<G>(syy);
+  exact &= gsum_reduce<G>(sxy);
+  exact &= gsum_reduce<G>(sw);
+  if (!run) return false;
+  if (!exact) {
+    if (gl == 0) atomicAdd(fallbacks, 1);
+    float wc[kWelschCache];
+    return welsch_step(pt, count, st, wc, best);
+  }
+  best(st.nvis, s_err.s, line);
+  ++st.nvis;
+  prev[0] = line[0], prev[1] = line[1], prev[2] = line[2], prev[3] = line[3];
+  line_from_moments(sx.s, sy.s, sxx.s, syy.s, sxy.s, sw.s, line);
+  ++st.i;
+  return true;
+}
+
+// One restart per warp: the fresh restarts of the largest clusters (work units [0, qctl[QC_UNITS_G32]) of the size-sorted
+// list) and the stragglers the lane kernel parked in the tail list.  Runs after quad_fit_kernel.
+__global__ void __launch_bounds__(128) quad_fitwarp_kernel(int* __restrict__ qctl, const FitRec* __restrict__ fits,
+                                                           const int* __restrict__ pool, const uint16_t* __restrict__ pick_table,
+                                                           int table_max, const int* __restrict__ order,
+                                                           const TailRec* __restrict__ tails, int tail_cap,
+                                                           FitResult* __restrict__ results) {
+  const int lane = threadIdx.x & 31;
+  const int fresh = qctl[QC_UNITS_G32];
+  int ntail = qctl[QC_TAIL_COUNT];
+  if (ntail > tail_cap) ntail = tail_cap;
+  while (true) {
+    int u = 0;
+    if (lane == 0) u = atomicAdd(&qctl[QC_WORK_G32], 1);
+    u = __shfl_sync(0xffffffffu, u, 0);
+    if (u >= fresh + ntail) break;
+    WelschState st;
+    WelschBest best;
+    PoolPts pa{pool};
+    int t, count;
+    if (u < fresh) {
+      const int ei = u / 20, k = u - 20 * ei, e = order[ei], slot = e >> 2, c = e & 3;
+      t = 20 * e + k;
+      const FitRec* fr = fits + slot;
+      count = fr->cl_off[c + 1] - fr->cl_off[c];
+      best.err = 1.7976931348623157e308;
+      best.sub_eps = false;
+      best.line[0] = best.line[1] = best.line[2] = best.line[3] = 0.f;
+      int picked[10];
+      const int np = load_picks(pick_table, table_max, count, k, picked);
+      pa.p = pool + fr->pool_off + fr->cl_off[c];
+      welsch_init(pa, picked, np, st);  // ten points: every lane computes the same initial line
+    } else {
+      const TailRec r = tails[u - fresh];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) st.line[q] = r.line[q], st.prev[q] = r.prev[q], best.line[q] = r.best_line[q];
+      st.i = r.i;
+      st.nvis = r.nvis;
+      best.err = r.best_err;
+      best.sub_eps = r.sub_eps != 0;
+      t = r.t;
+      count = r.count;
+      pa.p = pool + r.pool_index;
+    }
+    best.eps = count * 1.1920928955078125e-07;
+    while (welsch_step_group<32, 32>(pa, count, true, st, best, lane, &qctl[QC_FIT_FALLBACKS])) {
+    }
+    if (lane == 0) {
+      FitResult o;
+      o.err = best.err;
+      o.line[0] = best.line[0], o.line[1] = best.line[1], o.line[2] = best.line[2], o.line[3] = best.line[3];
+      o.sub_eps = best.sub_eps ? 1 : 0;
+      o.pad = 0;
+      results[t] = o;
+    }
   }
 }
 
@@ -283,7 +476,8 @@ __global__ void __launch_bounds__(1024) quad_fitorder_kernel(const int* __restri
 __global__ void __launch_bounds__(128) quad_fit_kernel(int* __restrict__ qctl, const FitRec* __restrict__ fits,
                                                        int fit_cap, const int* __restrict__ pool,
                                                        const uint16_t* __restrict__ pick_table, int table_max,
-                                                       const int* __restrict__ order, FitResult* __restrict__ results) {
+                                                       const int* __restrict__ order, FitResult* __restrict__ results,
+                                                       TailRec* __restrict__ tails, int tail_cap) {
   int nfit = qctl[QC_FIT_COUNT];
   if (nfit > fit_cap) nfit = fit_cap;
   const int total = 80 * nfit;
@@ -333,7 +527,31 @@ __global__ void __launch_bounds__(128) quad_fit_kernel(int* __restrict__ qctl, c
         }
       }
     }
-    if (__all_sync(0xffffffffu, !have)) break;
+    const unsigned act = __ballot_sync(0xffffffffu, have);
+    if (act == 0) break;
+    if (__any_sync(0xffffffffu, drained) && __popc(act) <= kTailLanes) {
+      // The work list has run dry and only a few lanes of this warp still own a restart -- the tail of the kernel, where
+      // one lane walks a whole cluster while 31 idle.  Park the restarts (between two passes their state is a handful of
+      // numbers); quad_fitwarp_kernel resumes each of them with the points dealt over a whole warp.
+      if (have) {
+        const int idx = atomicAdd(&qctl[QC_TAIL_COUNT], 1);
+        if (idx < tail_cap) {
+          TailRec r;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) r.line[q] = st.line[q], r.prev[q] = st.prev[q], r.best_line[q] = best.line[q];
+          r.best_err = best.err;
+          r.i = st.i;
+          r.nvis = st.nvis;
+          r.t = t;
+          r.count = count;
+          r.sub_eps = best.sub_eps ? 1 : 0;
+          r.pool_index = (int)(pa.p - pool);
+          tails[idx] = r;
+          have = false;
+        }
+      }
+      if (__all_sync(0xffffffffu, !have)) break;
+    }
     if (have && !welsch_step(pa, count, st, wcache, best)) {
       FitResult o;
       o.err = best.err;
@@ -459,6 +677,8 @@ __global__ void __launch_bounds__(32) quad_compact_kernel(const int* __restrict_
 }
 
 size_t quad_fitrec_bytes() { return sizeof(FitRec); }
+size_t quad_tailrec_bytes() { return sizeof(TailRec); }
+int quad_tail_cap(int sms) { return sms * 8 * 4 * kTailLanes; }  // every warp of the lane kernel parks at most kTailLanes restarts
 size_t quad_fitresult_bytes() { return sizeof(FitResult); }
 size_t quad_traj_bytes_per_cta() { return sizeof(WelschIter) * 600; }
 int quad_edge_warps(int sms) { return sms * kEdgeCtasPerSm * kEdgeWarps; }  // persistent warps
@@ -476,7 +696,7 @@ static int env_ctas(const char* name, int dflt, int maxv) {
 int launch_quad(int n, const FrameGeom& g, const uint8_t* bin, size_t bin_fstride, const int* labels, const int* legal,
                 int legal_cap, const int* counters, int* prefix, int* qctl, uint8_t* scratch, int edge_warps, void* fits,
                 int fit_cap, int fit_per_frame, int* frame_fit, int* pool, int pool_cap, const uint16_t* pick_table, int table_max, void* results,
-                int* exact_list, int* fit_order, void* traj, int exact_ctas, int sms, float* lines, int* quad_status,
+                int* exact_list, int* fit_order, void* tails, int tail_cap, void* traj, int exact_ctas, int sms, float* lines, int* quad_status,
                 float* quad_corners, int quad_cap, float* quads, int* quad_comp, int* n_quads, cudaStream_t stream,
                 int* launches) {
   QuadScratchLayout L = make_layout(g);
@@ -490,7 +710,10 @@ int launch_quad(int n, const FrameGeom& g, const uint8_t* bin, size_t bin_fstrid
       fit_cap, fit_per_frame, frame_fit, pool, pool_cap);
   quad_fitorder_kernel<<<1, 1024, 0, stream>>>(qctl, static_cast<const FitRec*>(fits), fit_cap, fit_order);
   quad_fit_kernel<<<sms * fit_ctas, 128, 0, stream>>>(qctl, static_cast<const FitRec*>(fits), fit_cap, pool, pick_table, table_max,
-                                                fit_order, static_cast<FitResult*>(results));
+                                                      fit_order, static_cast<FitResult*>(results), static_cast<TailRec*>(tails), tail_cap);
+  // one restart per warp: the largest clusters and the parked stragglers of the lane kernel
+  quad_fitwarp_kernel<<<sms * 8, 128, 0, stream>>>(qctl, static_cast<const FitRec*>(fits), pool, pick_table, table_max, fit_order,
+                                                   static_cast<const TailRec*>(tails), tail_cap, static_cast<FitResult*>(results));
   quad_fitmerge_kernel<<<(4 * fit_cap + 127) / 128, 128, 0, stream>>>(qctl, fit_cap, static_cast<const FitResult*>(results),
                                                                      lines, exact_list);
   quad_fitexact_kernel<<<exact_ctas, 32, 0, stream>>>(qctl, exact_list, static_cast<const FitRec*>(fits), pool, pick_table,
@@ -500,7 +723,7 @@ int launch_quad(int n, const FrameGeom& g, const uint8_t* bin, size_t bin_fstrid
   quad_compact_kernel<<<n, 32, 0, stream>>>(counters, legal_cap, quad_status, quad_corners, quad_cap, quads, quad_comp,
                                             n_quads);
   CTAG_CUDA_CHECK(cudaGetLastError());
-  if (launches) *launches += 8;
+  if (launches) *launches += 9;
   return CTAG_OK;
 }
 

@@ -139,6 +139,12 @@ class Detector:
         C.check(self._lib.ctag_debug_get_binary(self._h, frame, _ptr(out), w // 2), "ctag_debug_get_binary")
         return out
 
+    def debug_quad_counters(self):
+        out = np.zeros(16, np.int32)
+        C.check(self._lib.ctag_debug_get_quad_counters(self._h, _ptr(out)), "ctag_debug_get_quad_counters")
+        return {"fit_components": int(out[2]), "exact_edges": int(out[1]), "restarts_total": 80 * int(out[2]),
+                "restarts_one_per_warp": int(out[6]), "restarts_parked_in_tail": int(out[7]), "sequential_fallback_passes": int(out[10])}
+
     def debug_components(self, frame=0, cap=65536):
         out = np.zeros((cap, 6), np.int32)
         n = ctypes.c_int()

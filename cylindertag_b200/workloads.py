@@ -1,6 +1,6 @@
 """The synthetic workloads of BASELINE.json configs 3-5 as SURVEY 8(d) writes them, in one place for the golden
-generator (tests/golden/make_golden_ref.py), the parity tests and bench.py.  Input synthesis on the host (numpy / cv2
-through synth.py); not part of the detection path.
+generator (tests/golden/make_golden_ref.py), the parity tests and bench.py.  Input synthesis on the host (through
+synth.py); not part of the detection path.
 
 config 3: 256 frames 1920x1080 BGR, one 2f12c marker each, frame i from default_rng(1000 + i)
 config 4: 3840x2160 BGR, 4..8 markers per frame (4 + i % 5), seeds 2000 + i, three codebooks: 2f12c (shipped) and

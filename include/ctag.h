@@ -216,6 +216,11 @@ CTAG_API void* ctag_stream(const ctag_detector* det);
 /* Stage dumps of the most recent batch for parity tests (copied to host buffers). */
 CTAG_API int ctag_debug_get_gray(ctag_detector* det, int frame, uint8_t* out, size_t out_pitch);     /* w x h */
 CTAG_API int ctag_debug_get_binary(ctag_detector* det, int frame, uint8_t* out, size_t out_pitch);   /* (w/2) x (h/2), {0,255} */
+/* control words of the quad stage of the most recent batch (16 ints): [2] components that reached four edges, [1] edges
+ * that took the exact sub-EPS bookkeeping path, [6] restarts fitted one per warp from the start (20 per edge of a large
+ * cluster), [7] restarts the lane-per-restart kernel parked for the warp kernel at its tail, [10] reweighting passes that
+ * fell back from the parallel to the sequential summation */
+CTAG_API int ctag_debug_get_quad_counters(ctag_detector* det, int32_t* out16);
 /* legal components in reference order: 6 ints each {root_block, area, x0, y0, x1, y1} (inclusive bbox, half-res) */
 CTAG_API int ctag_debug_get_components(ctag_detector* det, int frame, int32_t* out, int cap, int* n_out);
 /* quads in component order: comp index + 4 corners (half-res coords) */

@@ -83,8 +83,8 @@ def test_product_package_does_not_import_oracle():
 
 
 def test_detection_modules_do_not_need_opencv():
-    """cv2 is the ORACLE's library.  In the product package only synth.py (input synthesis for tests / bench) may use
-    it; the detector, the mirror class and the C ABI binding must not."""
+    """cv2 is the ORACLE's library.  In the product package only synth.py (input synthesis for tests / bench; workloads.py
+    calls it) may use it; the detector, the mirror class and the C ABI binding must not."""
     pkg = os.path.join(ROOT, "cylindertag_b200")
     for f in os.listdir(pkg):
         if f.endswith(".py") and f != "synth.py":
