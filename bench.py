@@ -331,6 +331,7 @@ def main():
     ap.add_argument("--timeline", default="", help="write the stage timeline of the timed batches (ms, per batch) to this file")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-jpeg", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--no-traffic", action="store_true")
     ap.add_argument("--sustain", type=float, default=2.0, help="seconds of the sustained loop after the K timed steps")
@@ -438,6 +439,28 @@ def main():
         e2e["h2d_copy_alone_gbs_aggregate"] = world * n * run.fstride / copy_ms / 1e6
         e2e["frac_of_bare_copy"] = copy_ms / e2e["ms_per_step"]
 
+    # ---- compressed ingest: the same ring as JPEG byte strings, decoded on the GPU (nvJPEG) inside ctag_detect_batch_jpeg ----
+    e2e_jpeg = None
+    if not a.no_e2e and not a.no_jpeg:
+        try:
+            import cv2
+            jpegs = [cv2.imencode(".jpg", f, [cv2.IMWRITE_JPEG_QUALITY, 90])[1].reshape(-1).copy() for f in ring]
+            mj, cj, _ = det.detect_batch_jpeg(jpegs, 5, True, 5, run.cap)  # warm-up: decoder states, staging
+            barrier()
+            js = max(2, min(a.steps, 5))
+            t0 = time.perf_counter()
+            for _ in range(js):
+                mj, cj, _ = det.detect_batch_jpeg(jpegs, 5, True, 5, run.cap)
+            torch.cuda.synchronize()
+            dtj = max_over_ranks(time.perf_counter() - t0)
+            e2e_jpeg = {"value": n * js * world / dtj, "unit": "frames/s", "h2d_bytes_per_step": int(sum(j.size for j in jpegs)),
+                        "d2h_bytes_per_step": int(cj.sum()) * _capi.MARKER_DTYPE.itemsize + n * 48, "steps": js, "ms_per_step": 1000.0 * dtj / js,
+                        "decoder": det.jpeg_backend(), "jpeg_quality": 90, "markers_decoded_per_step": int(cj.sum()),
+                        "note": "JPEG byte strings in host memory -> ctag_detect_batch_jpeg (nvJPEG decode on the GPU into the BGR staging "
+                                "buffer, then the detect path); wall clock around synchronous calls; parity on decoded pixels: tests/test_jpeg_gpu.py"}
+        except Exception as exc:  # pragma: no cover
+            e2e_jpeg = {"error": str(exc)}
+
     # ---- multi-GPU: the sharded result equals the single-GPU list ----
     multi_parity = None
     if world > 1:
@@ -519,6 +542,8 @@ def main():
             line["sustained"] = sustained
         if e2e:
             line["e2e"] = e2e
+        if e2e_jpeg:
+            line["e2e_jpeg"] = e2e_jpeg
         if multi_parity:
             line["multi_gpu_parity"] = multi_parity
         if variants:

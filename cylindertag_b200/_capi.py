@@ -67,6 +67,9 @@ SIGNATURES = {
     "ctag_get_dictionary": (_I, [_P, ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_I), _P, _I]),
     "ctag_detect": (_I, [_P, _P, _I, _I, _SZ, _I, _I, _I, _P, _I, ctypes.POINTER(_I), ctypes.POINTER(_I)]),
     "ctag_detect_batch": (_I, [_P, _P, _I, _I, _I, _SZ, _SZ, _I, _I, _I, _I, _I, _P, _I, _P, _P]),
+    "ctag_detect_batch_jpeg": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P, ctypes.POINTER(_I), ctypes.POINTER(_I)]),
+    "ctag_jpeg_backend": (_I, [_P]),
+    "ctag_debug_get_input": (_I, [_P, _I, _P, _SZ]),
     "ctag_detect_batch_enqueue": (_I, [_P, _P, _I, _I, _I, _SZ, _SZ, _I, _I, _I, _I]),
     "ctag_detect_batch_collect": (_I, [_P, _P, _I, _P, _P]),
     "ctag_max_in_flight": (_I, []),

@@ -16,6 +16,7 @@
 
 #include "common.cuh"
 #include "kernels.cuh"
+#include "nvjpeg_dl.h"
 
 namespace ctag {
 
@@ -95,6 +96,9 @@ struct Slot {
   const uint8_t* gray = nullptr;  // full-res gray of the batch (the input itself when channels == 1)
   size_t gray_pitch = 0, gray_fs = 0;
   bool busy = false;
+  // compressed ingest (ctag_detect_batch_jpeg): one batched-decode state per backend, sized for jpeg_batch[] frames
+  nvjpegJpegState_t jpeg_state[2] = {nullptr, nullptr};
+  int jpeg_batch[2] = {0, 0};
 };
 
 }  // namespace ctag
@@ -115,6 +119,9 @@ struct ctag_detector {
   int last = -1;  // slot of the most recently collected batch (debug getters, stage times)
   float stage_ms[CTAG_STAGE_COUNT] = {0, 0, 0, 0, 0};
   int last_launches = 0;
+  nvjpegHandle_t jpeg_handle[2] = {nullptr, nullptr};  // [0] hardware engine (NVJPG), [1] default (CUDA) backend
+  int jpeg_tried[2] = {0, 0};
+  int jpeg_backend_used = -1;  // backend of the most recent compressed batch
   int debug_fail_chunk = -1;  // fault injection for the tests: fail the host pipeline when this chunk index is reached
   int chunk_frames = 0;  // frames per chunk of a host batch; 0 = automatic (CTAG_CHUNK at creation, ctag_set_option later)
 };
@@ -446,6 +453,96 @@ static int detect_batch_host(ctag_detector* d, const void* frames, int n, int w,
   return CTAG_OK;
 }
 
+// ---- compressed ingest (the reference reads its frames through cv::VideoCapture / imread, main.cpp:29,45-52)
+// nvJPEG decodes straight into the staging buffer in the interleaved BGR layout (16-byte pitch) the front kernel's tensor
+// map expects, on the slot's stream, so the decode of chunk c+1 overlaps the detection of chunk c and only the compressed
+// bytes cross PCIe.  Backend 0 = the NVJPG hardware engine, 1 = nvJPEG's CUDA decoder (used when the engine or the
+// bitstream does not qualify).
+static nvjpegHandle_t jpeg_handle(ctag_detector* d, int backend) {
+  if (!d->jpeg_tried[backend]) {
+    d->jpeg_tried[backend] = 1;
+    nvjpegHandle_t h = nullptr;
+    if (nvjpeg_api().CreateEx(backend == 0 ? NVJPEG_BACKEND_HARDWARE : NVJPEG_BACKEND_DEFAULT, nullptr, nullptr, NVJPEG_FLAGS_DEFAULT,
+                              &h) == NVJPEG_STATUS_SUCCESS)
+      d->jpeg_handle[backend] = h;
+  }
+  return d->jpeg_handle[backend];
+}
+
+static int jpeg_decode_chunk(ctag_detector* d, Slot* s, const uint8_t* const* jpeg, const size_t* bytes, int c, size_t dpitch, size_t dfs,
+                             int first_backend) {
+  std::vector<nvjpegImage_t> dst(c);
+  for (int f = 0; f < c; ++f) {
+    memset(&dst[f], 0, sizeof(nvjpegImage_t));
+    dst[f].channel[0] = s->d_stage + dfs * f;
+    dst[f].pitch[0] = dpitch;
+  }
+  for (int b = first_backend; b < 2; ++b) {
+    nvjpegHandle_t h = jpeg_handle(d, b);
+    if (!h) continue;
+    if (!s->jpeg_state[b] && nvjpeg_api().JpegStateCreate(h, &s->jpeg_state[b]) != NVJPEG_STATUS_SUCCESS) continue;
+    if (s->jpeg_batch[b] != c) {
+      if (nvjpeg_api().DecodeBatchedInitialize(h, s->jpeg_state[b], c, 1, NVJPEG_OUTPUT_BGRI) != NVJPEG_STATUS_SUCCESS) continue;
+      s->jpeg_batch[b] = c;
+    }
+    if (nvjpeg_api().DecodeBatched(h, s->jpeg_state[b], jpeg, bytes, dst.data(), s->stream) == NVJPEG_STATUS_SUCCESS) {
+      d->jpeg_backend_used = b;
+      return CTAG_OK;
+    }
+    s->jpeg_batch[b] = 0;  // the state may be half way through a batch: initialise it again next time
+  }
+  set_last_error_text("nvJPEG could not decode the batch (baseline JPEG, 3 components, equal sizes expected)");
+  return CTAG_ERR_UNSUPPORTED;
+}
+
+static int detect_batch_jpeg(ctag_detector* d, const uint8_t* const* jpeg, const size_t* bytes, int n, int w, int h, int adaptive_thresh,
+                             int corner_subpix, int subpix_dist, ctag_marker* out, int cap_per_frame, int* n_out, ctag_frame_info* info) {
+  const size_t dpitch = (size_t)round_up(w * 3, 16), dfs = dpitch * h;
+  int chunk = n;
+  if (n >= 8) {
+    chunk = (int)((((size_t)192 << 20) + dfs - 1) / dfs);
+    if (chunk > (n + 3) / 4) chunk = (n + 3) / 4;
+    if (chunk < 1) chunk = 1;
+  }
+  if (d->chunk_frames > 0) chunk = d->chunk_frames < n ? d->chunk_frames : n;
+  int done = 0, queued = 0, backend = 0;
+  int q_first[kMaxSlots], q_count[kMaxSlots];
+  while (done < n) {
+    while (queued < n && d->in_flight < (kSlots < 3 ? kSlots : 3)) {
+      const int c = n - queued < chunk ? n - queued : chunk;
+      Slot* s = &d->slot[d->next_enqueue];
+      int rc = ensure_stage(s, dfs * c);
+      if (rc != CTAG_OK) return rc;
+      rc = jpeg_decode_chunk(d, s, jpeg + queued, bytes + queued, c, dpitch, dfs, backend);
+      if (rc != CTAG_OK) return rc;
+      backend = d->jpeg_backend_used;  // once the engine has refused a chunk, do not ask it again for this batch
+      rc = enqueue_on_slot(d, s, s->d_stage, c, w, h, dpitch, dfs, 3, adaptive_thresh, corner_subpix, subpix_dist);
+      if (rc != CTAG_OK) return rc;
+      q_first[d->next_enqueue] = queued;
+      q_count[d->next_enqueue] = c;
+      d->next_enqueue = (d->next_enqueue + 1) % kSlots;
+      d->in_flight += 1;
+      queued += c;
+    }
+    const int si = d->next_collect;
+    Slot* s = &d->slot[si];
+    const int first = q_first[si], c = q_count[si];
+    d->last = si;
+    d->next_collect = (d->next_collect + 1) % kSlots;
+    d->in_flight -= 1;
+    int rc = collect_slot(d, s, out ? out + (size_t)first * cap_per_frame : nullptr, cap_per_frame, n_out ? n_out + first : nullptr,
+                          info ? info + first : nullptr);
+    if (rc != CTAG_OK) return rc;
+    if (out)
+      for (int f = 0; f < c; ++f) {
+        const int nm = s->h_summary[12 * f + 10];
+        for (int k = 0; k < nm && k < cap_per_frame; ++k) out[(size_t)(first + f) * cap_per_frame + k].frame = first + f;
+      }
+    done += c;
+  }
+  return CTAG_OK;
+}
+
 extern "C" {
 
 int ctag_create(ctag_detector** out, const int32_t* state, int rows, int cols, int feature_size, int cuda_device) {
@@ -509,6 +606,13 @@ void ctag_destroy(ctag_detector* d) {
     for (auto& e : s.ev)
       if (e) cudaEventDestroy(e);
     if (s.stream) cudaStreamDestroy(s.stream);
+  }
+  if (nvjpeg_api().ok) {
+    for (Slot& s : d->slot)
+      for (auto& st : s.jpeg_state)
+        if (st) nvjpeg_api().JpegStateDestroy(st);
+    for (auto& h : d->jpeg_handle)
+      if (h) nvjpeg_api().Destroy(h);
   }
   if (d->epoch) cudaEventDestroy(d->epoch);
   cudaFree(d->d_state);
@@ -619,6 +723,40 @@ int ctag_detect_batch_multi(ctag_detector* const* dets, int n_det, const void* f
   return CTAG_OK;
 }
 
+int ctag_detect_batch_jpeg(ctag_detector* d, const uint8_t* const* jpeg, const size_t* jpeg_bytes, int n, int adaptive_thresh,
+                           int corner_subpix, int subpix_dist, ctag_marker* out, int cap_per_frame, int* n_out, ctag_frame_info* info,
+                           int* width_out, int* height_out) {
+  if (!d || !jpeg || !jpeg_bytes || n <= 0) return CTAG_ERR_ARG;
+  if (d->in_flight != 0) return CTAG_ERR_ARG;
+  if (!nvjpeg_api().ok) {
+    set_last_error_text("libnvjpeg.so.12 could not be loaded: compressed ingest is unavailable (no CPU decoder is substituted)");
+    return CTAG_ERR_UNSUPPORTED;
+  }
+  CTAG_CUDA_CHECK(cudaSetDevice(d->device));
+  nvjpegHandle_t h = jpeg_handle(d, 1) ? jpeg_handle(d, 1) : jpeg_handle(d, 0);
+  if (!h) {
+    set_last_error_text("nvjpegCreateEx failed");
+    return CTAG_ERR_CUDA;
+  }
+  int w = 0, hgt = 0;
+  for (int f = 0; f < n; ++f) {
+    int comps = 0, ws[NVJPEG_MAX_COMPONENT], hs[NVJPEG_MAX_COMPONENT];
+    nvjpegChromaSubsampling_t ss;
+    if (!jpeg[f] || nvjpeg_api().GetImageInfo(h, jpeg[f], jpeg_bytes[f], &comps, &ss, ws, hs) != NVJPEG_STATUS_SUCCESS) return CTAG_ERR_ARG;
+    if (f == 0) w = ws[0], hgt = hs[0];
+    if (ws[0] != w || hs[0] != hgt) return CTAG_ERR_ARG;  // one batch = one frame size (the tensor map is per batch)
+  }
+  if (width_out) *width_out = w;
+  if (height_out) *height_out = hgt;
+  int rc = check_args(d, jpeg, n, w, hgt, 3, adaptive_thresh, corner_subpix, subpix_dist);
+  if (rc != CTAG_OK) return rc;
+  rc = detect_batch_jpeg(d, jpeg, jpeg_bytes, n, w, hgt, adaptive_thresh, corner_subpix, subpix_dist, out, cap_per_frame, n_out, info);
+  if (rc != CTAG_OK) drain_slots(d);
+  return rc;
+}
+
+int ctag_jpeg_backend(const ctag_detector* d) { return d ? d->jpeg_backend_used : -1; }
+
 int ctag_detect(ctag_detector* d, const uint8_t* gray, int w, int h, size_t pitch, int adaptive_thresh, int corner_subpix,
                 int subpix_dist, ctag_marker* out, int cap, int* n_out, int* frame_status) {
   ctag_frame_info info;
@@ -653,6 +791,15 @@ static Slot* last_slot(ctag_detector* d, int frame) {
   if (!d || d->last < 0) return nullptr;
   Slot* s = &d->slot[d->last];
   return (frame >= 0 && frame < s->n) ? s : nullptr;
+}
+
+int ctag_debug_get_input(ctag_detector* d, int frame, uint8_t* out, size_t out_pitch) {
+  Slot* s = last_slot(d, frame);
+  if (!s || !out || !s->d_stage) return CTAG_ERR_ARG;
+  CTAG_CUDA_CHECK(cudaSetDevice(d->device));
+  const size_t row = (size_t)s->w * s->channels, dpitch = (size_t)round_up((int)row, 16);
+  CTAG_CUDA_CHECK(cudaMemcpy2D(out, out_pitch, s->d_stage + dpitch * s->h * frame, dpitch, row, s->h, cudaMemcpyDeviceToHost));
+  return CTAG_OK;
 }
 
 int ctag_debug_get_gray(ctag_detector* d, int frame, uint8_t* out, size_t out_pitch) {

@@ -75,6 +75,34 @@ class Detector:
         self._shape, self._n = (h, w), n
         return out, cnt, info
 
+    def detect_batch_jpeg(self, jpegs, adaptive_thresh=5, corner_subpix=False, subpix_dist=3, cap_per_frame=16):
+        """jpegs: list of JPEG byte strings (bytes / uint8 arrays) of equally sized frames; decoded on the GPU by nvJPEG
+        (ctag_detect_batch_jpeg).  Returns (markers, counts, info)."""
+        bufs = [np.frombuffer(j, np.uint8) if isinstance(j, (bytes, bytearray, memoryview)) else np.ascontiguousarray(j, np.uint8).reshape(-1)
+                for j in jpegs]
+        n = len(bufs)
+        ptrs = (ctypes.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        sizes = (ctypes.c_size_t * n)(*[b.size for b in bufs])
+        out = np.zeros((n, cap_per_frame), C.MARKER_DTYPE)
+        cnt = np.zeros(n, np.int32)
+        info = np.zeros(n, C.INFO_DTYPE)
+        w, h = ctypes.c_int(), ctypes.c_int()
+        C.check(self._lib.ctag_detect_batch_jpeg(self._h, ptrs, sizes, n, int(adaptive_thresh), int(bool(corner_subpix)), int(subpix_dist),
+                                                 _ptr(out), cap_per_frame, _ptr(cnt), _ptr(info), ctypes.byref(w), ctypes.byref(h)),
+                "ctag_detect_batch_jpeg")
+        self._shape, self._n, self._channels = (h.value, w.value), n, 3
+        return out, cnt, info
+
+    def jpeg_backend(self):
+        return {0: "nvjpeg hardware engine (NVJPG)", 1: "nvjpeg CUDA backend"}.get(int(self._lib.ctag_jpeg_backend(self._h)), "none")
+
+    def debug_input(self, frame=0, channels=3):
+        """Staged input of the last host / JPEG batch as the kernels saw it (last chunk)."""
+        h, w = self._shape
+        out = np.zeros((h, w, channels) if channels > 1 else (h, w), np.uint8)
+        C.check(self._lib.ctag_debug_get_input(self._h, frame, _ptr(out), w * channels), "ctag_debug_get_input")
+        return out
+
     def detect(self, gray, adaptive_thresh=5, corner_subpix=False, subpix_dist=3, cap=16):
         """Single 8-bit gray host image through ctag_detect.  Returns (markers[count], frame_status)."""
         g = np.ascontiguousarray(gray, dtype=np.uint8)

@@ -148,6 +148,20 @@ CTAG_API int ctag_detect_batch_multi(ctag_detector* const* dets, int n_det, cons
                                      size_t pitch, size_t frame_stride, int channels, int adaptive_thresh, int corner_subpix,
                                      int subpix_dist, ctag_marker* out, int cap_per_frame, int* n_out, ctag_frame_info* info);
 
+/* Compressed ingest: the same batch call on JPEG byte strings (host memory), replacing the reference's
+ * decode-on-the-CPU front (cv::VideoCapture::read / cv::imread, main.cpp:29,45-52, then cvtColor, :54).  The frames are
+ * decoded on the GPU by nvJPEG -- the NVJPG hardware engine when the bitstream qualifies (baseline, single scan), else
+ * nvJPEG's CUDA decoder -- straight into the interleaved BGR layout the fused front kernel reads, chunk by chunk on the
+ * pipeline's streams, so only the compressed bytes cross PCIe.  All frames of a batch must have the same (even) size;
+ * *width_out / *height_out (optional) report it.  libnvjpeg is loaded on first use; without it the call fails with
+ * CTAG_ERR_UNSUPPORTED (there is no CPU decoder behind it).  Parity is defined on the decoded pixels:
+ * ctag_debug_get_input copies them back. */
+CTAG_API int ctag_detect_batch_jpeg(ctag_detector* det, const uint8_t* const* jpeg, const size_t* jpeg_bytes, int n,
+                                    int adaptive_thresh, int corner_subpix, int subpix_dist, ctag_marker* out, int cap_per_frame,
+                                    int* n_out, ctag_frame_info* info, int* width_out, int* height_out);
+/* Decoder used by the most recent compressed batch: 0 = NVJPG hardware engine, 1 = nvJPEG CUDA backend, -1 = none yet. */
+CTAG_API int ctag_jpeg_backend(const ctag_detector* det);
+
 /* Asynchronous pair for device-resident throughput runs: enqueue the whole detect path for a batch, then collect.
  * Up to ctag_max_in_flight() batches may be enqueued before the first collect (each has its own workspace and CUDA
  * stream, so the latency-bound sparse kernels of one batch overlap the dense kernels of the next); collect returns
@@ -215,6 +229,8 @@ CTAG_API void* ctag_stream(const ctag_detector* det);
 
 /* Stage dumps of the most recent batch for parity tests (copied to host buffers). */
 CTAG_API int ctag_debug_get_gray(ctag_detector* det, int frame, uint8_t* out, size_t out_pitch);     /* w x h */
+/* the staged input of a HOST or JPEG batch as the kernels saw it: w x h x channels, interleaved (last chunk only) */
+CTAG_API int ctag_debug_get_input(ctag_detector* det, int frame, uint8_t* out, size_t out_pitch);
 CTAG_API int ctag_debug_get_binary(ctag_detector* det, int frame, uint8_t* out, size_t out_pitch);   /* (w/2) x (h/2), {0,255} */
 /* control words of the quad stage of the most recent batch (16 ints): [2] components that reached four edges, [1] edges
  * that took the exact sub-EPS bookkeeping path, [6] restarts fitted one per warp from the start (20 per edge of a large
