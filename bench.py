@@ -444,7 +444,13 @@ def main():
     if not a.no_e2e and not a.no_jpeg:
         try:
             import cv2
-            jpegs = [cv2.imencode(".jpg", f, [cv2.IMWRITE_JPEG_QUALITY, 90])[1].reshape(-1).copy() for f in ring]
+            enc = [cv2.imencode(".jpg", f, [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_RST_INTERVAL, 16])[1].reshape(-1) for f in ring]
+            pinned = torch.empty(sum(e.size for e in enc), dtype=torch.uint8).pin_memory()  # like the raw e2e: pinned host memory
+            jpegs, pos = [], 0
+            for e in enc:
+                pinned[pos:pos + e.size] = torch.from_numpy(e)
+                jpegs.append(pinned[pos:pos + e.size].numpy())
+                pos += e.size
             mj, cj, _ = det.detect_batch_jpeg(jpegs, 5, True, 5, run.cap)  # warm-up: decoder states, staging
             barrier()
             js = max(2, min(a.steps, 5))
@@ -455,9 +461,21 @@ def main():
             dtj = max_over_ranks(time.perf_counter() - t0)
             e2e_jpeg = {"value": n * js * world / dtj, "unit": "frames/s", "h2d_bytes_per_step": int(sum(j.size for j in jpegs)),
                         "d2h_bytes_per_step": int(cj.sum()) * _capi.MARKER_DTYPE.itemsize + n * 48, "steps": js, "ms_per_step": 1000.0 * dtj / js,
-                        "decoder": det.jpeg_backend(), "jpeg_quality": 90, "markers_decoded_per_step": int(cj.sum()),
-                        "note": "JPEG byte strings in host memory -> ctag_detect_batch_jpeg (nvJPEG decode on the GPU into the BGR staging "
-                                "buffer, then the detect path); wall clock around synchronous calls; parity on decoded pixels: tests/test_jpeg_gpu.py"}
+                        "decoder": det.jpeg_backend(), "jpeg_quality": 90, "restart_interval_mcus": 16, "sampling": "4:2:0",
+                        "compressed_mb_per_frame": sum(j.size for j in jpegs) / n / 1e6, "markers_decoded_per_step": int(cj.sum()),
+                        "note": "JPEG byte strings in pinned host memory -> ctag_detect_batch_jpeg (decode on the GPU into the BGR staging "
+                                "buffer, then the detect path); wall clock around synchronous calls; decoded pixels equal cv::imdecode's and "
+                                "detections equal the reference's on them: tests/test_jpeg_gpu.py"}
+            # the same ring four times per call (256 frames): the decoder's kernels run one thread per restart interval and
+            # like many frames per launch
+            big = jpegs * 4
+            det.detect_batch_jpeg(big, 5, True, 5, run.cap)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                det.detect_batch_jpeg(big, 5, True, 5, run.cap)
+            torch.cuda.synchronize()
+            e2e_jpeg["value_256_frames_per_call"] = len(big) * 2 * world / max_over_ranks(time.perf_counter() - t0)
         except Exception as exc:  # pragma: no cover
             e2e_jpeg = {"error": str(exc)}
 

@@ -99,6 +99,14 @@ struct Slot {
   // compressed ingest (ctag_detect_batch_jpeg): one batched-decode state per backend, sized for jpeg_batch[] frames
   nvjpegJpegState_t jpeg_state[2] = {nullptr, nullptr};
   int jpeg_batch[2] = {0, 0};
+  // the CUDA JPEG decoder's buffers (jpeg.cu), grown on demand
+  uint8_t *d_jbytes = nullptr, *d_jplanes = nullptr, *d_jhdr = nullptr, *h_jhdr = nullptr, *d_jlast = nullptr;
+  uint32_t* d_jivl = nullptr;
+  int16_t* d_jcoefs = nullptr;
+  int *d_jstatus = nullptr, *h_jstatus = nullptr;
+  size_t jbytes_cap = 0, jplanes_cap = 0, jivl_cap = 0, jcoefs_cap = 0, jlast_cap = 0;
+  int w_expect = 0, h_expect = 0;  // frame size of the compressed batch being staged
+  int jhdr_cap = 0, jpeg_frames = 0;  // jpeg_frames > 0: the batch in this slot came through the CUDA decoder
 };
 
 }  // namespace ctag
@@ -121,7 +129,8 @@ struct ctag_detector {
   int last_launches = 0;
   nvjpegHandle_t jpeg_handle[2] = {nullptr, nullptr};  // [0] hardware engine (NVJPG), [1] default (CUDA) backend
   int jpeg_tried[2] = {0, 0};
-  int jpeg_backend_used = -1;  // backend of the most recent compressed batch
+  int jpeg_backend_used = -1;  // decoder of the most recent compressed batch: 2 = CUDA decoder (jpeg.cu), 0 / 1 = nvJPEG
+  int jpeg_decoder = 0;  // ctag_set_option("jpeg_decoder"): 0 = CUDA decoder first, nvJPEG for what it refuses; 1 = nvJPEG only
   int debug_fail_chunk = -1;  // fault injection for the tests: fail the host pipeline when this chunk index is reached
   int chunk_frames = 0;  // frames per chunk of a host batch; 0 = automatic (CTAG_CHUNK at creation, ctag_set_option later)
 };
@@ -471,6 +480,22 @@ static nvjpegHandle_t jpeg_handle(ctag_detector* d, int backend) {
 
 static int jpeg_decode_chunk(ctag_detector* d, Slot* s, const uint8_t* const* jpeg, const size_t* bytes, int c, size_t dpitch, size_t dfs,
                              int first_backend) {
+  {  // one batch = one frame size (the tensor map is per batch)
+    nvjpegHandle_t h = jpeg_handle(d, 1) ? jpeg_handle(d, 1) : jpeg_handle(d, 0);
+    if (!h) {
+      set_last_error_text("nvjpegCreateEx failed");
+      return CTAG_ERR_CUDA;
+    }
+    for (int f = 0; f < c; ++f) {
+      int comps = 0, ws[NVJPEG_MAX_COMPONENT], hs[NVJPEG_MAX_COMPONENT];
+      nvjpegChromaSubsampling_t ss;
+      if (nvjpeg_api().GetImageInfo(h, jpeg[f], bytes[f], &comps, &ss, ws, hs) != NVJPEG_STATUS_SUCCESS || ws[0] != s->w_expect ||
+          hs[0] != s->h_expect) {
+        set_last_error_text("ctag_detect_batch_jpeg: a frame is not a readable JPEG of the batch's size");
+        return CTAG_ERR_ARG;
+      }
+    }
+  }
   std::vector<nvjpegImage_t> dst(c);
   for (int f = 0; f < c; ++f) {
     memset(&dst[f], 0, sizeof(nvjpegImage_t));
@@ -495,13 +520,96 @@ static int jpeg_decode_chunk(ctag_detector* d, Slot* s, const uint8_t* const* jp
   return CTAG_ERR_UNSUPPORTED;
 }
 
+// ---- the CUDA decoder (jpeg.cu): baseline JPEG with restart markers, one GPU thread per restart interval ------------
+template <typename T>
+static int grow(T** p, size_t* cap, size_t need) {
+  if (*cap >= need) return CTAG_OK;
+  cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  const size_t want = need + need / 4;
+  CTAG_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(p), want * sizeof(T)));
+  *cap = want;
+  return CTAG_OK;
+}
+
+// Parses, uploads and decodes frames [0, c) of a chunk into s->d_stage.  Returns CTAG_OK, CTAG_ERR_UNSUPPORTED when a
+// frame is outside the decoder's envelope (*unsupported_frame says which), or an error.
+static int jpeg_cuda_chunk(ctag_detector* d, Slot* s, const uint8_t* const* jpeg, const size_t* bytes, int c, int w, int h, size_t dpitch,
+                           size_t dfs) {
+  const size_t hb = jpeg_header_bytes();
+  if (s->jhdr_cap < c) {
+    cudaFree(s->d_jhdr);
+    cudaFree(s->d_jstatus);
+    cudaFreeHost(s->h_jhdr);
+    cudaFreeHost(s->h_jstatus);
+    s->d_jhdr = s->h_jhdr = nullptr;
+    s->d_jstatus = s->h_jstatus = nullptr;
+    s->jhdr_cap = 0;
+    CTAG_CUDA_CHECK(cudaMalloc(&s->d_jhdr, hb * c));
+    CTAG_CUDA_CHECK(cudaMalloc(&s->d_jstatus, sizeof(int) * c));
+    CTAG_CUDA_CHECK(cudaMallocHost(&s->h_jhdr, hb * c));
+    CTAG_CUDA_CHECK(cudaMallocHost(&s->h_jstatus, sizeof(int) * c));
+    s->jhdr_cap = c;
+  }
+  size_t total_bytes = 0, plane_stride = 0;
+  int total_ivl = 0, max_ivl = 0, max_blocks = 0, all_420 = 1;
+  std::vector<size_t> scan_off(c), scan_len(c), place(c);
+  for (int f = 0; f < c; ++f) {
+    int fw = 0, fh = 0, ni = 0;
+    size_t pb = 0;
+    const int rc = jpeg_parse_frame(jpeg[f], bytes[f], s->h_jhdr + hb * f, &scan_off[f], &scan_len[f], &fw, &fh, &ni, &pb);
+    if (rc == 2) return CTAG_ERR_UNSUPPORTED;
+    if (rc != 0 || fw != w || fh != h) {
+      set_last_error_text("ctag_detect_batch_jpeg: a frame is not a readable JPEG of the batch's size");
+      return CTAG_ERR_ARG;
+    }
+    place[f] = total_bytes;  // frames start 16-byte aligned in the device buffer
+    jpeg_place_frame(s->h_jhdr + hb * f, (uint32_t)(total_bytes + scan_off[f]), (uint32_t)scan_len[f], total_ivl);
+    total_bytes += (bytes[f] + 15) & ~(size_t)15;
+    total_ivl += ni + 1;
+    if (ni > max_ivl) max_ivl = ni;
+    if (pb > plane_stride) plane_stride = pb;
+    const int nb = jpeg_frame_blocks(s->h_jhdr + hb * f);
+    if (nb > max_blocks) max_blocks = nb;
+    all_420 &= jpeg_frame_is_420(s->h_jhdr + hb * f);
+  }
+  const size_t coef_stride = (size_t)max_blocks * 64, last_stride = ((size_t)max_blocks + 15) & ~(size_t)15;
+  if (total_bytes + 32 >= 0xFFFFFFFFull) return CTAG_ERR_UNSUPPORTED;  // 32-bit offsets inside a chunk
+  int rc = grow(&s->d_jbytes, &s->jbytes_cap, total_bytes + 32);
+  if (rc == CTAG_OK) rc = grow(&s->d_jivl, &s->jivl_cap, (size_t)total_ivl);
+  if (rc == CTAG_OK) rc = grow(&s->d_jplanes, &s->jplanes_cap, plane_stride * c);
+  if (rc == CTAG_OK) rc = grow(&s->d_jcoefs, &s->jcoefs_cap, coef_stride * c);
+  if (rc == CTAG_OK) rc = grow(&s->d_jlast, &s->jlast_cap, last_stride * c);
+  if (rc == CTAG_OK) rc = ensure_stage(s, dfs * c);
+  if (rc != CTAG_OK) return rc;
+  for (int f = 0; f < c; ++f)
+    CTAG_CUDA_CHECK(cudaMemcpyAsync(s->d_jbytes + place[f], jpeg[f], bytes[f], cudaMemcpyHostToDevice, s->stream));
+  CTAG_CUDA_CHECK(cudaMemcpyAsync(s->d_jhdr, s->h_jhdr, hb * c, cudaMemcpyHostToDevice, s->stream));
+  int launches = 0;
+  rc = launch_jpeg_decode(s->d_jhdr, c, s->d_jbytes, s->d_jivl, max_ivl, s->d_jcoefs, coef_stride, s->d_jlast, last_stride, max_blocks,
+                          s->d_jplanes, plane_stride, s->d_stage, dpitch, dfs, w, h, all_420, s->d_jstatus, s->stream, &launches);
+  if (rc != CTAG_OK) return rc;
+  CTAG_CUDA_CHECK(cudaMemcpyAsync(s->h_jstatus, s->d_jstatus, sizeof(int) * c, cudaMemcpyDeviceToHost, s->stream));
+  s->jpeg_frames = c;
+  d->jpeg_backend_used = 2;
+  return CTAG_OK;
+}
+
 static int detect_batch_jpeg(ctag_detector* d, const uint8_t* const* jpeg, const size_t* bytes, int n, int w, int h, int adaptive_thresh,
                              int corner_subpix, int subpix_dist, ctag_marker* out, int cap_per_frame, int* n_out, ctag_frame_info* info) {
   const size_t dpitch = (size_t)round_up(w * 3, 16), dfs = dpitch * h;
+  bool use_cuda = d->jpeg_decoder != 1;
+  // Chunks: the Huffman kernel runs one thread per restart interval, a long sequential chain each, so it wants MANY frames
+  // per launch to fill the machine (a 4K frame with 16-MCU intervals is 2,025 threads): half the batch per chunk, up to
+  // about 1 GiB of decoded frames (the second chunk's decode overlaps the first chunk's detection).  nvJPEG decodes on the
+  // host side of the stream: small chunks as for raw host frames.
   int chunk = n;
   if (n >= 8) {
-    chunk = (int)((((size_t)192 << 20) + dfs - 1) / dfs);
-    if (chunk > (n + 3) / 4) chunk = (n + 3) / 4;
+    const size_t target = use_cuda ? (size_t)1 << 30 : (size_t)192 << 20;
+    chunk = (int)((target + dfs - 1) / dfs);
+    const int share = use_cuda ? (n + 1) / 2 : (n + 3) / 4;
+    if (chunk > share) chunk = share;
     if (chunk < 1) chunk = 1;
   }
   if (d->chunk_frames > 0) chunk = d->chunk_frames < n ? d->chunk_frames : n;
@@ -511,11 +619,26 @@ static int detect_batch_jpeg(ctag_detector* d, const uint8_t* const* jpeg, const
     while (queued < n && d->in_flight < (kSlots < 3 ? kSlots : 3)) {
       const int c = n - queued < chunk ? n - queued : chunk;
       Slot* s = &d->slot[d->next_enqueue];
-      int rc = ensure_stage(s, dfs * c);
-      if (rc != CTAG_OK) return rc;
-      rc = jpeg_decode_chunk(d, s, jpeg + queued, bytes + queued, c, dpitch, dfs, backend);
-      if (rc != CTAG_OK) return rc;
-      backend = d->jpeg_backend_used;  // once the engine has refused a chunk, do not ask it again for this batch
+      int rc = CTAG_ERR_UNSUPPORTED;
+      s->jpeg_frames = 0;
+      s->w_expect = w;
+      s->h_expect = h;
+      if (use_cuda) {
+        rc = jpeg_cuda_chunk(d, s, jpeg + queued, bytes + queued, c, w, h, dpitch, dfs);
+        if (rc == CTAG_ERR_UNSUPPORTED && queued == 0) use_cuda = false;  // e.g. no restart markers: nvJPEG for this batch
+        else if (rc != CTAG_OK) return rc;
+      }
+      if (!use_cuda) {
+        if (!nvjpeg_api().ok) {
+          set_last_error_text("the frames are outside the CUDA decoder's envelope (baseline JPEG with restart markers) and libnvjpeg.so.12 is not available");
+          return CTAG_ERR_UNSUPPORTED;
+        }
+        rc = ensure_stage(s, dfs * c);
+        if (rc != CTAG_OK) return rc;
+        rc = jpeg_decode_chunk(d, s, jpeg + queued, bytes + queued, c, dpitch, dfs, backend);
+        if (rc != CTAG_OK) return rc;
+        backend = d->jpeg_backend_used;  // once the engine has refused a chunk, do not ask it again for this batch
+      }
       rc = enqueue_on_slot(d, s, s->d_stage, c, w, h, dpitch, dfs, 3, adaptive_thresh, corner_subpix, subpix_dist);
       if (rc != CTAG_OK) return rc;
       q_first[d->next_enqueue] = queued;
@@ -533,6 +656,11 @@ static int detect_batch_jpeg(ctag_detector* d, const uint8_t* const* jpeg, const
     int rc = collect_slot(d, s, out ? out + (size_t)first * cap_per_frame : nullptr, cap_per_frame, n_out ? n_out + first : nullptr,
                           info ? info + first : nullptr);
     if (rc != CTAG_OK) return rc;
+    for (int f = 0; f < s->jpeg_frames; ++f)
+      if (s->h_jstatus[f] != 0) {
+        set_last_error_text("ctag_detect_batch_jpeg: restart markers of a frame do not match its header (corrupt stream)");
+        return CTAG_ERR_ARG;
+      }
     if (out)
       for (int f = 0; f < c; ++f) {
         const int nm = s->h_summary[12 * f + 10];
@@ -603,6 +731,15 @@ void ctag_destroy(ctag_detector* d) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     free_workspace(&s);
     cudaFree(s.d_stage);
+    cudaFree(s.d_jbytes);
+    cudaFree(s.d_jplanes);
+    cudaFree(s.d_jcoefs);
+    cudaFree(s.d_jlast);
+    cudaFree(s.d_jhdr);
+    cudaFree(s.d_jivl);
+    cudaFree(s.d_jstatus);
+    cudaFreeHost(s.h_jhdr);
+    cudaFreeHost(s.h_jstatus);
     for (auto& e : s.ev)
       if (e) cudaEventDestroy(e);
     if (s.stream) cudaStreamDestroy(s.stream);
@@ -626,6 +763,11 @@ int ctag_set_option(ctag_detector* d, const char* key, int value) {
   if (!strcmp(key, "chunk_frames")) {
     if (value < 0) return CTAG_ERR_ARG;
     d->chunk_frames = value;
+    return CTAG_OK;
+  }
+  if (!strcmp(key, "jpeg_decoder")) {
+    if (value < 0 || value > 1) return CTAG_ERR_ARG;
+    d->jpeg_decoder = value;
     return CTAG_OK;
   }
   if (!strcmp(key, "debug_fail_chunk")) {
@@ -728,23 +870,30 @@ int ctag_detect_batch_jpeg(ctag_detector* d, const uint8_t* const* jpeg, const s
                            int* width_out, int* height_out) {
   if (!d || !jpeg || !jpeg_bytes || n <= 0) return CTAG_ERR_ARG;
   if (d->in_flight != 0) return CTAG_ERR_ARG;
-  if (!nvjpeg_api().ok) {
-    set_last_error_text("libnvjpeg.so.12 could not be loaded: compressed ingest is unavailable (no CPU decoder is substituted)");
-    return CTAG_ERR_UNSUPPORTED;
-  }
   CTAG_CUDA_CHECK(cudaSetDevice(d->device));
-  nvjpegHandle_t h = jpeg_handle(d, 1) ? jpeg_handle(d, 1) : jpeg_handle(d, 0);
-  if (!h) {
-    set_last_error_text("nvjpegCreateEx failed");
-    return CTAG_ERR_CUDA;
-  }
+  // the batch's frame size: from the SOF segment of the first frame (every frame is checked against it when its chunk
+  // is parsed / decoded)
   int w = 0, hgt = 0;
-  for (int f = 0; f < n; ++f) {
-    int comps = 0, ws[NVJPEG_MAX_COMPONENT], hs[NVJPEG_MAX_COMPONENT];
-    nvjpegChromaSubsampling_t ss;
-    if (!jpeg[f] || nvjpeg_api().GetImageInfo(h, jpeg[f], jpeg_bytes[f], &comps, &ss, ws, hs) != NVJPEG_STATUS_SUCCESS) return CTAG_ERR_ARG;
-    if (f == 0) w = ws[0], hgt = hs[0];
-    if (ws[0] != w || hs[0] != hgt) return CTAG_ERR_ARG;  // one batch = one frame size (the tensor map is per batch)
+  for (int f = 0; f < n; ++f)
+    if (!jpeg[f] || jpeg_bytes[f] < 4) return CTAG_ERR_ARG;
+  {
+    const uint8_t* p = jpeg[0];
+    const size_t len = jpeg_bytes[0];
+    if (p[0] != 0xFF || p[1] != 0xD8) return CTAG_ERR_ARG;
+    size_t i = 2;
+    while (i + 9 < len && p[i] == 0xFF) {
+      const int m = p[i + 1];
+      if (m == 0xFF) { ++i; continue; }
+      const size_t seg = ((size_t)p[i + 2] << 8) | p[i + 3];
+      if (m >= 0xC0 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+        hgt = (p[i + 5] << 8) | p[i + 6];
+        w = (p[i + 7] << 8) | p[i + 8];
+        break;
+      }
+      if (m == 0xDA) break;
+      i += 2 + seg;
+    }
+    if (w <= 0 || hgt <= 0) return CTAG_ERR_ARG;
   }
   if (width_out) *width_out = w;
   if (height_out) *height_out = hgt;

@@ -42,6 +42,19 @@ int launch_quad(int n, const FrameGeom& g, const uint8_t* bin, size_t bin_fstrid
                 float* quad_corners, int quad_cap, float* quads, int* quad_comp, int* n_quads, cudaStream_t stream,
                 int* launches);
 
+// Compressed ingest (jpeg.cu): baseline JPEG with restart markers -> interleaved BGR frames.  jpeg_parse_frame returns
+// 0, 1 (not a JPEG / corrupt) or 2 (outside the decoder's envelope: progressive, no restart markers, ...).
+size_t jpeg_header_bytes();
+int jpeg_parse_frame(const uint8_t* data, size_t len, void* header_out, size_t* scan_off, size_t* scan_len, int* w, int* h,
+                     int* n_intervals, size_t* plane_bytes);
+void jpeg_place_frame(void* header, uint32_t data_off, uint32_t data_len, int interval_first);
+int jpeg_frame_blocks(const void* header);
+int jpeg_frame_is_420(const void* header);
+int launch_jpeg_decode(const void* d_hdr, int n, const uint8_t* d_bytes, uint32_t* d_ivl, int max_intervals, int16_t* d_coefs,
+                       size_t coef_stride, uint8_t* d_last, size_t last_stride, int max_blocks, uint8_t* d_planes, size_t plane_stride,
+                       uint8_t* d_bgr, size_t pitch, size_t frame_stride, int w, int h, int all_420, int* d_status, cudaStream_t stream,
+                       int* launches);
+
 // K5/K6 (feature.cu): quad pairing, coordinate lift, edge refinement.  fstate[frame] = {status, n_features,
 // n_features going on, overflow}.
 size_t sizeof_quad_geom();

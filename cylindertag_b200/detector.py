@@ -94,7 +94,8 @@ class Detector:
         return out, cnt, info
 
     def jpeg_backend(self):
-        return {0: "nvjpeg hardware engine (NVJPG)", 1: "nvjpeg CUDA backend"}.get(int(self._lib.ctag_jpeg_backend(self._h)), "none")
+        return {0: "nvjpeg hardware engine (NVJPG)", 1: "nvjpeg hybrid backend", 2: "cuda decoder (csrc/jpeg.cu)"}.get(
+            int(self._lib.ctag_jpeg_backend(self._h)), "none")
 
     def debug_input(self, frame=0, channels=3):
         """Staged input of the last host / JPEG batch as the kernels saw it (last chunk)."""

@@ -105,6 +105,8 @@ CTAG_API void ctag_destroy(ctag_detector* det);
 /* Tuning knobs of one detector (the defaults are the measured best; environment variables of the same meaning are
  * read ONCE, when the detector is created).  Keys: "chunk_frames" -- frames per chunk of a host batch in
  * ctag_detect_batch(is_device=0), 0 = automatic (about 192 MiB of frames, at most a quarter of the batch).
+ * "jpeg_decoder" -- 0 (default): ctag_detect_batch_jpeg uses the library's CUDA decoder and falls back to nvJPEG for
+ * batches it refuses, 1: nvJPEG only.
  * "debug_fail_chunk" -- fault injection for the tests: the next host batch fails with CTAG_ERR_CUDA when it reaches
  * that chunk index (one shot; -1 = off).  Not allowed while batches are pending.  Unknown key: CTAG_ERR_ARG. */
 CTAG_API int ctag_set_option(ctag_detector* det, const char* key, int value);
@@ -150,16 +152,22 @@ CTAG_API int ctag_detect_batch_multi(ctag_detector* const* dets, int n_det, cons
 
 /* Compressed ingest: the same batch call on JPEG byte strings (host memory), replacing the reference's
  * decode-on-the-CPU front (cv::VideoCapture::read / cv::imread, main.cpp:29,45-52, then cvtColor, :54).  The frames are
- * decoded on the GPU by nvJPEG -- the NVJPG hardware engine when the bitstream qualifies (baseline, single scan), else
- * nvJPEG's CUDA decoder -- straight into the interleaved BGR layout the fused front kernel reads, chunk by chunk on the
- * pipeline's streams, so only the compressed bytes cross PCIe.  All frames of a batch must have the same (even) size;
- * *width_out / *height_out (optional) report it.  libnvjpeg is loaded on first use; without it the call fails with
- * CTAG_ERR_UNSUPPORTED (there is no CPU decoder behind it).  Parity is defined on the decoded pixels:
- * ctag_debug_get_input copies them back. */
+ * decoded on the GPU straight into the interleaved BGR layout the fused front kernel reads, chunk by chunk on the
+ * pipeline's streams, so only the compressed bytes cross PCIe.
+ *   Decoder 2, the library's own CUDA decoder (csrc/jpeg.cu): baseline / sequential JPEG, 8 bit, gray or YCbCr 4:4:4 /
+ *   4:2:2 / 4:2:0, WITH restart markers (DRI): a restart interval is the unit that decodes independently, one GPU thread
+ *   each.  Its pixels are those of cv::imdecode (libjpeg-turbo defaults: integer IDCT, fancy upsampling), byte for byte.
+ *   Decoders 0 / 1, nvJPEG (loaded with dlopen on first use): for batches the CUDA decoder refuses (no restart markers,
+ *   progressive): the NVJPG hardware engine when nvJPEG offers it on the device, else nvJPEG's hybrid decoder.
+ * ctag_set_option("jpeg_decoder", 1) forces nvJPEG.  All frames of a batch must have the same (even) size; *width_out /
+ * *height_out (optional) report it.  There is no CPU decoder behind this call: when neither GPU decoder can take the
+ * batch it fails with CTAG_ERR_UNSUPPORTED.  Parity is defined on the decoded pixels: ctag_debug_get_input copies them
+ * back. */
 CTAG_API int ctag_detect_batch_jpeg(ctag_detector* det, const uint8_t* const* jpeg, const size_t* jpeg_bytes, int n,
                                     int adaptive_thresh, int corner_subpix, int subpix_dist, ctag_marker* out, int cap_per_frame,
                                     int* n_out, ctag_frame_info* info, int* width_out, int* height_out);
-/* Decoder used by the most recent compressed batch: 0 = NVJPG hardware engine, 1 = nvJPEG CUDA backend, -1 = none yet. */
+/* Decoder used by the most recent compressed batch: 2 = the library's CUDA decoder, 0 = nvJPEG on the NVJPG hardware
+ * engine, 1 = nvJPEG hybrid backend, -1 = none yet. */
 CTAG_API int ctag_jpeg_backend(const ctag_detector* det);
 
 /* Asynchronous pair for device-resident throughput runs: enqueue the whole detect path for a batch, then collect.

@@ -12,7 +12,7 @@ ROOT = os.path.join(HERE, "..", "..")
 def build_harness(force=False):
     src = os.path.join(HERE, "harness.cpp")
     deps = [src] + [os.path.join(ROOT, "cylindertag_b200", "csrc", f) for f in
-                    ("libm_core.cuh", "fit_core.cuh", "quad_core.cuh", "feature_core.cuh", "decode_core.cuh")]
+                    ("libm_core.cuh", "fit_core.cuh", "quad_core.cuh", "feature_core.cuh", "decode_core.cuh", "jpeg_core.cuh")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", LIB, src]

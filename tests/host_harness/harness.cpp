@@ -8,6 +8,7 @@
 #include "../../cylindertag_b200/csrc/quad_core.cuh"
 #include "../../cylindertag_b200/csrc/feature_core.cuh"
 #include "../../cylindertag_b200/csrc/decode_core.cuh"
+#include "../../cylindertag_b200/csrc/jpeg_core.cuh"
 
 using namespace ctag::core;
 
@@ -143,5 +144,43 @@ void hh_expand_both(const int32_t* pts, int n, int init, int end, int32_t* out4)
   for (int i = 0; i < n; ++i) packed[i] = pt_pack(pts[2 * i], pts[2 * i + 1]);
   expand_span_seq(packed.data(), n, init, end, &out4[0], &out4[1]);
   expand_span(packed.data(), n, init, end, Lanes{0, 1}, &out4[2], &out4[3]);
+}
+
+// Baseline JPEG through the decoder cores of the compressed-ingest path (jpeg_core.cuh), one restart interval at a time
+// like the GPU kernel.  out: h rows of `pitch` bytes, BGR interleaved.  Returns 0, or the parse status (1 bad, 2
+// unsupported); *w / *h are set as soon as the header is known.
+int hh_jpeg_decode(const uint8_t* data, size_t len, uint8_t* out, size_t pitch, int cap_w, int cap_h, int* w, int* h, int mode) {
+  using namespace ctag::jpeg;
+  static FrameHeader fh;
+  size_t so = 0, sl = 0;
+  int rc = parse_header(data, len, fh, &so, &sl);
+  if (rc != JP_OK) return rc;
+  *w = fh.width;
+  *h = fh.height;
+  if (!out) return 0;
+  if (fh.width > cap_w || fh.height > cap_h) return 3;
+  std::vector<uint32_t> off(fh.n_intervals + 1);
+  rc = find_intervals_host(data + so, sl, fh.n_intervals, off.data());
+  if (rc != JP_OK) return rc;
+  std::vector<uint8_t> planes(fh.plane_bytes);
+  if (mode == 0) {
+    for (int k = 0; k < fh.n_intervals; ++k) decode_interval(fh, data + so + off[k], data + so + off[k + 1], k, planes.data());
+  } else {  // the GPU's two-step form: coefficients first (fast bit reader), inverse DCT per block afterwards
+    std::vector<uint8_t> padded(data, data + len);
+    padded.resize(len + 32, 0);
+    std::vector<int16_t> coefs((size_t)fh.n_blocks * 64, 0);
+    std::vector<uint8_t> last(fh.n_blocks, 0);
+    for (int k = 0; k < fh.n_intervals; ++k)
+      decode_interval_coefs(fh, padded.data() + so + off[k], padded.data() + so + off[k + 1], k, coefs.data(), last.data());
+    for (int c = 0; c < fh.ncomp; ++c)
+      for (int b = 0; b < fh.blocks_x[c] * fh.mcus_y * fh.comp_v[c]; ++b) {
+        const int bx = b % fh.blocks_x[c], by = b / fh.blocks_x[c], blk = fh.block_first[c] + b;
+        idct_block_from_coefs(coefs.data() + (size_t)blk * 64, last[blk], planes.data() + fh.plane_off[c] + (size_t)by * 8 * fh.plane_pitch[c] + bx * 8,
+                              fh.plane_pitch[c]);
+      }
+  }
+  for (int y = 0; y < fh.height; ++y)
+    for (int x = 0; x < fh.width; ++x) output_pixel(fh, planes.data(), x, y, out + (size_t)y * pitch + 3 * x);
+  return 0;
 }
 }
