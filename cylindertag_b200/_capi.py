@@ -80,6 +80,10 @@ SIGNATURES = {
     "ctag_project_points": (_I, [_P, _I, _P, _P, _P, _P, _I, _P]),
     "ctag_gray_to_3ch": (_I, [_P, _I, _I, _SZ, _P, _SZ]),
     "ctag_draw_axis": (_I, [_P, _I, _I, _SZ, _P, _P, _I, _P, _P, _P, _P, _I, _P, _P, _I]),
+    "ctag_codebook_capacity": (_I, [_I, _I]),
+    "ctag_generate_codebook": (_I, [_I, _I, _I, ctypes.c_uint64, _P, _I, ctypes.POINTER(_I)]),
+    "ctag_check_codebook": (_I, [_P, _I, _I, _I]),
+    "ctag_render_frames": (_I, [_P, _P, _I, _I, _I, _SZ, _SZ, _I, _P, _P, _P]),
     "ctag_last_launch_count": (_I, [_P]),
     "ctag_stream": (_P, [_P]),
     "ctag_debug_get_gray": (_I, [_P, _I, _P, _SZ]),

@@ -906,6 +906,60 @@ int ctag_detect_batch_jpeg(ctag_detector* d, const uint8_t* const* jpeg, const s
 
 int ctag_jpeg_backend(const ctag_detector* d) { return d ? d->jpeg_backend_used : -1; }
 
+int ctag_render_frames(ctag_detector* d, void* frames_dev, int n, int w, int h, size_t pitch, size_t frame_stride, int channels,
+                       const float* marker_specs, const int* marker_start, const float* frame_params) {
+  if (!d || !frames_dev || n <= 0 || w <= 0 || h <= 0 || (channels != 1 && channels != 3) || !marker_start || !frame_params) return CTAG_ERR_ARG;
+  if (pitch < (size_t)w * channels) return CTAG_ERR_ARG;
+  if (frame_stride == 0) frame_stride = pitch * (size_t)h;
+  const int nm = marker_start[n];
+  if (nm < 0 || (nm > 0 && !marker_specs)) return CTAG_ERR_ARG;
+  for (int f = 0; f < n; ++f)
+    if (marker_start[f + 1] < marker_start[f]) return CTAG_ERR_ARG;
+  CTAG_CUDA_CHECK(cudaSetDevice(d->device));
+  const size_t mb = render_marker_dev_bytes();
+  std::vector<uint8_t> packed(mb * (size_t)(nm > 0 ? nm : 1));
+  for (int f = 0; f < n; ++f)
+    for (int m = marker_start[f]; m < marker_start[f + 1]; ++m) {
+      const float* sp = marker_specs + 16 * (size_t)m;
+      const int row = (int)sp[10];
+      if (row < 0 || row >= d->rows) return CTAG_ERR_ARG;
+      render_pack_marker(sp, d->cols, row * d->cols, frame_params + 8 * (size_t)f, w, h, packed.data() + mb * m);
+    }
+  float* d_img = nullptr;
+  float* d_fp = nullptr;
+  void* d_mk = nullptr;
+  int* d_ms = nullptr;
+  // frames are rendered in groups that keep the float scene buffer below 1 GiB
+  int group = (int)(((size_t)1 << 30) / ((size_t)w * h * sizeof(float)));
+  if (group < 1) group = 1;
+  if (group > n) group = n;
+  cudaError_t e = cudaMalloc(&d_img, (size_t)group * w * h * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&d_fp, sizeof(float) * 8 * n);
+  if (e == cudaSuccess) e = cudaMalloc(&d_mk, packed.size());
+  if (e == cudaSuccess) e = cudaMalloc(&d_ms, sizeof(int) * (n + 1));
+  if (e == cudaSuccess) e = cudaMemcpy(d_fp, frame_params, sizeof(float) * 8 * n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_mk, packed.data(), packed.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_ms, marker_start, sizeof(int) * (n + 1), cudaMemcpyHostToDevice);
+  int rc = CTAG_OK;
+  if (e == cudaSuccess) {
+    for (int f0 = 0; f0 < n && rc == CTAG_OK; f0 += group) {
+      const int c = n - f0 < group ? n - f0 : group;
+      rc = launch_render(d_img, c, w, h, d_fp + 8 * f0, d_mk, d_ms + f0, d->d_state, static_cast<uint8_t*>(frames_dev) + frame_stride * f0,
+                         pitch, frame_stride, channels, 0);
+    }
+    if (rc == CTAG_OK) e = cudaDeviceSynchronize();
+  }
+  cudaFree(d_img);
+  cudaFree(d_fp);
+  cudaFree(d_mk);
+  cudaFree(d_ms);
+  if (e != cudaSuccess) {
+    set_last_error("ctag_render_frames", e, __FILE__, __LINE__);
+    return CTAG_ERR_CUDA;
+  }
+  return rc;
+}
+
 int ctag_detect(ctag_detector* d, const uint8_t* gray, int w, int h, size_t pitch, int adaptive_thresh, int corner_subpix,
                 int subpix_dist, ctag_marker* out, int cap, int* n_out, int* frame_status) {
   ctag_frame_info info;

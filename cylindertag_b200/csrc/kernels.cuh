@@ -55,6 +55,12 @@ int launch_jpeg_decode(const void* d_hdr, int n, const uint8_t* d_bytes, uint32_
                        uint8_t* d_bgr, size_t pitch, size_t frame_stride, int w, int h, int all_420, int* d_status, cudaStream_t stream,
                        int* launches);
 
+// Synthetic frames on the GPU (render.cu).
+size_t render_marker_dev_bytes();
+void render_pack_marker(const float* spec, int cols, int row_off, const float* K, int w, int h, void* out);
+int launch_render(float* d_img, int n, int w, int h, const float* d_fparams, const void* d_markers, const int* d_marker_start,
+                  const int* d_states, uint8_t* out, size_t pitch, size_t frame_stride, int channels, cudaStream_t stream);
+
 // K5/K6 (feature.cu): quad pairing, coordinate lift, edge refinement.  fstate[frame] = {status, n_features,
 // n_features going on, overflow}.
 size_t sizeof_quad_geom();

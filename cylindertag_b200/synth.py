@@ -61,6 +61,23 @@ def generate_codebook(cols: int, feature_size: int, rows: int, seed: int = 7) ->
     return np.array(out, dtype=np.int32)
 
 
+def generate_codebook_dfs(cols: int, feature_size: int, rows: int, seed: int = 7) -> np.ndarray:
+    """The reference generator's depth-first search (CylinderTag_generator.m:34-216) in the library
+    (ctag_generate_codebook, host code): reaches the full capacity, e.g. 41 rows for 2f12c like the shipped book."""
+    import ctypes
+    from . import _capi as C
+    lib = C.load()
+    cap = lib.ctag_codebook_capacity(cols, feature_size)
+    if cap < 0:
+        raise ValueError("cols / feature_size outside the generator's range")
+    rows = min(rows, cap)
+    out = np.zeros((rows, cols), np.int32)
+    n = ctypes.c_int()
+    C.check(lib.ctag_generate_codebook(cols, feature_size, rows, seed, out.ctypes.data_as(ctypes.c_void_p), rows, ctypes.byref(n)),
+            "ctag_generate_codebook")
+    return out[:n.value]
+
+
 def check_codebook(state: np.ndarray, feature_size: int) -> bool:
     seen = set()
     for row in state.tolist():
@@ -273,6 +290,40 @@ def synthetic_frame(seed: int, w: int, h: int, state: np.ndarray, n_markers: int
     frame = render_frame(w, h, [s for _, s in specs], rng, blur_sigma=float(rng.uniform(0.3, 1.2)),
                          noise_sigma=float(rng.uniform(0.5, 3.0)), channels=channels)
     return frame, specs
+
+
+def render_frames_gpu(det, frames_ptr: int, seeds, w: int, h: int, n_markers, channels: int = 3, pitch: int | None = None,
+                      frame_stride: int = 0):
+    """The same scenes as synthetic_frame(seed, ...) -- random_specs drawn from default_rng(seed), blur / noise levels from the
+    same stream -- rendered by the library's CUDA renderer (ctag_render_frames) straight into device memory at `frames_ptr`
+    (e.g. a torch tensor's data_ptr()).  n_markers: int or one int per frame.  Returns the rendered dictionary rows per frame.
+    Pixel values differ from the host renderer's (other background texture / noise stream); the geometry is the same."""
+    import ctypes
+    from . import _capi as C
+    state = det.state
+    seeds = list(seeds)
+    nm = [n_markers] * len(seeds) if isinstance(n_markers, int) else list(n_markers)
+    K = camera_matrix(w, h)
+    specs, start, fparams, truth = [], [0], [], []
+    for seed, k in zip(seeds, nm):
+        rng = np.random.default_rng(seed)
+        sp = random_specs(state, k, w, h, rng, K)
+        blur, noise = float(rng.uniform(0.3, 1.2)), float(rng.uniform(0.5, 3.0))
+        for row, s in sorted(sp, key=lambda rs: -float(np.asarray(rs[1].tvec)[2])):  # far markers first
+            specs.append(list(np.asarray(s.rvec, np.float64)) + list(np.asarray(s.tvec, np.float64)) +
+                         [s.radius, s.ratio, s.black, s.white, float(row)] + [0.0] * 5)
+        start.append(len(specs))
+        truth.append([row for row, _ in sp])
+        bits = np.array([seed * 2654435761 % (1 << 32), (seed * 40503 + 12345) % (1 << 32)], np.uint32).view(np.float32)
+        fparams.append([K[0, 0], K[1, 1], K[0, 2], K[1, 2], blur, noise, bits[0], bits[1]])
+    sp_arr = np.ascontiguousarray(np.array(specs, np.float32).reshape(-1, 16))
+    st_arr = np.ascontiguousarray(np.array(start, np.int32))
+    fp_arr = np.ascontiguousarray(np.array(fparams, np.float32))
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    pitch = pitch or w * channels
+    C.check(C.load().ctag_render_frames(det._h, ctypes.c_void_p(frames_ptr), len(seeds), w, h, pitch, frame_stride, channels, vp(sp_arr),
+                                        vp(st_arr), vp(fp_arr)), "ctag_render_frames")
+    return truth
 
 
 def video_sequence(gray: np.ndarray, n_frames: int = 120, seed: int = 2024, first: int = 0, count: int | None = None):

@@ -213,6 +213,31 @@ CTAG_API int ctag_draw_axis(uint8_t* img3, int w, int h, size_t pitch, const cta
                             int n_model_corners, const float* base, const float* axis, const float* intrinsic,
                             const float* dist, int n_dist, const double* rvec, const double* tvec, int axis_length);
 
+/* ---- dictionary generation (host code, no GPU work) ---------------------------- */
+
+/* The reference ships one dictionary; CylinderTag_generator.m (MATLAB) searches others.  ctag_generate_codebook is that
+ * search (:34-216): rows are grown state by state, candidates ordered by the continuations they leave, with backtracking,
+ * every cyclic window of feature_size states unique over the book read forwards and as its inverse (:247-286).
+ * ctag_codebook_capacity = legal windows that differ from their inverse / (2 * cols) (:36-39): 41 for 2-state windows on
+ * 12 columns, the size of the shipped CTag_2f12c.marker, which the search reaches.  `rows` is clamped to the capacity;
+ * *rows_out rows were found (state_out: rows x cols, row-major, room for cap_rows rows).  feature_size 2..4. */
+CTAG_API int ctag_codebook_capacity(int cols, int feature_size);
+CTAG_API int ctag_generate_codebook(int cols, int feature_size, int rows, uint64_t seed, int32_t* state_out, int cap_rows, int* rows_out);
+/* 1 if every state is legal and every window reading is unique (testConflict, :247-286), 0 if not, < 0 on bad arguments */
+CTAG_API int ctag_check_codebook(const int32_t* state, int rows, int cols, int feature_size);
+
+/* Synthetic camera frames rendered on the GPU, straight into device memory in the layout ctag_detect_batch_enqueue takes
+ * (CylinderTag_generator.m:206-245 only draws flat marker bitmaps).  Scene model of SURVEY Appendix D.3 / D.6:
+ * each marker is a row of the detector's dictionary wrapped once around a cylinder (column width W = 2 pi r / (1.5 cols),
+ * height L = ratio * W), pinhole camera looking along +Z, x_cam = R(rvec) x_obj + tvec, 3 x 3 rays per pixel, smooth
+ * background in [140, 220], Gaussian blur, Gaussian noise, 8-bit rounding; channels = 3 adds +-6 levels of chroma noise.
+ *   marker_specs  [n_markers][16] floats: rvec(3) tvec(3) radius ratio black white dictionary_row, rest unused;
+ *                 markers of frame f are marker_start[f] .. marker_start[f + 1] (far markers first: later ones occlude)
+ *   frame_params  [n][8] floats: fx fy cx cy blur_sigma noise_sigma noise_seed(bit pattern) background_seed(bit pattern)
+ * Synchronous.  Not bit-compatible with the host renderer of cylindertag_b200/synth.py. */
+CTAG_API int ctag_render_frames(ctag_detector* det, void* frames_dev, int n, int w, int h, size_t pitch, size_t frame_stride,
+                                int channels, const float* marker_specs, const int* marker_start, const float* frame_params);
+
 /* ---- instrumentation ------------------------------------------------------------------------ */
 
 /* Stage identifiers for ctag_stage_time_ms / ctag_debug_*. */

@@ -10,6 +10,7 @@
 // The .marker format is the one CylinderTag::load_from_file reads (CylinderTag.cpp:24-32):
 //   `rows cols featureSize` then rows x cols integers.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <fstream>
 #include <set>
@@ -88,6 +89,201 @@ inline Mat1i generate_codebook(int cols, int feature_size, int rows, uint64_t se
   }
   if (out.rows < rows) return Mat1i();
   return out;
+}
+
+// ---- depth-first search of the reference's generator (CylinderTag_generator.m:34-216) ---------------------------------
+// A window of `f` consecutive states is a number in [0, 64^f); `used` marks every window taken by a row, read forwards or as
+// its inverse (:247-286).  A row grows one state at a time (:62-159): the candidates for the next state are the legal states
+// whose new window and its inverse are both free (:97-112); they are tried in DESCENDING order of how many continuations
+// each would leave (:113-139, ties in random order), backtracking when a branch dies; the last state closes the cycle and
+// is drawn at random, at most 100 times, checking all f wrap-around windows (:160-190).  Rows are added until `rows` are
+// found or the search budget is spent; a book that stalls is thrown away and started again from the next random stream
+// (the MATLAB script is simply re-run by hand in that case).  Capacity (:36-39): the windows that are legal and differ from
+// their own inverse, divided by 2 * cols -- 41 rows for two-state windows on twelve columns, the size of the shipped book.
+namespace detail {
+struct DfsGen {
+  int cols, f, rows_wanted;
+  std::vector<int> legal;
+  std::vector<uint8_t> used;
+  std::vector<int64_t> pw;  // 64^k
+  uint64_t x;
+  long long nodes = 0, node_budget = 0;
+  std::vector<int32_t> book;
+  int rows = 0;
+
+  uint64_t next() {
+    uint64_t z = (x += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+  }
+  // window code of states w[0..f-1] (first state in the lowest digit, as in the .m file) and of its inverse reading
+  int64_t code(const int* w) const {
+    int64_t c = 0;
+    for (int k = 0; k < f; ++k) c += (int64_t)w[k] * pw[k];
+    return c;
+  }
+  int64_t inv_code(const int* w) const {
+    int64_t c = 0;
+    for (int k = 0; k < f; ++k) c += (int64_t)inverse_state(w[k]) * pw[f - 1 - k];
+    return c;
+  }
+  bool free_window(const int* w) const {
+    const int64_t a = code(w), b = inv_code(w);
+    return a != b && !used[a] && !used[b];
+  }
+  void mark(const int* w, uint8_t v) {
+    used[code(w)] = v;
+    used[inv_code(w)] = v;
+  }
+  // one row by depth-first search; `row` holds the states placed so far
+  bool dfs(std::vector<int>& row) {
+    if (++nodes > node_budget) return false;
+    const int n = (int)row.size();
+    if (n == cols) return true;
+    std::vector<int> w(f);
+    if (n < f) {  // the first window: random free start (:69-91)
+      for (int tries = 0; tries < 200; ++tries) {
+        std::vector<int> start(f);
+        for (int k = 0; k < f; ++k) start[k] = legal[next() % legal.size()];
+        if (!free_window(start.data())) continue;
+        mark(start.data(), 1);
+        row = start;
+        if (dfs(row)) return true;
+        mark(start.data(), 0);
+        row.clear();
+        if (nodes > node_budget) return false;
+      }
+      return false;
+    }
+    if (n < cols - 1) {
+      struct Cand { int s, options; uint64_t tie; };
+      std::vector<Cand> cands;
+      for (int s : legal) {
+        for (int k = 0; k < f - 1; ++k) w[k] = row[n - f + 1 + k];
+        w[f - 1] = s;
+        if (!free_window(w.data())) continue;
+        int options = 0;  // continuations one step further (:113-129)
+        std::vector<int> w2(f);
+        for (int k = 0; k < f - 2; ++k) w2[k] = row[n - f + 2 + k];
+        if (f >= 2) w2[f - 2] = s;
+        for (int t : legal) {
+          w2[f - 1] = t;
+          if (free_window(w2.data()) && !(code(w2.data()) == code(w.data()) || code(w2.data()) == inv_code(w.data()))) ++options;
+        }
+        cands.push_back({s, options, next()});
+      }
+      std::sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) { return a.options != b.options ? a.options > b.options : a.tie < b.tie; });
+      for (const Cand& c : cands) {
+        if (c.options == 0) break;  // (:141-143)
+        for (int k = 0; k < f - 1; ++k) w[k] = row[n - f + 1 + k];
+        w[f - 1] = c.s;
+        mark(w.data(), 1);
+        row.push_back(c.s);
+        if (dfs(row)) return true;
+        row.pop_back();
+        for (int k = 0; k < f - 1; ++k) w[k] = row[n - f + 1 + k];
+        w[f - 1] = c.s;
+        mark(w.data(), 0);
+        if (nodes > node_budget) return false;
+      }
+      return false;
+    }
+    // the last state closes the cycle: f windows wrap around (:160-190); every legal state is tried, in random order
+    std::vector<int> order = legal;
+    for (size_t i = order.size(); i > 1; --i) std::swap(order[i - 1], order[next() % i]);
+    for (int s : order) {
+      row.push_back(s);
+      std::vector<int64_t> codes;
+      bool ok = true;
+      for (int j = 0; j < f && ok; ++j) {  // windows starting at positions cols - f + j
+        for (int k = 0; k < f; ++k) w[k] = row[(cols - f + j + k) % cols];
+        ok = free_window(w.data());
+        const int64_t a = code(w.data()), b = inv_code(w.data());
+        for (int64_t c : codes) ok = ok && c != a && c != b;
+        codes.push_back(a);
+        codes.push_back(b);
+      }
+      if (ok) {
+        for (int64_t c : codes) used[c] = 1;
+        return true;
+      }
+      row.pop_back();
+    }
+    return false;
+  }
+};
+}  // namespace detail
+
+inline int codebook_capacity(int cols, int feature_size) {
+  detail::DfsGen g;
+  g.f = feature_size;
+  g.pw.assign(feature_size + 1, 1);
+  for (int k = 1; k <= feature_size; ++k) g.pw[k] = g.pw[k - 1] * 64;
+  long long usable = 0;
+  std::vector<int> w(feature_size, 0), legal;
+  for (int s = 0; s < 64; ++s)
+    if (legal_state(s)) legal.push_back(s);
+  std::vector<int> idx(feature_size, 0);
+  while (true) {
+    for (int k = 0; k < feature_size; ++k) w[k] = legal[idx[k]];
+    if (g.code(w.data()) != g.inv_code(w.data())) ++usable;
+    int k = 0;
+    while (k < feature_size && ++idx[k] == (int)legal.size()) idx[k++] = 0;
+    if (k == feature_size) break;
+  }
+  return (int)(usable / (2 * cols));
+}
+
+// The reference's search.  Returns the book (possibly with fewer than `rows` rows if the budget ran out; rows is clamped
+// to the capacity).  `restarts`: books thrown away and begun again before giving up.
+inline Mat1i generate_codebook_dfs(int cols, int feature_size, int rows, uint64_t seed = 7, int restarts = 200,
+                                   long long nodes_per_row = 200000) {
+  Mat1i best;
+  best.cols = cols;
+  if (cols < feature_size + 1 || feature_size < 1 || feature_size > 4) return best;
+  const int cap = codebook_capacity(cols, feature_size);
+  if (rows > cap) rows = cap;
+  for (int attempt = 0; attempt <= restarts; ++attempt) {
+    detail::DfsGen g;
+    g.cols = cols;
+    g.f = feature_size;
+    g.rows_wanted = rows;
+    for (int s = 0; s < 64; ++s)
+      if (legal_state(s)) g.legal.push_back(s);
+    g.pw.assign(feature_size + 1, 1);
+    for (int k = 1; k <= feature_size; ++k) g.pw[k] = g.pw[k - 1] * 64;
+    g.used.assign((size_t)g.pw[feature_size], 0);
+    g.x = seed + 0x632BE59BD9B4E019ull * (uint64_t)attempt;
+    int failures = 0;
+    while (g.rows < rows && failures < 40) {
+      std::vector<int> row;
+      g.nodes = 0;
+      g.node_budget = nodes_per_row;
+      if (g.dfs(row)) {
+        g.book.insert(g.book.end(), row.begin(), row.end());
+        g.rows += 1;
+        failures = 0;
+      } else {
+        // undo whatever the failed search still holds (dfs unmarks on the way back; a budget stop may leave marks)
+        std::fill(g.used.begin(), g.used.end(), 0);
+        for (int r = 0; r < g.rows; ++r) {
+          std::vector<int> w(feature_size);
+          for (int j = 0; j < cols; ++j) {
+            for (int k = 0; k < feature_size; ++k) w[k] = g.book[(size_t)r * cols + (j + k) % cols];
+            g.mark(w.data(), 1);
+          }
+        }
+        ++failures;
+      }
+    }
+    if (g.rows > best.rows) {
+      best.rows = g.rows;
+      best.data = g.book;
+    }
+    if (best.rows >= rows) break;
+  }
+  return best;
 }
 
 // .marker writer (the format of CylinderTag.cpp:24-32)

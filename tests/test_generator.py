@@ -35,3 +35,29 @@ def test_generated_dictionary_obeys_the_rules(gen, tmp_path, cols, fsz, rows):
 def test_shipped_dictionary_passes_the_cxx_checker_rules(marker_path):
     state, fs = o.load_marker_file(marker_path)
     assert synth.check_codebook(np.asarray(state), fs)
+
+
+def test_dfs_generator_reaches_the_capacity_of_the_shipped_book(marker_path):
+    """CylinderTag_generator.m:36-39 caps a 2f12c book at 41 rows -- the size of the shipped CTag_2f12c.marker; the
+    library's restatement of its depth-first search gets there, and the larger layouts give the 100 rows the .m asks for."""
+    import ctypes
+    from cylindertag_b200 import _capi as C
+    lib = C.load()
+    assert lib.ctag_codebook_capacity(12, 2) == 41 and lib.ctag_codebook_capacity(15, 3) == 1092
+    shipped, fs = o.load_marker_file(marker_path)
+    assert shipped.shape == (41, 12)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    assert lib.ctag_check_codebook(vp(np.ascontiguousarray(shipped, np.int32)), 41, 12, 2) == 1
+    for seed in (7, 8, 2024):
+        book = synth.generate_codebook_dfs(12, 2, 41, seed=seed)
+        assert book.shape == (41, 12) and synth.check_codebook(book, 2)
+        assert lib.ctag_check_codebook(vp(np.ascontiguousarray(book, np.int32)), 41, 12, 2) == 1
+        # 984 of the 992 usable windows are taken, like the shipped book (SURVEY D.2)
+        fw = {(int(r[j]), int(r[(j + 1) % 12])) for r in book for j in range(12)}
+        assert len(fw) == 41 * 12
+    for cols, fsz in ((15, 3), (18, 4)):
+        book = synth.generate_codebook_dfs(cols, fsz, 100, seed=7)
+        assert book.shape == (100, cols) and synth.check_codebook(book, fsz)
+    broken = synth.generate_codebook_dfs(12, 2, 10).copy()
+    broken[1] = broken[0]
+    assert lib.ctag_check_codebook(vp(np.ascontiguousarray(broken, np.int32)), 10, 12, 2) == 0
