@@ -411,10 +411,13 @@ static int detect_batch_host(ctag_detector* d, const void* frames, int n, int w,
   if (d->chunk_frames > 0) chunk = d->chunk_frames < n ? d->chunk_frames : n;
   int done = 0, queued = 0;
   int q_first[kMaxSlots], q_count[kMaxSlots];
+  // at most three chunks in flight: copies queued on more streams share the copy engine and every chunk arrives later
+  // (64 4K BGR frames: 29.8 ms with 3 or 4, 31.2 ms with 6).  The synchronous calls therefore rotate over the first three
+  // workspaces only (nothing is pending at entry), which also keeps the staging memory to three buffers.
+  const int ring = kSlots < 3 ? kSlots : 3;
+  d->next_enqueue = d->next_collect = 0;
   while (done < n) {
-    // at most three chunks in flight: copies queued on more streams share the copy engine and every chunk arrives later
-    // (64 4K BGR frames: 29.8 ms with 3 or 4, 31.2 ms with 6)
-    while (queued < n && d->in_flight < (kSlots < 3 ? kSlots : 3)) {
+    while (queued < n && d->in_flight < ring) {
       const int c = n - queued < chunk ? n - queued : chunk;
       Slot* s = &d->slot[d->next_enqueue];
       if (d->debug_fail_chunk >= 0 && queued / chunk == d->debug_fail_chunk) {
@@ -439,7 +442,7 @@ static int detect_batch_host(ctag_detector* d, const void* frames, int n, int w,
       if (rc != CTAG_OK) return rc;
       q_first[d->next_enqueue] = queued;
       q_count[d->next_enqueue] = c;
-      d->next_enqueue = (d->next_enqueue + 1) % kSlots;
+      d->next_enqueue = (d->next_enqueue + 1) % ring;
       d->in_flight += 1;
       queued += c;
     }
@@ -447,7 +450,7 @@ static int detect_batch_host(ctag_detector* d, const void* frames, int n, int w,
     Slot* s = &d->slot[si];
     const int first = q_first[si], c = q_count[si];
     d->last = si;
-    d->next_collect = (d->next_collect + 1) % kSlots;
+    d->next_collect = (d->next_collect + 1) % ring;
     d->in_flight -= 1;
     rc = collect_slot(d, s, out ? out + (size_t)first * cap_per_frame : nullptr, cap_per_frame, n_out ? n_out + first : nullptr,
                       info ? info + first : nullptr);
@@ -459,6 +462,7 @@ static int detect_batch_host(ctag_detector* d, const void* frames, int n, int w,
       }
     done += c;
   }
+  d->next_enqueue = d->next_collect = 0;
   return CTAG_OK;
 }
 
@@ -615,8 +619,10 @@ static int detect_batch_jpeg(ctag_detector* d, const uint8_t* const* jpeg, const
   if (d->chunk_frames > 0) chunk = d->chunk_frames < n ? d->chunk_frames : n;
   int done = 0, queued = 0, backend = 0;
   int q_first[kMaxSlots], q_count[kMaxSlots];
+  const int ring = kSlots < 3 ? kSlots : 3;  // as in detect_batch_host: three workspaces, nothing pending at entry
+  d->next_enqueue = d->next_collect = 0;
   while (done < n) {
-    while (queued < n && d->in_flight < (kSlots < 3 ? kSlots : 3)) {
+    while (queued < n && d->in_flight < ring) {
       const int c = n - queued < chunk ? n - queued : chunk;
       Slot* s = &d->slot[d->next_enqueue];
       int rc = CTAG_ERR_UNSUPPORTED;
@@ -643,7 +649,7 @@ static int detect_batch_jpeg(ctag_detector* d, const uint8_t* const* jpeg, const
       if (rc != CTAG_OK) return rc;
       q_first[d->next_enqueue] = queued;
       q_count[d->next_enqueue] = c;
-      d->next_enqueue = (d->next_enqueue + 1) % kSlots;
+      d->next_enqueue = (d->next_enqueue + 1) % ring;
       d->in_flight += 1;
       queued += c;
     }
@@ -651,7 +657,7 @@ static int detect_batch_jpeg(ctag_detector* d, const uint8_t* const* jpeg, const
     Slot* s = &d->slot[si];
     const int first = q_first[si], c = q_count[si];
     d->last = si;
-    d->next_collect = (d->next_collect + 1) % kSlots;
+    d->next_collect = (d->next_collect + 1) % ring;
     d->in_flight -= 1;
     int rc = collect_slot(d, s, out ? out + (size_t)first * cap_per_frame : nullptr, cap_per_frame, n_out ? n_out + first : nullptr,
                           info ? info + first : nullptr);
