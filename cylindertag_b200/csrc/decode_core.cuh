@@ -309,9 +309,11 @@ CT_HD int organize_and_decode(const FeatureRec* feats, int nf, const int* state,
     if (decode_ok) {
       // ---- match_dictionary (:1269-1324): coverage of every (direction, row, shift) in parallel ... ----
       const int* cd = sc.cover + 2 * srows * scols;
+      // (dir, i, j) of entry t = ln.id, ln.id + ln.n, ... kept by carries instead of two divisions per entry
+      int dir = 0, i = ln.id / scols, j = ln.id - (ln.id / scols) * scols;
+      while (i >= srows) i -= srows, ++dir;
+      const int step_i = ln.n / scols, step_j = ln.n - step_i * scols;
       for (int t = ln.id; t < 2 * srows * scols; t += ln.n) {
-        int dir = t / (srows * scols), rc = t - dir * srows * scols;
-        int i = rc / scols, j = rc - i * scols;
         int cov = 0;
         const int* row = state + i * scols;
         if (dir == 0) {
@@ -337,6 +339,10 @@ CT_HD int organize_and_decode(const FeatureRec* feats, int nf, const int* state,
           }
         }
         sc.cover[t] = cov;
+        j += step_j;
+        i += step_i;
+        if (j >= scols) j -= scols, ++i;
+        while (i >= srows) i -= srows, ++dir;
       }
       w_sync();
       // ---- ... then the max / second bookkeeping of the reference's single sequential scan

@@ -21,6 +21,12 @@ __global__ void __launch_bounds__(32) pair_kernel(const float* __restrict__ quad
                                                   int quad_cap, QuadGeom* __restrict__ geom, FeatureRec* __restrict__ feats,
                                                   int feat_cap, int feature_size, int* __restrict__ fstate /* [frame][4] */) {
   __shared__ uint8_t visited[CTAG_MAX_FRAME_QUADS];
+  // the greedy search reads every quad O(Q / 32) times along ONE dependent chain: frames with up to kPairSmem quads (all
+  // but pathological ones) keep corners and derived geometry in shared memory, where a read costs tens of cycles
+  // instead of an L2 round trip
+  constexpr int kPairSmem = 256;
+  __shared__ float s_q[kPairSmem * 8];
+  __shared__ QuadGeom s_g[kPairSmem];
   const int fr = blockIdx.x, lane = threadIdx.x;
   const int nq_true = n_quads[fr];
   const bool overflow_q = nq_true > quad_cap;  // the reference's isVisited[1000] would overflow (SURVEY C-4)
@@ -28,6 +34,13 @@ __global__ void __launch_bounds__(32) pair_kernel(const float* __restrict__ quad
   const float* Q = quads + (size_t)fr * quad_cap * 8;
   QuadGeom* G = geom + (size_t)fr * quad_cap;
   FeatureRec* F = feats + (size_t)fr * feat_cap;
+  const bool in_smem = nq <= kPairSmem;
+  if (in_smem) {
+    for (int i = lane; i < 8 * nq; i += 32) s_q[i] = Q[i];
+    __syncwarp();
+    Q = s_q;
+    G = s_g;
+  }
   for (int i = lane; i < nq; i += 32) {
     QuadGeom g;
     quad_geom(Q + 8 * i, &g);
@@ -161,8 +174,24 @@ __global__ void __launch_bounds__(32) decode_kernel(const FeatureRec* __restrict
   sc.mk = &s_mk;
   const int nf = fstate[fr * 4 + 2];
   int ngroups = 0, flagged = 0, stale = 0, nm = 0;
+  // the frame's features (at most CTAG_MAX_FRAME_FEATURES records of 84 bytes) move to shared memory first: everything
+  // below is one dependent chain on lane 0 and reads them over and over
+  __shared__ FeatureRec s_feats[CTAG_MAX_FRAME_FEATURES];
+  {
+    const int* src = reinterpret_cast<const int*>(feats + (size_t)fr * feat_cap);
+    int* dst = reinterpret_cast<int*>(s_feats);
+    const int words = (nf < CTAG_MAX_FRAME_FEATURES ? nf : CTAG_MAX_FRAME_FEATURES) * (int)(sizeof(FeatureRec) / 4);
+    for (int i = lane; i < words; i += 32) dst[i] = src[i];
+    __syncwarp();
+  }
+  // ... and so does the dictionary (behind the coverage table): the match reads every entry up to 20 times
+  int* s_state = sc.cover + 2 * srows * scols + 32;
+  if (nf > 0) {
+    for (int i = lane; i < srows * scols; i += 32) s_state[i] = state[i];
+    __syncwarp();
+  }
   if (nf > 0)
-    nm = organize_and_decode(feats + (size_t)fr * feat_cap, nf, state, srows, scols, fsz, Lanes{lane, 32}, sc,
+    nm = organize_and_decode(nf <= CTAG_MAX_FRAME_FEATURES ? s_feats : feats + (size_t)fr * feat_cap, nf, s_state, srows, scols, fsz, Lanes{lane, 32}, sc,
                              markers + (size_t)fr * marker_cap, marker_cap, fr, &ngroups, &flagged, &stale);
   // pack this frame's markers behind those of the other frames (one D2H copy for the whole batch)
   const int nstore = nm < marker_cap ? nm : marker_cap;
@@ -195,7 +224,7 @@ __global__ void __launch_bounds__(32) decode_kernel(const FeatureRec* __restrict
 
 size_t sizeof_quad_geom() { return sizeof(QuadGeom); }
 size_t sizeof_feature_rec() { return sizeof(FeatureRec); }
-size_t decode_smem_bytes(int srows, int scols) { return sizeof(int) * (384 + 32 + 2 * (size_t)srows * scols + 32); }
+size_t decode_smem_bytes(int srows, int scols) { return sizeof(int) * (384 + 32 + 3 * (size_t)srows * scols + 32); }
 
 int launch_features(int n, const FrameGeom& g, const float* quads, const int* n_quads, int quad_cap, void* geom, void* feats,
                     int feat_cap, int feature_size, int* fstate, const uint8_t* gray, size_t gray_pitch, size_t gray_fstride,

@@ -12,6 +12,11 @@ struct QuadGeom {
   float cx, cy;
   float d[4];
   float ang1, ang2;
+  // Angles that depend on the quad alone, computed once per quad (in parallel over the quads) instead of inside the
+  // sequential pairing loop: ea = the four edge directions pair_side may pick (:495,:499,:508,:512: c0-c3, c1-c2, c0-c1,
+  // c2-c3), ca = direction from each corner to the centre (featureOrganization, :577-578).
+  float ea[4];
+  float ca[4];
 };
 
 CT_HD float dist_pts(float ax, float ay, float bx, float by) {  // distance_2points (:1252-1254)
@@ -26,8 +31,15 @@ CT_HD void quad_geom(const float* q, QuadGeom* g) {
     g->d[j] = sqrtf((q[2 * j] - q[2 * k]) * (q[2 * j] - q[2 * k]) + (q[2 * j + 1] - q[2 * k + 1]) * (q[2 * j + 1] - q[2 * k + 1]));
   }
   // plain arithmetic means of two angles, no wrap handling (SURVEY C-14)
-  g->ang1 = (float)((atan2_deg(q[1] - q[3], q[0] - q[2]) + atan2_deg(q[7] - q[5], q[6] - q[4])) / 2);
-  g->ang2 = (float)((atan2_deg(q[3] - q[5], q[2] - q[4]) + atan2_deg(q[1] - q[7], q[0] - q[6])) / 2);
+  const double a01 = atan2_deg(q[1] - q[3], q[0] - q[2]), a12 = atan2_deg(q[3] - q[5], q[2] - q[4]),
+               a03 = atan2_deg(q[1] - q[7], q[0] - q[6]);
+  g->ang1 = (float)((a01 + atan2_deg(q[7] - q[5], q[6] - q[4])) / 2);
+  g->ang2 = (float)((a12 + a03) / 2);
+  g->ea[0] = (float)a03;
+  g->ea[1] = (float)a12;
+  g->ea[2] = (float)a01;
+  g->ea[3] = (float)atan2_deg(q[5] - q[7], q[4] - q[6]);
+  for (int i = 0; i < 4; ++i) g->ca[i] = (float)atan2_deg(g->cy - q[2 * i + 1], g->cx - q[2 * i]);
 }
 
 // |d| < thr  or  ||d| - 180| < thr  or  ||d| - 360| < thr   (:490 and friends)
@@ -37,21 +49,19 @@ CT_HD bool near_mod(float diff, float thr) {
 }
 
 // role of one quad in a candidate pair (:490-515 / :516-541): returns tag; the second test overrides the first
-CT_HD bool pair_side(const float* q, const QuadGeom& g, float fa, float* lng, float* sht, float* ea) {
+CT_HD bool pair_side(const float*, const QuadGeom& g, float fa, float* lng, float* sht, float* ea) {
   bool tag = false;
   if (near_mod(fa - g.ang1, 5.0f)) {
     tag = true;
     *lng = (g.d[0] + g.d[2]) / 2;
     *sht = g.d[1] < g.d[3] ? g.d[1] : g.d[3];  // std::min(a,b): b < a ? b : a -- same value for floats
-    if (g.d[1] < g.d[3]) *ea = (float)atan2_deg(q[1] - q[7], q[0] - q[6]);
-    else *ea = (float)atan2_deg(q[3] - q[5], q[2] - q[4]);
+    *ea = g.d[1] < g.d[3] ? g.ea[0] : g.ea[1];
   }
   if (near_mod(fa - g.ang2, 5.0f)) {
     tag = true;
     *sht = g.d[0] < g.d[2] ? g.d[0] : g.d[2];
     *lng = (g.d[1] + g.d[3]) / 2;
-    if (g.d[0] > g.d[2]) *ea = (float)atan2_deg(q[1] - q[3], q[0] - q[2]);
-    else *ea = (float)atan2_deg(q[5] - q[7], q[4] - q[6]);
+    *ea = g.d[0] > g.d[2] ? g.ea[2] : g.ea[3];
   }
   return tag;
 }
@@ -74,11 +84,8 @@ CT_HD bool pair_test(const float* qi, const QuadGeom& gi, const float* qj, const
 // featureOrganization (:571-598): rotate both quads so that corners 2,3 / 6,7 face each other; out = 8 corners + centre
 CT_HD void feature_organize(const float* q1, const float* q2, const QuadGeom& g1, const QuadGeom& g2, float fa, float* out16,
                             float* center2) {
-  float a1[4], a2[4];
-  for (int i = 0; i < 4; ++i) {
-    a1[i] = (float)atan2_deg(g1.cy - q1[2 * i + 1], g1.cx - q1[2 * i]);
-    a2[i] = (float)atan2_deg(g2.cy - q2[2 * i + 1], g2.cx - q2[2 * i]);
-  }
+  const float* a1 = g1.ca;
+  const float* a2 = g2.ca;
   float amax = 0, amin = 360;
   int p1 = -1, p2 = -1;
   for (int i = 0; i < 4; ++i) {

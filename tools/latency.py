@@ -23,9 +23,8 @@ if a.res == "testbmp":
     det = Detector(marker_path=os.path.join(data, "CTag_2f12c.marker"))
 else:
     w, h = {"4k": (3840, 2160), "1080p": (1920, 1080)}[a.res]
-    sys.path.insert(0, ROOT)
-    import bench
-    state, fs = bench.load_dictionary()
+    from cylindertag_b200 import workloads
+    state, fs = workloads.codebook("2f12c")
     gray, _ = synth.synthetic_frame(2000, w, h, state, 6, channels=1)
     det = Detector(state=state, feature_size=fs)
 for _ in range(10):
