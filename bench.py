@@ -103,8 +103,16 @@ def bind_to_gpu_numa_node(local):
                              capture_output=True, text=True, timeout=20).stdout.strip().lower()
         bus = bus[-12:] if len(bus) > 12 else bus  # 00000000:1b:00.0 -> 0000:1b:00.0
         node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        guessed = False
         if node < 0:
-            return {"gpu_bus": bus, "numa_node": node, "bound": False}
+            # the container hides the GPU's node: spread the ranks over the online nodes in order (HGX boxes hang GPUs 0-3
+            # off socket 0 and 4-7 off socket 1), which at least keeps the pinned buffers of one rank on one node
+            nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+            world = int(os.environ.get("WORLD_SIZE", "1"))
+            if len(nodes) < 2 or world < 2:
+                return {"gpu_bus": bus, "numa_node": node, "bound": False, "nodes_online": len(nodes)}
+            node = nodes[min(local * len(nodes) // world, len(nodes) - 1)]
+            guessed = True
         cpus = []
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             a, _, b = part.partition("-")
@@ -113,15 +121,17 @@ def bind_to_gpu_numa_node(local):
         if not allowed:
             return {"gpu_bus": bus, "numa_node": node, "bound": False}
         os.sched_setaffinity(0, allowed)
-        return {"gpu_bus": bus, "numa_node": node, "bound": True, "cpus": len(allowed)}
+        return {"gpu_bus": bus, "numa_node": node, "bound": True, "cpus": len(allowed), "node_guessed_from_rank": guessed}
     except Exception as exc:  # pragma: no cover
         return {"bound": False, "error": str(exc)}
 
 
-def load_ring(kind, rank, world, barrier=None):
+def load_ring(kind, rank, world, barrier=None, limit=0):
     """The distinct frames of a workload, rendered once per box (cached under /tmp) with the ranks sharing the work."""
     from cylindertag_b200 import workloads as wl
     jobs = [(4, "2f12c", i) for i in range(wl.CONFIG5_DISTINCT)] if kind == "config5" else [(3, None, i) for i in range(wl.CONFIG3_FRAMES)]
+    if limit:
+        jobs = jobs[:limit]
     if world > 1:
         mine = [j for k, j in enumerate(jobs) if k % world == rank]
         wl.render_many(mine, workers=max(1, (os.cpu_count() or 8) // world))
@@ -148,7 +158,7 @@ def run_reference_arm(a):
     from cylindertag_b200 import workloads as wl
     cores = os.cpu_count() or 1
     state, fs = wl.codebook("2f12c")
-    frames = np.stack(load_ring("config5", 0, 1))
+    frames = np.stack(load_ring("config5", 0, 1, limit=a.ring))
     for _ in range(min(a.warmup, 1)):
         cpu_reference_pass(frames[:cores], state, fs, cores)
     t0, fps = time.perf_counter(), []
@@ -337,6 +347,7 @@ def main():
     ap.add_argument("--no-traffic", action="store_true")
     ap.add_argument("--sustain", type=float, default=2.0, help="seconds of the sustained loop after the K timed steps")
     ap.add_argument("--traffic-probe", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--ring", type=int, default=0, help=argparse.SUPPRESS)  # tests: first N frames of the ring (reference arm)
     a = ap.parse_args()
     if a.traffic_probe:
         return traffic_probe()

@@ -6,7 +6,9 @@
 // block index yields the reference order directly: component order == ascending root index.
 //
 //   ccl_local  : one CTA per 32x32-block tile (64x64 px).  Union-find in shared memory, partial stats per local
-//                root, one label word per 2x2 block written to HBM (not one per pixel).
+//                root, one label word per 2x2 block written to HBM (not one per pixel) -- for tiles that hold
+//                foreground; an empty tile writes nothing, and a flag byte per (block row, tile column) tells
+//                ccl_final which label segments exist, so empty image regions cost one read of the binary image.
 //   ccl_merge  : unions across tile borders (global atomicMin union-find over the local roots only).
 //   ccl_final  : flattens every block label to its global root, folds the partial stats of merged local roots
 //                into the global root, lists the global roots of each 1024-block span in ascending order
@@ -68,7 +70,8 @@ __device__ __forceinline__ void uf_unite(int* L, int a, int b) {
 __global__ void __launch_bounds__(256) ccl_local_kernel(const uint8_t* __restrict__ bin, size_t bin_fstride, FrameGeom g,
                                                         int* __restrict__ labels, int* __restrict__ st_area,
                                                         int* __restrict__ st_x0, int* __restrict__ st_y0,
-                                                        int* __restrict__ st_x1, int* __restrict__ st_y1) {
+                                                        int* __restrict__ st_x1, int* __restrict__ st_y1,
+                                                        uint8_t* __restrict__ seg_flags, int seg_pitch, size_t seg_fstride) {
   __shared__ int L[1024];
   __shared__ uint8_t pat[1024];
   __shared__ int sA[1024], sX0[1024], sY0[1024], sX1[1024], sY1[1024];
@@ -90,18 +93,11 @@ __global__ void __launch_bounds__(256) ccl_local_kernel(const uint8_t* __restric
       if (bx0 + k >= g.bw) p4[k] = 0;
     }
   }
-  // empty tile: only the background labels have to be written
-  if (!__syncthreads_or(p4[0] | p4[1] | p4[2] | p4[3])) {
-    if (by < g.bh && bx0 < g.bw) {
-      int* dst = labels + base + (size_t)by * g.bw + bx0;
-      if (bx0 + 3 < g.bw && ((base + (size_t)by * g.bw + bx0) & 3) == 0) {
-        *reinterpret_cast<int4*>(dst) = make_int4(-1, -1, -1, -1);
-      } else {
-        for (int k = 0; k < 4 && bx0 + k < g.bw; ++k) dst[k] = -1;
-      }
-    }
-    return;
-  }
+  // Empty tile (the common case): nothing is written at all.  seg_flags[by][tile column] (zeroed per batch) says which
+  // 32-block row segments belong to a tile that holds foreground; only those have valid labels, and every reader of the
+  // label array either checks the flag (ccl_final) or looks at foreground pixels only (ccl_merge, the quad stage).
+  if (!__syncthreads_or(p4[0] | p4[1] | p4[2] | p4[3])) return;
+  if (tq == 0 && by < g.bh) seg_flags[(size_t)fr * seg_fstride + (size_t)by * seg_pitch + blockIdx.x] = 1;
   const int l0 = ty * 32 + 4 * tq;  // tile-local index of the first owned block
   // Horizontal runs first: block i is glued to block i-1 when the right column of i-1 and the left column of i both
   // hold a pixel (any such pair is 8-adjacent).  Every block starts out pointing at the first block of its run, so
@@ -293,7 +289,8 @@ __global__ void __launch_bounds__(256) ccl_final_kernel(FrameGeom g, int* __rest
                                                         int* __restrict__ st_x0, int* __restrict__ st_y0,
                                                         int* __restrict__ st_x1, int* __restrict__ st_y1,
                                                         int* __restrict__ roots_tmp, int* __restrict__ span_count,
-                                                        int spans_per_frame) {
+                                                        int spans_per_frame, const uint8_t* __restrict__ seg_flags, int seg_pitch,
+                                                        size_t seg_fstride) {
   __shared__ int warp_cnt[8];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const int fr = blockIdx.y;
@@ -301,12 +298,20 @@ __global__ void __launch_bounds__(256) ccl_final_kernel(FrameGeom g, int* __rest
   int* lab = labels + base;
   const int i0 = blockIdx.x * 1024 + 4 * t;
   int e4[4] = {-1, -1, -1, -1};
-  if (i0 + 3 < g.nblocks && ((base + i0) & 3) == 0) {
-    const int4 v = *reinterpret_cast<const int4*>(lab + i0);
-    e4[0] = v.x, e4[1] = v.y, e4[2] = v.z, e4[3] = v.w;
+  const uint8_t* sf = seg_flags + (size_t)fr * seg_fstride;
+  if (i0 + 3 < g.nblocks && ((base + i0) & 3) == 0 && (g.bw & 3) == 0) {
+    // the four blocks lie in one row and one tile column: one flag byte decides whether their labels exist at all
+    const int by = i0 / g.bw, bx = i0 - by * g.bw;
+    if (sf[(size_t)by * seg_pitch + (bx >> 5)]) {
+      const int4 v = *reinterpret_cast<const int4*>(lab + i0);
+      e4[0] = v.x, e4[1] = v.y, e4[2] = v.z, e4[3] = v.w;
+    }
   } else {
     for (int k = 0; k < 4; ++k)
-      if (i0 + k < g.nblocks) e4[k] = lab[i0 + k];
+      if (i0 + k < g.nblocks) {
+        const int by = (i0 + k) / g.bw, bx = (i0 + k) - by * g.bw;
+        if (sf[(size_t)by * seg_pitch + (bx >> 5)]) e4[k] = lab[i0 + k];
+      }
   }
   int nroot = 0;
   unsigned rootmask = 0;
@@ -435,15 +440,21 @@ __global__ void __launch_bounds__(1024) ccl_list_kernel(FrameGeom g, const int* 
   }
 }
 
+size_t ccl_seg_flag_bytes(const FrameGeom& g) { return (size_t)((g.bw + 31) / 32) * g.bh; }
+
 int launch_ccl(const uint8_t* bin, size_t bin_fstride, int n, const FrameGeom& g, int* labels, int* st_area, int* st_x0,
-               int* st_y0, int* st_x1, int* st_y1, int* roots_tmp, int* span_count, int* legal, int legal_cap,
+               int* st_y0, int* st_x1, int* st_y1, int* roots_tmp, int* span_count, uint8_t* seg_flags, int* legal, int legal_cap,
                int* counters, cudaStream_t stream, int* launches) {
   dim3 tiles((g.bw + 31) / 32, (g.bh + 31) / 32, n);
-  ccl_local_kernel<<<tiles, 256, 0, stream>>>(bin, bin_fstride, g, labels, st_area, st_x0, st_y0, st_x1, st_y1);
+  const int seg_pitch = (g.bw + 31) / 32;
+  const size_t seg_fstride = ccl_seg_flag_bytes(g);
+  CTAG_CUDA_CHECK(cudaMemsetAsync(seg_flags, 0, seg_fstride * n, stream));
+  ccl_local_kernel<<<tiles, 256, 0, stream>>>(bin, bin_fstride, g, labels, st_area, st_x0, st_y0, st_x1, st_y1, seg_flags, seg_pitch,
+                                               seg_fstride);
   ccl_merge_kernel<<<tiles, 64, 0, stream>>>(bin, bin_fstride, g, labels);
   int spans = (g.nblocks + 1023) / 1024;
   ccl_final_kernel<<<dim3(spans, n), 256, 0, stream>>>(g, labels, st_area, st_x0, st_y0, st_x1, st_y1, roots_tmp,
-                                                        span_count, spans);
+                                                        span_count, spans, seg_flags, seg_pitch, seg_fstride);
   ccl_list_kernel<<<n, 1024, 0, stream>>>(g, st_area, st_x0, st_y0, st_x1, st_y1, roots_tmp, span_count, spans, legal,
                                           legal_cap, counters);
   CTAG_CUDA_CHECK(cudaGetLastError());

@@ -20,8 +20,9 @@ int launch_front_generic(const void* frames_dev, int n, const FrameGeom& g, int 
 
 // K2/K3 (ccl.cu): block-based union-find labelling, stats, ordered legal-component list.
 // legal[frame][k] = {root, area, x0, y0, x1, y1}; counters[frame] = {n_components, n_legal, overflow, 0}.
+size_t ccl_seg_flag_bytes(const FrameGeom& g);
 int launch_ccl(const uint8_t* bin, size_t bin_fstride, int n, const FrameGeom& g, int* labels, int* st_area, int* st_x0,
-               int* st_y0, int* st_x1, int* st_y1, int* roots_tmp, int* span_count, int* legal, int legal_cap,
+               int* st_y0, int* st_x1, int* st_y1, int* roots_tmp, int* span_count, uint8_t* seg_flags, int* legal, int legal_cap,
                int* counters, cudaStream_t stream, int* launches);
 
 // K4 (quad.cu): edges (warp per component) -> Welsch fits (thread per restart, merge, exact fallback) -> corner

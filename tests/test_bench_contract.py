@@ -1,4 +1,4 @@
-"""bench.py's reference arm (`--impl reference`: the CPU restatement on the host cores, the driver's baseline run) on a
+"""bench.py's reference arm (`--impl reference`: the reference's own code (oracle/_ref) on the host cores, the driver's baseline run) on a
 tiny configuration -- CPU only: it must print ONE JSON line with the contract's keys and run without a GPU.  Also the
 torchrun case: under WORLD_SIZE > 1 rank 0 alone reports, the other ranks exit quietly."""
 import json
@@ -7,8 +7,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-ARGS = ["--impl", "reference", "--steps", "1", "--warmup", "0", "--res", "1080p", "--batch", "4", "--distinct", "2",
-        "--markers", "2"]
+ARGS = ["--impl", "reference", "--steps", "1", "--warmup", "0", "--ring", "2"]
 
 
 def _run(env_extra=None):
@@ -28,7 +27,7 @@ def test_reference_arm_prints_the_contract_line():
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
     assert d["vs_baseline"] is None and d["data"] == "synthetic" and "workload" in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
