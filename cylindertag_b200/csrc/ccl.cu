@@ -67,7 +67,7 @@ __device__ __forceinline__ void uf_unite(int* L, int a, int b) {
 
 // 256 threads per 32x32-block tile; thread t owns the four horizontally adjacent blocks (4*(t&7) .. +3, t>>3) so that the
 // binary image is read with 8-byte loads and empty tiles (the common case) write their labels with 16-byte stores.
-__global__ void __launch_bounds__(256) ccl_local_kernel(const uint8_t* __restrict__ bin, size_t bin_fstride, FrameGeom g,
+__global__ void __launch_bounds__(256, 8) ccl_local_kernel(const uint8_t* __restrict__ bin, size_t bin_fstride, FrameGeom g,
                                                         int* __restrict__ labels, int* __restrict__ st_area,
                                                         int* __restrict__ st_x0, int* __restrict__ st_y0,
                                                         int* __restrict__ st_x1, int* __restrict__ st_y1,
@@ -79,12 +79,18 @@ __global__ void __launch_bounds__(256) ccl_local_kernel(const uint8_t* __restric
   const int bx0 = blockIdx.x * 32 + 4 * tq, by = blockIdx.y * 32 + ty, fr = blockIdx.z;
   const size_t base = (size_t)fr * g.nblocks;
   int p4[4] = {0, 0, 0, 0};
+  uint2 a = make_uint2(0u, 0u), b = make_uint2(0u, 0u);
   if (by < g.bh && bx0 < g.bw) {
     // 8 pixels of two rows; bpitch is a multiple of 16 and columns >= hw inside the pitch are zero (front kernel)
     const uint8_t* r0 = bin + (size_t)fr * bin_fstride + (size_t)(2 * by) * g.bpitch + 2 * bx0;
-    const uint2 a = *reinterpret_cast<const uint2*>(r0);
-    uint2 b = make_uint2(0u, 0u);
+    a = *reinterpret_cast<const uint2*>(r0);
     if (2 * by + 1 < g.hh) b = *reinterpret_cast<const uint2*>(r0 + g.bpitch);
+  }
+  // Empty tile (the common case): nothing is written at all.  seg_flags[by][tile column] (zeroed per batch) says which
+  // 32-block row segments belong to a tile that holds foreground; only those have valid labels, and every reader of the
+  // label array either checks the flag (ccl_merge, ccl_final) or looks at foreground pixels only (the quad stage).
+  if (!__syncthreads_or((a.x | a.y | b.x | b.y) != 0u)) return;
+  {
     const uint32_t aw[2] = {a.x, a.y}, bw_[2] = {b.x, b.y};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -93,10 +99,6 @@ __global__ void __launch_bounds__(256) ccl_local_kernel(const uint8_t* __restric
       if (bx0 + k >= g.bw) p4[k] = 0;
     }
   }
-  // Empty tile (the common case): nothing is written at all.  seg_flags[by][tile column] (zeroed per batch) says which
-  // 32-block row segments belong to a tile that holds foreground; only those have valid labels, and every reader of the
-  // label array either checks the flag (ccl_final) or looks at foreground pixels only (ccl_merge, the quad stage).
-  if (!__syncthreads_or(p4[0] | p4[1] | p4[2] | p4[3])) return;
   if (tq == 0 && by < g.bh) seg_flags[(size_t)fr * seg_fstride + (size_t)by * seg_pitch + blockIdx.x] = 1;
   const int l0 = ty * 32 + 4 * tq;  // tile-local index of the first owned block
   // Horizontal runs first: block i is glued to block i-1 when the right column of i-1 and the left column of i both
@@ -251,8 +253,11 @@ __device__ __forceinline__ void gunite(int* lab, int a, int b) {
 
 // 64 threads per tile: threads 0..31 = top row of the tile (checks UL,U,UR), 32..63 = left column (checks L,UL,DL)
 __global__ void __launch_bounds__(64) ccl_merge_kernel(const uint8_t* __restrict__ bin, size_t bin_fstride, FrameGeom g,
-                                                       int* __restrict__ labels) {
+                                                       int* __restrict__ labels, const uint8_t* __restrict__ seg_flags,
+                                                       int seg_pitch, size_t seg_fstride) {
   const int t = threadIdx.x, fr = blockIdx.z;
+  // a tile without foreground has nothing on its border either (its first row is always inside the frame)
+  if (!seg_flags[(size_t)fr * seg_fstride + (size_t)(blockIdx.y * 32) * seg_pitch + blockIdx.x]) return;
   const uint8_t* b = bin + (size_t)fr * bin_fstride;
   int* lab = labels + (size_t)fr * g.nblocks;
   int bx, by;
@@ -283,83 +288,95 @@ __global__ void __launch_bounds__(64) ccl_merge_kernel(const uint8_t* __restrict
   }
 }
 
-// Four consecutive blocks per thread (16-byte label loads; background runs are skipped at once).
-// roots_tmp[span*1024 + k] = k-th global root (ascending) of the 1024-block span; span_count[span].
+// One warp per 1024-block span, in eight chunks of 128 blocks (four consecutive blocks per lane: 16-byte label loads).
+// A chunk whose row segments hold no foreground (seg_flags) is not read; a span without any ends after the flag loads.
+// roots_tmp[span*1024 + k] = k-th global root (ascending) of the span; span_count[span].
 __global__ void __launch_bounds__(256) ccl_final_kernel(FrameGeom g, int* __restrict__ labels, int* __restrict__ st_area,
                                                         int* __restrict__ st_x0, int* __restrict__ st_y0,
                                                         int* __restrict__ st_x1, int* __restrict__ st_y1,
                                                         int* __restrict__ roots_tmp, int* __restrict__ span_count,
                                                         int spans_per_frame, const uint8_t* __restrict__ seg_flags, int seg_pitch,
                                                         size_t seg_fstride) {
-  __shared__ int warp_cnt[8];
-  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  const int fr = blockIdx.y;
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31, fr = blockIdx.y;
+  const int span = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (span >= spans_per_frame) return;
   const size_t base = (size_t)fr * g.nblocks;
   int* lab = labels + base;
-  const int i0 = blockIdx.x * 1024 + 4 * t;
-  int e4[4] = {-1, -1, -1, -1};
   const uint8_t* sf = seg_flags + (size_t)fr * seg_fstride;
-  if (i0 + 3 < g.nblocks && ((base + i0) & 3) == 0 && (g.bw & 3) == 0) {
-    // the four blocks lie in one row and one tile column: one flag byte decides whether their labels exist at all
-    const int by = i0 / g.bw, bx = i0 - by * g.bw;
-    if (sf[(size_t)by * seg_pitch + (bx >> 5)]) {
-      const int4 v = *reinterpret_cast<const int4*>(lab + i0);
-      e4[0] = v.x, e4[1] = v.y, e4[2] = v.z, e4[3] = v.w;
-    }
-  } else {
-    for (int k = 0; k < 4; ++k)
-      if (i0 + k < g.nblocks) {
-        const int by = (i0 + k) / g.bw, bx = (i0 + k) - by * g.bw;
-        if (sf[(size_t)by * seg_pitch + (bx >> 5)]) e4[k] = lab[i0 + k];
-      }
-  }
-  int nroot = 0;
-  unsigned rootmask = 0;
-  if ((e4[0] & e4[1] & e4[2] & e4[3]) >= 0) {  // at least one foreground block (labels are >= 0, background is -1)
+  // with these two the four blocks of a lane lie in one row and one tile column, 16-byte aligned
+  const bool vec = (base & 3) == 0 && (g.bw & 3) == 0;
+  unsigned live = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int e = e4[k], i = i0 + k;
-      if (e < 0) continue;
-      const int r = gfind(lab, i);
-      if (e & kTag) {
-        lab[i] = r;
-      } else if (r != i) {
-        // a tile-local root that was merged into another tree: fold its partial stats into the global root
-        atomicAdd(&st_area[base + r], st_area[base + i]);
-        atomicMin(&st_x0[base + r], st_x0[base + i]);
-        atomicMin(&st_y0[base + r], st_y0[base + i]);
-        atomicMax(&st_x1[base + r], st_x1[base + i]);
-        atomicMax(&st_y1[base + r], st_y1[base + i]);
-        lab[i] = r;
-      } else {
-        rootmask |= 1u << k;
-        ++nroot;
-      }
+  for (int c = 0; c < 8; ++c) {
+    const int i0 = span * 1024 + c * 128 + 4 * lane;
+    if (i0 >= g.nblocks) continue;
+    if (vec && i0 + 3 < g.nblocks) {
+      const int by = i0 / g.bw, bx = i0 - by * g.bw;
+      if (sf[(size_t)by * seg_pitch + (bx >> 5)]) live |= 1u << c;
+    } else {
+      live |= 1u << c;  // ragged: decided block by block below
     }
   }
-  // exclusive prefix of the per-thread root counts over the CTA (warp shuffle scan + 8 warp totals)
-  int inc = nroot;
+  int total = 0;
+  int* out = roots_tmp + base + (size_t)span * 1024;
+  if (__any_sync(kFull, live != 0)) {
+    for (int c = 0; c < 8; ++c) {
+      const bool mine = (live >> c) & 1u;
+      if (!__any_sync(kFull, mine)) continue;
+      const int i0 = span * 1024 + c * 128 + 4 * lane;
+      int e4[4] = {-1, -1, -1, -1};
+      if (mine) {
+        if (vec && i0 + 3 < g.nblocks) {
+          const int4 v = *reinterpret_cast<const int4*>(lab + i0);
+          e4[0] = v.x, e4[1] = v.y, e4[2] = v.z, e4[3] = v.w;
+        } else {
+          for (int k = 0; k < 4; ++k)
+            if (i0 + k < g.nblocks) {
+              const int by = (i0 + k) / g.bw, bx = (i0 + k) - by * g.bw;
+              if (sf[(size_t)by * seg_pitch + (bx >> 5)]) e4[k] = lab[i0 + k];
+            }
+        }
+      }
+      int nroot = 0;
+      unsigned rootmask = 0;
+      if ((e4[0] & e4[1] & e4[2] & e4[3]) >= 0) {  // at least one foreground block (labels are >= 0, background is -1)
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int n = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += n;
-  }
-  if (lane == 31) warp_cnt[wid] = inc;
-  __syncthreads();
-  int woff = 0, total = 0;
+        for (int k = 0; k < 4; ++k) {
+          const int e = e4[k], i = i0 + k;
+          if (e < 0) continue;
+          const int r = gfind(lab, i);
+          if (e & kTag) {
+            lab[i] = r;
+          } else if (r != i) {
+            // a tile-local root that was merged into another tree: fold its partial stats into the global root
+            atomicAdd(&st_area[base + r], st_area[base + i]);
+            atomicMin(&st_x0[base + r], st_x0[base + i]);
+            atomicMin(&st_y0[base + r], st_y0[base + i]);
+            atomicMax(&st_x1[base + r], st_x1[base + i]);
+            atomicMax(&st_y1[base + r], st_y1[base + i]);
+            lab[i] = r;
+          } else {
+            rootmask |= 1u << k;
+            ++nroot;
+          }
+        }
+      }
+      if (!__any_sync(kFull, nroot != 0)) continue;
+      int inc = nroot;  // inclusive prefix of the per-lane root counts
 #pragma unroll
-  for (int w = 0; w < 8; ++w) {
-    const int c = warp_cnt[w];
-    if (w < wid) woff += c;
-    total += c;
-  }
-  if (t == 0) span_count[fr * spans_per_frame + blockIdx.x] = total;
-  if (nroot) {
-    int pos = woff + inc - nroot;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += n;
+      }
+      int pos = total + inc - nroot;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (rootmask & (1u << k)) roots_tmp[base + (size_t)blockIdx.x * 1024 + pos++] = i0 + k;
+      for (int k = 0; k < 4; ++k)
+        if (rootmask & (1u << k)) out[pos++] = i0 + k;
+      total += __shfl_sync(kFull, inc, 31);
+    }
   }
+  if (lane == 0) span_count[fr * spans_per_frame + span] = total;
 }
 
 __device__ __forceinline__ int block_exclusive_scan_1024(int v, int* total, int* sh /*33 ints*/) {
@@ -451,9 +468,9 @@ int launch_ccl(const uint8_t* bin, size_t bin_fstride, int n, const FrameGeom& g
   CTAG_CUDA_CHECK(cudaMemsetAsync(seg_flags, 0, seg_fstride * n, stream));
   ccl_local_kernel<<<tiles, 256, 0, stream>>>(bin, bin_fstride, g, labels, st_area, st_x0, st_y0, st_x1, st_y1, seg_flags, seg_pitch,
                                                seg_fstride);
-  ccl_merge_kernel<<<tiles, 64, 0, stream>>>(bin, bin_fstride, g, labels);
+  ccl_merge_kernel<<<tiles, 64, 0, stream>>>(bin, bin_fstride, g, labels, seg_flags, seg_pitch, seg_fstride);
   int spans = (g.nblocks + 1023) / 1024;
-  ccl_final_kernel<<<dim3(spans, n), 256, 0, stream>>>(g, labels, st_area, st_x0, st_y0, st_x1, st_y1, roots_tmp,
+  ccl_final_kernel<<<dim3((spans + 7) / 8, n), 256, 0, stream>>>(g, labels, st_area, st_x0, st_y0, st_x1, st_y1, roots_tmp,
                                                         span_count, spans, seg_flags, seg_pitch, seg_fstride);
   ccl_list_kernel<<<n, 1024, 0, stream>>>(g, st_area, st_x0, st_y0, st_x1, st_y1, roots_tmp, span_count, spans, legal,
                                           legal_cap, counters);
