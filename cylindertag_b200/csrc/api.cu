@@ -74,6 +74,7 @@ struct Slot {
   size_t stage_bytes = 0;
   std::vector<void*> owned;  // device allocations of the workspace (freed together)
   uint8_t *d_gray = nullptr, *d_bin = nullptr, *d_quad_scratch = nullptr;
+  uint8_t* d_tile_any = nullptr;   // front kernel -> CCL: which 64x64 tiles of the binary image hold foreground
   uint8_t* d_seg_flags = nullptr;  // CCL: which 32-block label segments exist (ccl.cu)
   uint8_t *d_half = nullptr, *d_tiles = nullptr;  // generic-window front end only (allocated on first use)
   size_t tiles_bytes = 0;
@@ -228,6 +229,7 @@ static int ensure_workspace(ctag_detector* d, Slot* s, int n, int w, int h) {
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_roots_tmp, nb));
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_span_count, (size_t)s->spans * cap));
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_seg_flags, ccl_seg_flag_bytes(g) * cap));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_tile_any, ccl_tile_hint_bytes(g) * cap));
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_legal, (size_t)s->legal_cap * 6 * cap));
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_counters, (size_t)4 * cap));
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_prefix, (size_t)cap + 1));
@@ -308,9 +310,12 @@ static int enqueue_on_slot(ctag_detector* d, Slot* s, const void* frames_dev, in
     s->gray_fs = s->gray_fstride;
   }
   cudaStream_t st = s->stream;
+  const uint8_t* tile_any = nullptr;
   if (window == kWin) {
+    CTAG_CUDA_CHECK(cudaMemsetAsync(s->d_tile_any, 0, ccl_tile_hint_bytes(s->geo) * n, st));
+    tile_any = s->d_tile_any;
     rc = launch_front(frames_dev, n, s->geo, channels, pitch, frame_stride, s->d_gray, s->gray_fstride, s->d_bin,
-                      s->bin_fstride, st, s->ev[0]);
+                      s->bin_fstride, ccl_tile_hint(s->geo, s->d_tile_any), st, s->ev[0]);
     s->launches += 1;
   } else {
     CTAG_CUDA_CHECK(cudaEventRecord(s->ev[0], st));
@@ -320,7 +325,7 @@ static int enqueue_on_slot(ctag_detector* d, Slot* s, const void* frames_dev, in
   if (rc != CTAG_OK) return rc;
   CTAG_CUDA_CHECK(cudaEventRecord(s->ev[1], st));
   rc = launch_ccl(s->d_bin, s->bin_fstride, n, s->geo, s->d_labels, s->d_st_area, s->d_st_x0, s->d_st_y0, s->d_st_x1,
-                  s->d_st_y1, s->d_roots_tmp, s->d_span_count, s->d_seg_flags, s->d_legal, s->legal_cap, s->d_counters, st, &s->launches);
+                  s->d_st_y1, s->d_roots_tmp, s->d_span_count, s->d_seg_flags, tile_any, s->d_legal, s->legal_cap, s->d_counters, st, &s->launches);
   if (rc != CTAG_OK) return rc;
   CTAG_CUDA_CHECK(cudaEventRecord(s->ev[2], st));
   rc = launch_quad(n, s->geo, s->d_bin, s->bin_fstride, s->d_labels, s->d_legal, s->legal_cap, s->d_counters, s->d_prefix,

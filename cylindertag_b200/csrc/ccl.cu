@@ -67,16 +67,16 @@ __device__ __forceinline__ void uf_unite(int* L, int a, int b) {
 
 // 256 threads per 32x32-block tile; thread t owns the four horizontally adjacent blocks (4*(t&7) .. +3, t>>3) so that the
 // binary image is read with 8-byte loads and empty tiles (the common case) write their labels with 16-byte stores.
-__global__ void __launch_bounds__(256, 8) ccl_local_kernel(const uint8_t* __restrict__ bin, size_t bin_fstride, FrameGeom g,
-                                                        int* __restrict__ labels, int* __restrict__ st_area,
-                                                        int* __restrict__ st_x0, int* __restrict__ st_y0,
-                                                        int* __restrict__ st_x1, int* __restrict__ st_y1,
-                                                        uint8_t* __restrict__ seg_flags, int seg_pitch, size_t seg_fstride) {
+__device__ __forceinline__ void ccl_local_tile(const uint8_t* __restrict__ bin, size_t bin_fstride, const FrameGeom& g,
+                                               int* __restrict__ labels, int* __restrict__ st_area, int* __restrict__ st_x0,
+                                               int* __restrict__ st_y0, int* __restrict__ st_x1, int* __restrict__ st_y1,
+                                               uint8_t* __restrict__ seg_flags, int seg_pitch, size_t seg_fstride,
+                                               int tile_x, int tile_y, int fr) {
   __shared__ int L[1024];
   __shared__ uint8_t pat[1024];
   __shared__ int sA[1024], sX0[1024], sY0[1024], sX1[1024], sY1[1024];
   const int t = threadIdx.x, tq = t & 7, ty = t >> 3;
-  const int bx0 = blockIdx.x * 32 + 4 * tq, by = blockIdx.y * 32 + ty, fr = blockIdx.z;
+  const int bx0 = tile_x * 32 + 4 * tq, by = tile_y * 32 + ty;
   const size_t base = (size_t)fr * g.nblocks;
   int p4[4] = {0, 0, 0, 0};
   uint2 a = make_uint2(0u, 0u), b = make_uint2(0u, 0u);
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256, 8) ccl_local_kernel(const uint8_t* __rest
       if (bx0 + k >= g.bw) p4[k] = 0;
     }
   }
-  if (tq == 0 && by < g.bh) seg_flags[(size_t)fr * seg_fstride + (size_t)by * seg_pitch + blockIdx.x] = 1;
+  if (tq == 0 && by < g.bh) seg_flags[(size_t)fr * seg_fstride + (size_t)by * seg_pitch + tile_x] = 1;
   const int l0 = ty * 32 + 4 * tq;  // tile-local index of the first owned block
   // Horizontal runs first: block i is glued to block i-1 when the right column of i-1 and the left column of i both
   // hold a pixel (any such pair is 8-adjacent).  Every block starts out pointing at the first block of its run, so
@@ -219,11 +219,45 @@ __global__ void __launch_bounds__(256, 8) ccl_local_kernel(const uint8_t* __rest
           st_x1[base + gi] = sX1[l];
           st_y1[base + gi] = sY1[l];
         } else {
-          e = kTag | ((blockIdx.y * 32 + (r >> 5)) * g.bw + blockIdx.x * 32 + (r & 31));
+          e = kTag | ((tile_y * 32 + (r >> 5)) * g.bw + tile_x * 32 + (r & 31));
         }
       }
       labels[base + gi] = e;
     }
+  }
+}
+
+// Persistent grid over the tiles of the batch (frame, tile row, tile column).  CTA c owns tiles c, c + G, c + 2G, ...; a
+// warp looks at the foreground flags (TileHint, written with the binary image) of the next 32 of them at once, and only
+// tiles that hold foreground are worked on -- a handful per frame -- so an empty image region costs one byte read
+// instead of a CTA launch and 8 KB of pixels.  Without flags (tile_any == nullptr) every tile is read.
+__global__ void __launch_bounds__(256, 8) ccl_local_kernel(const uint8_t* __restrict__ bin, size_t bin_fstride, FrameGeom g,
+                                                           int* __restrict__ labels, int* __restrict__ st_area,
+                                                           int* __restrict__ st_x0, int* __restrict__ st_y0,
+                                                           int* __restrict__ st_x1, int* __restrict__ st_y1,
+                                                           uint8_t* __restrict__ seg_flags, int seg_pitch, size_t seg_fstride,
+                                                           const uint8_t* __restrict__ tile_any, int tiles_x, int tiles_y,
+                                                           int ntiles) {
+  __shared__ unsigned s_mask;
+  const int G = gridDim.x;
+  for (int tile0 = blockIdx.x; tile0 < ntiles; tile0 += 32 * G) {
+    if (threadIdx.x < 32) {
+      const int tile = tile0 + (int)threadIdx.x * G;
+      const bool live = tile < ntiles && (!tile_any || tile_any[tile]);
+      const unsigned m = __ballot_sync(0xffffffffu, live);
+      if (threadIdx.x == 0) s_mask = m;
+    }
+    __syncthreads();
+    unsigned m = s_mask;
+    while (m) {
+      const int tile = tile0 + (__ffs(m) - 1) * G;
+      m &= m - 1;
+      const int tpf = tiles_x * tiles_y, fr = tile / tpf, rem = tile - fr * tpf, ty = rem / tiles_x;
+      ccl_local_tile(bin, bin_fstride, g, labels, st_area, st_x0, st_y0, st_x1, st_y1, seg_flags, seg_pitch, seg_fstride,
+                     rem - ty * tiles_x, ty, fr);
+      __syncthreads();  // the tile's shared arrays are reused by the next one (and s_mask by the next round)
+    }
+    __syncthreads();
   }
 }
 
@@ -252,22 +286,18 @@ __device__ __forceinline__ void gunite(int* lab, int a, int b) {
 }
 
 // 64 threads per tile: threads 0..31 = top row of the tile (checks UL,U,UR), 32..63 = left column (checks L,UL,DL)
-__global__ void __launch_bounds__(64) ccl_merge_kernel(const uint8_t* __restrict__ bin, size_t bin_fstride, FrameGeom g,
-                                                       int* __restrict__ labels, const uint8_t* __restrict__ seg_flags,
-                                                       int seg_pitch, size_t seg_fstride) {
-  const int t = threadIdx.x, fr = blockIdx.z;
-  // a tile without foreground has nothing on its border either (its first row is always inside the frame)
-  if (!seg_flags[(size_t)fr * seg_fstride + (size_t)(blockIdx.y * 32) * seg_pitch + blockIdx.x]) return;
+__device__ __forceinline__ void ccl_merge_tile(const uint8_t* __restrict__ bin, size_t bin_fstride, const FrameGeom& g,
+                                               int* __restrict__ labels, int tile_x, int tile_y, int fr, int t) {
   const uint8_t* b = bin + (size_t)fr * bin_fstride;
   int* lab = labels + (size_t)fr * g.nblocks;
   int bx, by;
   const bool toprow = t < 32;
   if (toprow) {
-    bx = blockIdx.x * 32 + t;
-    by = blockIdx.y * 32;
+    bx = tile_x * 32 + t;
+    by = tile_y * 32;
   } else {
-    bx = blockIdx.x * 32;
-    by = blockIdx.y * 32 + (t - 32);
+    bx = tile_x * 32;
+    by = tile_y * 32 + (t - 32);
   }
   if (bx >= g.bw || by >= g.bh) return;
   int p = block_pattern(b, g, bx, by);
@@ -285,6 +315,30 @@ __global__ void __launch_bounds__(64) ccl_merge_kernel(const uint8_t* __restrict
     if ((p & 5) && (q & 10)) gunite(lab, i, i - 1);
     if (by > 0 && (p & 1) && (block_pattern(b, g, bx - 1, by - 1) & 8)) gunite(lab, i, i - g.bw - 1);
     if (by < g.bh - 1 && (p & 4) && (block_pattern(b, g, bx - 1, by + 1) & 2)) gunite(lab, i, i + g.bw - 1);
+  }
+}
+
+// Two tiles per 128-thread CTA at a time, persistent grid like ccl_local; a tile whose first segment flag is clear holds
+// no foreground (its first block row is always inside the frame) and has nothing on its border either.
+__global__ void __launch_bounds__(128) ccl_merge_kernel(const uint8_t* __restrict__ bin, size_t bin_fstride, FrameGeom g,
+                                                        int* __restrict__ labels, const uint8_t* __restrict__ seg_flags,
+                                                        int seg_pitch, size_t seg_fstride, int tiles_x, int tiles_y, int ntiles) {
+  const int half = threadIdx.x >> 6, t = threadIdx.x & 63, lane = threadIdx.x & 31;
+  const int G = 2 * gridDim.x, first = 2 * blockIdx.x + half, tpf = tiles_x * tiles_y;
+  for (int tile0 = first; tile0 < ntiles; tile0 += 32 * G) {
+    const int mine = tile0 + lane * G;
+    bool live = false;
+    if (mine < ntiles) {
+      const int fr = mine / tpf, rem = mine - fr * tpf, ty = rem / tiles_x;
+      live = seg_flags[(size_t)fr * seg_fstride + (size_t)(ty * 32) * seg_pitch + (rem - ty * tiles_x)] != 0;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, live);  // both warps of a half compute the same mask
+    while (m) {
+      const int tile = tile0 + (__ffs(m) - 1) * G;
+      m &= m - 1;
+      const int fr = tile / tpf, rem = tile - fr * tpf, ty = rem / tiles_x;
+      ccl_merge_tile(bin, bin_fstride, g, labels, rem - ty * tiles_x, ty, fr, t);
+    }
   }
 }
 
@@ -307,12 +361,14 @@ __global__ void __launch_bounds__(256) ccl_final_kernel(FrameGeom g, int* __rest
   // with these two the four blocks of a lane lie in one row and one tile column, 16-byte aligned
   const bool vec = (base & 3) == 0 && (g.bw & 3) == 0;
   unsigned live = 0;
+  const int by0 = (span * 1024) / g.bw, rem0 = span * 1024 - by0 * g.bw;  // one division per warp
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const int i0 = span * 1024 + c * 128 + 4 * lane;
     if (i0 >= g.nblocks) continue;
     if (vec && i0 + 3 < g.nblocks) {
-      const int by = i0 / g.bw, bx = i0 - by * g.bw;
+      int by = by0, bx = rem0 + c * 128 + 4 * lane;
+      while (bx >= g.bw) bx -= g.bw, ++by;
       if (sf[(size_t)by * seg_pitch + (bx >> 5)]) live |= 1u << c;
     } else {
       live |= 1u << c;  // ragged: decided block by block below
@@ -321,6 +377,7 @@ __global__ void __launch_bounds__(256) ccl_final_kernel(FrameGeom g, int* __rest
   int total = 0;
   int* out = roots_tmp + base + (size_t)span * 1024;
   if (__any_sync(kFull, live != 0)) {
+    volatile int* labv = lab;
     for (int c = 0; c < 8; ++c) {
       const bool mine = (live >> c) & 1u;
       if (!__any_sync(kFull, mine)) continue;
@@ -341,11 +398,33 @@ __global__ void __launch_bounds__(256) ccl_final_kernel(FrameGeom g, int* __rest
       int nroot = 0;
       unsigned rootmask = 0;
       if ((e4[0] & e4[1] & e4[2] & e4[3]) >= 0) {  // at least one foreground block (labels are >= 0, background is -1)
+        // The four root searches advance in lockstep, so that their loads overlap: x = current node, nx = lab[x].
+        // The block's own entry is already here; a tagged entry names the tile-local root to start from.
+        int x[4], nx[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const int e = e4[k], i = i0 + k;
+          const int e = e4[k];
+          x[k] = (e >= 0 && (e & kTag)) ? (e & ~kTag) : i0 + k;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) nx[k] = e4[k] < 0 ? x[k] : ((e4[k] & kTag) ? labv[x[k]] : e4[k]);
+        while (true) {
+          unsigned moved = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (nx[k] != x[k]) {
+              x[k] = nx[k];
+              moved |= 1u << k;
+            }
+          if (!moved) break;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (moved & (1u << k)) nx[k] = labv[x[k]];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int e = e4[k], i = i0 + k, r = x[k];
           if (e < 0) continue;
-          const int r = gfind(lab, i);
           if (e & kTag) {
             lab[i] = r;
           } else if (r != i) {
@@ -458,17 +537,33 @@ __global__ void __launch_bounds__(1024) ccl_list_kernel(FrameGeom g, const int* 
 }
 
 size_t ccl_seg_flag_bytes(const FrameGeom& g) { return (size_t)((g.bw + 31) / 32) * g.bh; }
+size_t ccl_tile_hint_bytes(const FrameGeom& g) { return (size_t)((g.bw + 31) / 32) * ((g.bh + 31) / 32); }
+TileHint ccl_tile_hint(const FrameGeom& g, uint8_t* buf) {
+  TileHint h;
+  h.any = buf;
+  h.pitch = (g.bw + 31) / 32;
+  h.fstride = (int)ccl_tile_hint_bytes(g);
+  return h;
+}
 
 int launch_ccl(const uint8_t* bin, size_t bin_fstride, int n, const FrameGeom& g, int* labels, int* st_area, int* st_x0,
-               int* st_y0, int* st_x1, int* st_y1, int* roots_tmp, int* span_count, uint8_t* seg_flags, int* legal, int legal_cap,
+               int* st_y0, int* st_x1, int* st_y1, int* roots_tmp, int* span_count, uint8_t* seg_flags, const uint8_t* tile_any, int* legal, int legal_cap,
                int* counters, cudaStream_t stream, int* launches) {
-  dim3 tiles((g.bw + 31) / 32, (g.bh + 31) / 32, n);
-  const int seg_pitch = (g.bw + 31) / 32;
+  const int tiles_x = (g.bw + 31) / 32, tiles_y = (g.bh + 31) / 32, ntiles = tiles_x * tiles_y * n;
+  const int seg_pitch = tiles_x;
+  static int sms_cache[64] = {0};
+  int dev = 0;
+  CTAG_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!sms_cache[dev]) CTAG_CUDA_CHECK(cudaDeviceGetAttribute(&sms_cache[dev], cudaDevAttrMultiProcessorCount, dev));
+  const int sms = sms_cache[dev];
   const size_t seg_fstride = ccl_seg_flag_bytes(g);
   CTAG_CUDA_CHECK(cudaMemsetAsync(seg_flags, 0, seg_fstride * n, stream));
-  ccl_local_kernel<<<tiles, 256, 0, stream>>>(bin, bin_fstride, g, labels, st_area, st_x0, st_y0, st_x1, st_y1, seg_flags, seg_pitch,
-                                               seg_fstride);
-  ccl_merge_kernel<<<tiles, 64, 0, stream>>>(bin, bin_fstride, g, labels, seg_flags, seg_pitch, seg_fstride);
+  // one wave of resident CTAs (8 per SM for ccl_local: 26 KB of shared memory each)
+  ccl_local_kernel<<<min(ntiles, 8 * sms), 256, 0, stream>>>(bin, bin_fstride, g, labels, st_area, st_x0, st_y0, st_x1, st_y1,
+                                                              seg_flags, seg_pitch, seg_fstride, tile_any, tiles_x, tiles_y, ntiles);
+  ccl_merge_kernel<<<min((ntiles + 1) / 2, 8 * sms), 128, 0, stream>>>(bin, bin_fstride, g, labels, seg_flags, seg_pitch,
+                                                                        seg_fstride, tiles_x, tiles_y, ntiles);
   int spans = (g.nblocks + 1023) / 1024;
   ccl_final_kernel<<<dim3((spans + 7) / 8, n), 256, 0, stream>>>(g, labels, st_area, st_x0, st_y0, st_x1, st_y1, roots_tmp,
                                                         span_count, spans, seg_flags, seg_pitch, seg_fstride);

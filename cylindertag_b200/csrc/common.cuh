@@ -29,6 +29,13 @@ struct FrameGeom {
   int area_max;    // round(0.01*hw*hh)
 };
 
+// Which 64x64-pixel tiles of the binary image (= 32x32 CCL blocks) hold foreground: any[frame*fstride + ty*pitch + tx],
+// zeroed per batch, set by the kernel that writes the binary image.  any == nullptr: not tracked.
+struct TileHint {
+  uint8_t* any;
+  int pitch, fstride;
+};
+
 #define CTAG_CUDA_CHECK(expr)                                  \
   do {                                                         \
     cudaError_t _e = (expr);                                   \

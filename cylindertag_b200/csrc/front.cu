@@ -86,7 +86,7 @@ __device__ __forceinline__ void issue_tile_load(const CUtensorMap* tmap, uint32_
 template <int C>
 __global__ void __launch_bounds__(front::NT, 3) front_kernel(const __grid_constant__ CUtensorMap tmap, FrameGeom geo, TileGrid tg,
                                                           uint8_t* __restrict__ gray_out, size_t gray_fstride,
-                                                          uint8_t* __restrict__ bin_out, size_t bin_fstride) {
+                                                          uint8_t* __restrict__ bin_out, size_t bin_fstride, TileHint hint) {
   using namespace front;
   using L = Layout<C>;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(front::NT, 3) front_kernel(const __grid_consta
     __syncthreads();
     phase_threshold(tmin, tmax, thr16, geo, cx, cy, tid);
     __syncthreads();
-    phase_compare_store(P, thr16, bin_out, bin_fstride, geo, fr, cx, cy, tid);
+    phase_compare_store(P, thr16, bin_out, bin_fstride, hint, geo, fr, cx, cy, tid);
     // no barrier needed here: the next iteration touches g/bgr (free since phase B / phase A) and reaches HT, P and
     // the small arrays only after further barriers
   }
@@ -348,7 +348,7 @@ __device__ __forceinline__ void convert_rows(const uint8_t* stage, uint8_t* g, i
 __global__ void __launch_bounds__(front::NT, 3)
     front_bgr_slide_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_constant__ CUtensorMap tmap_top, FrameGeom geo,
                            RunGrid rg, uint8_t* __restrict__ gray_out, size_t gray_fstride, uint8_t* __restrict__ bin_out,
-                           size_t bin_fstride) {
+                           size_t bin_fstride, TileHint hint) {
   using namespace front;
   using L = SlideLayout;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(front::NT, 3)
     __syncthreads();
     phase_threshold(tmin, tmax, thr16, geo, cx, cy, tid);
     __syncthreads();
-    phase_compare_store(P, thr16, bin_out, bin_fstride, geo, fr, cx, cy, tid);
+    phase_compare_store(P, thr16, bin_out, bin_fstride, hint, geo, fr, cx, cy, tid);
 
     t = nt, t_end = nt_end, run = nrun, valid = nvalid, first = nfirst;
     fr = nfr, cx = ncx, cy = ncy;
@@ -512,7 +512,7 @@ __device__ __forceinline__ void issue_gray_rows(const CUtensorMap* tmap_main, co
 
 __global__ void __launch_bounds__(front::NT, 4)
     front_gray_slide_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_constant__ CUtensorMap tmap_top, FrameGeom geo,
-                            RunGrid rg, uint8_t* __restrict__ bin_out, size_t bin_fstride) {
+                            RunGrid rg, uint8_t* __restrict__ bin_out, size_t bin_fstride, TileHint hint) {
   using namespace front;
   using L = GraySlideLayout;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -589,7 +589,7 @@ __global__ void __launch_bounds__(front::NT, 4)
     __syncthreads();
     phase_threshold(tmin, tmax, thr16, geo, cx, cy, tid);
     __syncthreads();
-    phase_compare_store(P, thr16, bin_out, bin_fstride, geo, fr, cx, cy, tid);
+    phase_compare_store(P, thr16, bin_out, bin_fstride, hint, geo, fr, cx, cy, tid);
 
     t = nt, t_end = nt_end, run = nrun, valid = nvalid, first = nfirst;
     fr = nfr, cx = ncx, cy = ncy;
@@ -642,7 +642,7 @@ static int resident_ctas(const void* kernel, int smem_bytes, int slot, int* out)
 
 template <int C>
 static int launch_front_t(const CUtensorMap& tmap, int n, const FrameGeom& geo, uint8_t* gray_out, size_t gray_fstride,
-                          uint8_t* bin_out, size_t bin_fstride, cudaStream_t stream, cudaEvent_t ev_start) {
+                          uint8_t* bin_out, size_t bin_fstride, TileHint hint, cudaStream_t stream, cudaEvent_t ev_start) {
   using namespace front;
   int grid = 0;
   const int rc = resident_ctas((const void*)front_kernel<C>, Layout<C>::total, C == 3 ? 0 : 1, &grid);
@@ -656,7 +656,7 @@ static int launch_front_t(const CUtensorMap& tmap, int n, const FrameGeom& geo, 
   tg.m_row = tg.tiles_x > 1 ? (uint32_t)((1ull << 32) / (uint64_t)tg.tiles_x) : 0xFFFFFFFFu;
   if (grid > tg.ntiles) grid = tg.ntiles;  // persistent: one wave of resident CTAs
   if (ev_start) CTAG_CUDA_CHECK(cudaEventRecord(ev_start, stream));
-  front_kernel<C><<<grid, NT, Layout<C>::total, stream>>>(tmap, geo, tg, gray_out, gray_fstride, bin_out, bin_fstride);
+  front_kernel<C><<<grid, NT, Layout<C>::total, stream>>>(tmap, geo, tg, gray_out, gray_fstride, bin_out, bin_fstride, hint);
   CTAG_CUDA_CHECK(cudaGetLastError());
   return CTAG_OK;
 }
@@ -690,8 +690,8 @@ static int make_run_grid(const void* kernel, int smem_bytes, int slot, int n, co
 }
 
 static int launch_front_slide(const CUtensorMap& tmap_main, const CUtensorMap& tmap_top, int n, const FrameGeom& geo, int channels,
-                              uint8_t* gray_out, size_t gray_fstride, uint8_t* bin_out, size_t bin_fstride, cudaStream_t stream,
-                              cudaEvent_t ev_start) {
+                              uint8_t* gray_out, size_t gray_fstride, uint8_t* bin_out, size_t bin_fstride, TileHint hint,
+                              cudaStream_t stream, cudaEvent_t ev_start) {
   using namespace front;
   RunGrid rg;
   int grid = 0;
@@ -700,20 +700,20 @@ static int launch_front_slide(const CUtensorMap& tmap_main, const CUtensorMap& t
     if (rc != CTAG_OK) return rc;
     if (ev_start) CTAG_CUDA_CHECK(cudaEventRecord(ev_start, stream));
     front_bgr_slide_kernel<<<grid, NT, SlideLayout::total, stream>>>(tmap_main, tmap_top, geo, rg, gray_out, gray_fstride, bin_out,
-                                                                    bin_fstride);
+                                                                    bin_fstride, hint);
   } else {
     const int rc = make_run_grid((const void*)front_gray_slide_kernel, GraySlideLayout::total, 3, n, geo, &rg, &grid);
     if (rc != CTAG_OK) return rc;
     if (ev_start) CTAG_CUDA_CHECK(cudaEventRecord(ev_start, stream));
-    front_gray_slide_kernel<<<grid, NT, GraySlideLayout::total, stream>>>(tmap_main, tmap_top, geo, rg, bin_out, bin_fstride);
+    front_gray_slide_kernel<<<grid, NT, GraySlideLayout::total, stream>>>(tmap_main, tmap_top, geo, rg, bin_out, bin_fstride, hint);
   }
   CTAG_CUDA_CHECK(cudaGetLastError());
   return CTAG_OK;
 }
 
 int launch_front(const void* frames_dev, int n, const FrameGeom& geo, int channels, size_t pitch, size_t frame_stride,
-                 uint8_t* gray_out, size_t gray_fstride, uint8_t* bin_out, size_t bin_fstride, cudaStream_t stream,
-                 cudaEvent_t ev_start) {
+                 uint8_t* gray_out, size_t gray_fstride, uint8_t* bin_out, size_t bin_fstride, TileHint hint,
+                 cudaStream_t stream, cudaEvent_t ev_start) {
   using namespace front;
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) {
@@ -746,11 +746,11 @@ int launch_front(const void* frames_dev, int n, const FrameGeom& geo, int channe
       set_last_error_text("cuTensorMapEncodeTiled failed");
       return CTAG_ERR_CUDA;
     }
-    return launch_front_slide(tmap_main, tmap_top, n, geo, channels, gray_out, gray_fstride, bin_out, bin_fstride, stream,
+    return launch_front_slide(tmap_main, tmap_top, n, geo, channels, gray_out, gray_fstride, bin_out, bin_fstride, hint, stream,
                               ev_start);
   }
-  return channels == 3 ? launch_front_t<3>(tmap, n, geo, gray_out, gray_fstride, bin_out, bin_fstride, stream, ev_start)
-                       : launch_front_t<1>(tmap, n, geo, gray_out, gray_fstride, bin_out, bin_fstride, stream, ev_start);
+  return channels == 3 ? launch_front_t<3>(tmap, n, geo, gray_out, gray_fstride, bin_out, bin_fstride, hint, stream, ev_start)
+                       : launch_front_t<1>(tmap, n, geo, gray_out, gray_fstride, bin_out, bin_fstride, hint, stream, ev_start);
 }
 
 }  // namespace ctag

@@ -255,7 +255,8 @@ __device__ __forceinline__ void phase_threshold(const uint8_t* tmin, const uint8
 
 // ---- phase F: threshold the owned 80x40 pixels, 16 per thread, 128-bit stores -----------------------------------------
 __device__ __forceinline__ void phase_compare_store(const uint8_t* P, const uint8_t* thr16, uint8_t* __restrict__ bin_out,
-                                                    size_t bin_fstride, const FrameGeom& geo, int fr, int cx, int cy, int tid) {
+                                                    size_t bin_fstride, const TileHint& hint, const FrameGeom& geo, int fr, int cx,
+                                                    int cy, int tid) {
   using namespace front;
   if (tid >= OH * 5) return;
   const int i = tid / 5, q = tid - i * 5;
@@ -281,6 +282,8 @@ __device__ __forceinline__ void phase_compare_store(const uint8_t* P, const uint
     }
     *reinterpret_cast<uint4*>(bin_out + (size_t)fr * bin_fstride + (size_t)yh * geo.bpitch + xh0) =
         make_uint4(o[0], o[1], o[2], o[3]);
+    // the 16 pixels lie in one 64x64 tile; foreground is rare, so this store almost never happens
+    if ((o[0] | o[1] | o[2] | o[3]) && hint.any) hint.any[(size_t)fr * hint.fstride + (yh >> 6) * hint.pitch + (xh0 >> 6)] = 1;
   }
 }
 

@@ -8,8 +8,8 @@ namespace ctag {
 // `ev_start` (optional) is recorded on the stream right in front of the kernel, behind the host-side preparation
 // (tensor maps), so that stage timings measure the kernel and not the host.
 int launch_front(const void* frames_dev, int n, const FrameGeom& geo, int channels, size_t pitch, size_t frame_stride,
-                 uint8_t* gray_out, size_t gray_fstride, uint8_t* bin_out, size_t bin_fstride, cudaStream_t stream,
-                 cudaEvent_t ev_start = nullptr);
+                 uint8_t* gray_out, size_t gray_fstride, uint8_t* bin_out, size_t bin_fstride, TileHint hint,
+                 cudaStream_t stream, cudaEvent_t ev_start = nullptr);
 int front_smem_bytes(int channels);
 
 // front_generic.cu: the same stages for an adaptiveThresh window other than 5 (three plain kernels, half-res image in HBM).
@@ -20,9 +20,12 @@ int launch_front_generic(const void* frames_dev, int n, const FrameGeom& g, int 
 
 // K2/K3 (ccl.cu): block-based union-find labelling, stats, ordered legal-component list.
 // legal[frame][k] = {root, area, x0, y0, x1, y1}; counters[frame] = {n_components, n_legal, overflow, 0}.
+// `tile_any` (nullable, ccl_tile_hint_bytes(g) per frame): the front kernel's per-tile foreground flags (TileHint).
 size_t ccl_seg_flag_bytes(const FrameGeom& g);
+size_t ccl_tile_hint_bytes(const FrameGeom& g);
+TileHint ccl_tile_hint(const FrameGeom& g, uint8_t* buf);
 int launch_ccl(const uint8_t* bin, size_t bin_fstride, int n, const FrameGeom& g, int* labels, int* st_area, int* st_x0,
-               int* st_y0, int* st_x1, int* st_y1, int* roots_tmp, int* span_count, uint8_t* seg_flags, int* legal, int legal_cap,
+               int* st_y0, int* st_x1, int* st_y1, int* roots_tmp, int* span_count, uint8_t* seg_flags, const uint8_t* tile_any, int* legal, int legal_cap,
                int* counters, cudaStream_t stream, int* launches);
 
 // K4 (quad.cu): edges (warp per component) -> Welsch fits (thread per restart, merge, exact fallback) -> corner
