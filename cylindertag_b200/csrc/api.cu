@@ -80,7 +80,7 @@ struct Slot {
   size_t tiles_bytes = 0;
   size_t gray_fstride = 0, bin_fstride = 0;
   int *d_labels = nullptr, *d_st_area = nullptr, *d_st_x0 = nullptr, *d_st_y0 = nullptr, *d_st_x1 = nullptr,
-      *d_st_y1 = nullptr, *d_roots_tmp = nullptr, *d_span_count = nullptr, *d_legal = nullptr, *d_counters = nullptr;
+      *d_st_y1 = nullptr, *d_roots_tmp = nullptr, *d_tile_list = nullptr, *d_legal = nullptr, *d_counters = nullptr;
   int legal_cap = 0, spans = 0;
   int *d_prefix = nullptr, *d_qctl = nullptr, *d_quad_status = nullptr, *d_quad_comp = nullptr, *d_n_quads = nullptr,
       *d_exact_list = nullptr, *d_fit_order = nullptr, *d_frame_fit = nullptr, *d_pool = nullptr;
@@ -226,8 +226,8 @@ static int ensure_workspace(ctag_detector* d, Slot* s, int n, int w, int h) {
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_st_y0, nb));
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_st_x1, nb));
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_st_y1, nb));
-  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_roots_tmp, nb));
-  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_span_count, (size_t)s->spans * cap));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_roots_tmp, ccl_roots_ints(g) * cap));
+  CTAG_CUDA_CHECK(slot_alloc(s, &s->d_tile_list, ccl_tile_list_ints(g, cap)));
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_seg_flags, ccl_seg_flag_bytes(g) * cap));
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_tile_any, ccl_tile_hint_bytes(g) * cap));
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_legal, (size_t)s->legal_cap * 6 * cap));
@@ -325,7 +325,7 @@ static int enqueue_on_slot(ctag_detector* d, Slot* s, const void* frames_dev, in
   if (rc != CTAG_OK) return rc;
   CTAG_CUDA_CHECK(cudaEventRecord(s->ev[1], st));
   rc = launch_ccl(s->d_bin, s->bin_fstride, n, s->geo, s->d_labels, s->d_st_area, s->d_st_x0, s->d_st_y0, s->d_st_x1,
-                  s->d_st_y1, s->d_roots_tmp, s->d_span_count, s->d_seg_flags, tile_any, s->d_legal, s->legal_cap, s->d_counters, st, &s->launches);
+                  s->d_st_y1, s->d_roots_tmp, s->d_tile_list, s->d_seg_flags, tile_any, s->d_legal, s->legal_cap, s->d_counters, st, &s->launches);
   if (rc != CTAG_OK) return rc;
   CTAG_CUDA_CHECK(cudaEventRecord(s->ev[2], st));
   rc = launch_quad(n, s->geo, s->d_bin, s->bin_fstride, s->d_labels, s->d_legal, s->legal_cap, s->d_counters, s->d_prefix,

@@ -5,16 +5,18 @@
 // 2x2-block raster index they touch, so a union-find over 2x2 blocks whose root is always the minimum
 // block index yields the reference order directly: component order == ascending root index.
 //
-//   ccl_local  : one CTA per 32x32-block tile (64x64 px).  Union-find in shared memory, partial stats per local
-//                root, one label word per 2x2 block written to HBM (not one per pixel) -- for tiles that hold
-//                foreground; an empty tile writes nothing, and a flag byte per (block row, tile column) tells
-//                ccl_final which label segments exist, so empty image regions cost one read of the binary image.
+//   ccl_tiles  : list of the 32x32-block tiles (64x64 px) that hold foreground, from the flags the front kernel wrote
+//                together with the binary image (TileHint); a frame has a handful of them.  All later kernels are
+//                persistent grids over this list, so an empty image region costs one byte read.
+//   ccl_local  : one CTA per listed tile.  Union-find in shared memory, partial stats per local root, one label
+//                word per 2x2 block written to HBM (not one per pixel); a flag byte per (block row, tile column)
+//                = "this 32-block label segment exists".  Labels of unlisted tiles are never written nor read.
 //   ccl_merge  : unions across tile borders (global atomicMin union-find over the local roots only).
-//   ccl_final  : flattens every block label to its global root, folds the partial stats of merged local roots
-//                into the global root, lists the global roots of each 1024-block span in ascending order
-//                (ballot + prefix scan).
-//   ccl_list   : one CTA per frame: scan of the per-span root counts -> ordered component list, area filter,
-//                second scan -> ordered list of legal components {root, area, bbox}.
+//   ccl_final  : per listed tile: flattens every block label to its global root, folds the partial stats of merged
+//                local roots into the global root, lists the global roots of every row segment in ascending order
+//                (prefix over the eight lanes of a row) and stores their number in the segment's flag byte.
+//   ccl_list   : one CTA per frame: scan of the per-segment root counts in raster order -> ordered component list,
+//                area filter, second scan -> ordered list of legal components {root, area, bbox}.
 //
 // A pixel (x,y) belongs to component `root` iff binary(x,y) != 0 and label[(y>>1)*bw + (x>>1)] == root, because all
 // foreground pixels of one 2x2 block are mutually 8-connected.
@@ -227,37 +229,35 @@ __device__ __forceinline__ void ccl_local_tile(const uint8_t* __restrict__ bin, 
   }
 }
 
-// Persistent grid over the tiles of the batch (frame, tile row, tile column).  CTA c owns tiles c, c + G, c + 2G, ...; a
-// warp looks at the foreground flags (TileHint, written with the binary image) of the next 32 of them at once, and only
-// tiles that hold foreground are worked on -- a handful per frame -- so an empty image region costs one byte read
-// instead of a CTA launch and 8 KB of pixels.  Without flags (tile_any == nullptr) every tile is read.
+// tile_list[0 .. *tile_count) = ids ((frame * tiles_y + tile row) * tiles_x + tile column) of the tiles to look at: those
+// the front kernel flagged (TileHint), or all of them when there are no flags.  Order does not matter.
+__global__ void __launch_bounds__(256) ccl_tiles_kernel(const uint8_t* __restrict__ tile_any, int ntiles,
+                                                        int* __restrict__ tile_list, int* __restrict__ tile_count) {
+  const int tile = blockIdx.x * 256 + threadIdx.x, lane = threadIdx.x & 31;
+  const bool live = tile < ntiles && (!tile_any || tile_any[tile]);
+  const unsigned m = __ballot_sync(0xffffffffu, live);
+  if (!m) return;
+  int at = 0;
+  if (lane == 0) at = atomicAdd(tile_count, __popc(m));
+  at = __shfl_sync(0xffffffffu, at, 0);
+  if (live) tile_list[at + __popc(m & ((1u << lane) - 1u))] = tile;
+}
+
+// Persistent grid: CTA c works on list entries c, c + G, c + 2G, ... (neighbouring tiles go to different CTAs).
 __global__ void __launch_bounds__(256, 8) ccl_local_kernel(const uint8_t* __restrict__ bin, size_t bin_fstride, FrameGeom g,
                                                            int* __restrict__ labels, int* __restrict__ st_area,
                                                            int* __restrict__ st_x0, int* __restrict__ st_y0,
                                                            int* __restrict__ st_x1, int* __restrict__ st_y1,
                                                            uint8_t* __restrict__ seg_flags, int seg_pitch, size_t seg_fstride,
-                                                           const uint8_t* __restrict__ tile_any, int tiles_x, int tiles_y,
-                                                           int ntiles) {
-  __shared__ unsigned s_mask;
-  const int G = gridDim.x;
-  for (int tile0 = blockIdx.x; tile0 < ntiles; tile0 += 32 * G) {
-    if (threadIdx.x < 32) {
-      const int tile = tile0 + (int)threadIdx.x * G;
-      const bool live = tile < ntiles && (!tile_any || tile_any[tile]);
-      const unsigned m = __ballot_sync(0xffffffffu, live);
-      if (threadIdx.x == 0) s_mask = m;
-    }
-    __syncthreads();
-    unsigned m = s_mask;
-    while (m) {
-      const int tile = tile0 + (__ffs(m) - 1) * G;
-      m &= m - 1;
-      const int tpf = tiles_x * tiles_y, fr = tile / tpf, rem = tile - fr * tpf, ty = rem / tiles_x;
-      ccl_local_tile(bin, bin_fstride, g, labels, st_area, st_x0, st_y0, st_x1, st_y1, seg_flags, seg_pitch, seg_fstride,
-                     rem - ty * tiles_x, ty, fr);
-      __syncthreads();  // the tile's shared arrays are reused by the next one (and s_mask by the next round)
-    }
-    __syncthreads();
+                                                           const int* __restrict__ tile_list, const int* __restrict__ tile_count,
+                                                           int tiles_x, int tiles_y) {
+  const int count = *tile_count, tpf = tiles_x * tiles_y;
+  for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
+    const int tile = tile_list[idx];
+    const int fr = tile / tpf, rem = tile - fr * tpf, ty = rem / tiles_x;
+    ccl_local_tile(bin, bin_fstride, g, labels, st_area, st_x0, st_y0, st_x1, st_y1, seg_flags, seg_pitch, seg_fstride,
+                   rem - ty * tiles_x, ty, fr);
+    __syncthreads();  // the tile's shared arrays are reused by the next one
   }
 }
 
@@ -318,144 +318,114 @@ __device__ __forceinline__ void ccl_merge_tile(const uint8_t* __restrict__ bin, 
   }
 }
 
-// Two tiles per 128-thread CTA at a time, persistent grid like ccl_local; a tile whose first segment flag is clear holds
-// no foreground (its first block row is always inside the frame) and has nothing on its border either.
-__global__ void __launch_bounds__(128) ccl_merge_kernel(const uint8_t* __restrict__ bin, size_t bin_fstride, FrameGeom g,
-                                                        int* __restrict__ labels, const uint8_t* __restrict__ seg_flags,
-                                                        int seg_pitch, size_t seg_fstride, int tiles_x, int tiles_y, int ntiles) {
-  const int half = threadIdx.x >> 6, t = threadIdx.x & 63, lane = threadIdx.x & 31;
-  const int G = 2 * gridDim.x, first = 2 * blockIdx.x + half, tpf = tiles_x * tiles_y;
-  for (int tile0 = first; tile0 < ntiles; tile0 += 32 * G) {
-    const int mine = tile0 + lane * G;
-    bool live = false;
-    if (mine < ntiles) {
-      const int fr = mine / tpf, rem = mine - fr * tpf, ty = rem / tiles_x;
-      live = seg_flags[(size_t)fr * seg_fstride + (size_t)(ty * 32) * seg_pitch + (rem - ty * tiles_x)] != 0;
-    }
-    unsigned m = __ballot_sync(0xffffffffu, live);  // both warps of a half compute the same mask
-    while (m) {
-      const int tile = tile0 + (__ffs(m) - 1) * G;
-      m &= m - 1;
-      const int fr = tile / tpf, rem = tile - fr * tpf, ty = rem / tiles_x;
-      ccl_merge_tile(bin, bin_fstride, g, labels, rem - ty * tiles_x, ty, fr, t);
-    }
+// 64 threads per listed tile; a tile whose first segment flag is clear holds no foreground (its first block row is always
+// inside the frame) and has nothing on its border either.
+__global__ void __launch_bounds__(64) ccl_merge_kernel(const uint8_t* __restrict__ bin, size_t bin_fstride, FrameGeom g,
+                                                       int* __restrict__ labels, const uint8_t* __restrict__ seg_flags,
+                                                       int seg_pitch, size_t seg_fstride, const int* __restrict__ tile_list,
+                                                       const int* __restrict__ tile_count, int tiles_x, int tiles_y) {
+  const int count = *tile_count, tpf = tiles_x * tiles_y;
+  for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
+    const int tile = tile_list[idx];
+    const int fr = tile / tpf, rem = tile - fr * tpf, ty = rem / tiles_x, tx = rem - ty * tiles_x;
+    if (!seg_flags[(size_t)fr * seg_fstride + (size_t)(ty * 32) * seg_pitch + tx]) continue;
+    ccl_merge_tile(bin, bin_fstride, g, labels, tx, ty, fr, threadIdx.x);
   }
 }
 
-// One warp per 1024-block span, in eight chunks of 128 blocks (four consecutive blocks per lane: 16-byte label loads).
-// A chunk whose row segments hold no foreground (seg_flags) is not read; a span without any ends after the flag loads.
-// roots_tmp[span*1024 + k] = k-th global root (ascending) of the span; span_count[span].
+// 256 threads per listed tile, thread t owns the four blocks (4*(t&7) .. +3) of tile row t>>3 like ccl_local.
+// roots_tmp[segment * 32 + k] = k-th global root (ascending) of the 32-block row segment (block row, tile column);
+// the segment's flag byte becomes 0x80 | number of roots.
 __global__ void __launch_bounds__(256) ccl_final_kernel(FrameGeom g, int* __restrict__ labels, int* __restrict__ st_area,
                                                         int* __restrict__ st_x0, int* __restrict__ st_y0,
                                                         int* __restrict__ st_x1, int* __restrict__ st_y1,
-                                                        int* __restrict__ roots_tmp, int* __restrict__ span_count,
-                                                        int spans_per_frame, const uint8_t* __restrict__ seg_flags, int seg_pitch,
-                                                        size_t seg_fstride) {
+                                                        int* __restrict__ roots_tmp, uint8_t* __restrict__ seg_flags,
+                                                        int seg_pitch, size_t seg_fstride, const int* __restrict__ tile_list,
+                                                        const int* __restrict__ tile_count, int tiles_x, int tiles_y) {
   constexpr unsigned kFull = 0xffffffffu;
-  const int lane = threadIdx.x & 31, fr = blockIdx.y;
-  const int span = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (span >= spans_per_frame) return;
-  const size_t base = (size_t)fr * g.nblocks;
-  int* lab = labels + base;
-  const uint8_t* sf = seg_flags + (size_t)fr * seg_fstride;
-  // with these two the four blocks of a lane lie in one row and one tile column, 16-byte aligned
-  const bool vec = (base & 3) == 0 && (g.bw & 3) == 0;
-  unsigned live = 0;
-  const int by0 = (span * 1024) / g.bw, rem0 = span * 1024 - by0 * g.bw;  // one division per warp
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const int i0 = span * 1024 + c * 128 + 4 * lane;
-    if (i0 >= g.nblocks) continue;
-    if (vec && i0 + 3 < g.nblocks) {
-      int by = by0, bx = rem0 + c * 128 + 4 * lane;
-      while (bx >= g.bw) bx -= g.bw, ++by;
-      if (sf[(size_t)by * seg_pitch + (bx >> 5)]) live |= 1u << c;
-    } else {
-      live |= 1u << c;  // ragged: decided block by block below
-    }
-  }
-  int total = 0;
-  int* out = roots_tmp + base + (size_t)span * 1024;
-  if (__any_sync(kFull, live != 0)) {
+  const int tq = threadIdx.x & 7, trow = threadIdx.x >> 3;
+  const int count = *tile_count, tpf = tiles_x * tiles_y;
+  for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
+    const int tile = tile_list[idx];
+    const int fr = tile / tpf, rem = tile - fr * tpf, ty = rem / tiles_x, tx = rem - ty * tiles_x;
+    uint8_t* sf = seg_flags + (size_t)fr * seg_fstride;
+    if (!sf[(size_t)(ty * 32) * seg_pitch + tx]) continue;  // no foreground after all (only without TileHint)
+    const int by = ty * 32 + trow, bx0 = tx * 32 + 4 * tq, i0 = by * g.bw + bx0;
+    const size_t base = (size_t)fr * g.nblocks;
+    int* lab = labels + base;
     volatile int* labv = lab;
-    for (int c = 0; c < 8; ++c) {
-      const bool mine = (live >> c) & 1u;
-      if (!__any_sync(kFull, mine)) continue;
-      const int i0 = span * 1024 + c * 128 + 4 * lane;
-      int e4[4] = {-1, -1, -1, -1};
-      if (mine) {
-        if (vec && i0 + 3 < g.nblocks) {
-          const int4 v = *reinterpret_cast<const int4*>(lab + i0);
-          e4[0] = v.x, e4[1] = v.y, e4[2] = v.z, e4[3] = v.w;
-        } else {
-          for (int k = 0; k < 4; ++k)
-            if (i0 + k < g.nblocks) {
-              const int by = (i0 + k) / g.bw, bx = (i0 + k) - by * g.bw;
-              if (sf[(size_t)by * seg_pitch + (bx >> 5)]) e4[k] = lab[i0 + k];
-            }
-        }
+    int e4[4] = {-1, -1, -1, -1};
+    if (by < g.bh) {
+      if (bx0 + 3 < g.bw && ((base + i0) & 3) == 0) {
+        const int4 v = *reinterpret_cast<const int4*>(lab + i0);
+        e4[0] = v.x, e4[1] = v.y, e4[2] = v.z, e4[3] = v.w;
+      } else {
+        for (int k = 0; k < 4; ++k)
+          if (bx0 + k < g.bw) e4[k] = lab[i0 + k];
       }
-      int nroot = 0;
-      unsigned rootmask = 0;
-      if ((e4[0] & e4[1] & e4[2] & e4[3]) >= 0) {  // at least one foreground block (labels are >= 0, background is -1)
-        // The four root searches advance in lockstep, so that their loads overlap: x = current node, nx = lab[x].
-        // The block's own entry is already here; a tagged entry names the tile-local root to start from.
-        int x[4], nx[4];
+    }
+    int nroot = 0;
+    unsigned rootmask = 0;
+    if ((e4[0] & e4[1] & e4[2] & e4[3]) >= 0) {  // at least one foreground block (labels are >= 0, background is -1)
+      // The four root searches advance in lockstep, so that their loads overlap: x = current node, nx = lab[x].
+      // The block's own entry is already here; a tagged entry names the tile-local root to start from.
+      int x[4], nx[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int e = e4[k];
-          x[k] = (e >= 0 && (e & kTag)) ? (e & ~kTag) : i0 + k;
-        }
+      for (int k = 0; k < 4; ++k) {
+        const int e = e4[k];
+        x[k] = (e >= 0 && (e & kTag)) ? (e & ~kTag) : i0 + k;
+      }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) nx[k] = e4[k] < 0 ? x[k] : ((e4[k] & kTag) ? labv[x[k]] : e4[k]);
-        while (true) {
-          unsigned moved = 0;
+      for (int k = 0; k < 4; ++k) nx[k] = e4[k] < 0 ? x[k] : ((e4[k] & kTag) ? labv[x[k]] : e4[k]);
+      while (true) {
+        unsigned moved = 0;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (nx[k] != x[k]) {
-              x[k] = nx[k];
-              moved |= 1u << k;
-            }
-          if (!moved) break;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (moved & (1u << k)) nx[k] = labv[x[k]];
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int e = e4[k], i = i0 + k, r = x[k];
-          if (e < 0) continue;
-          if (e & kTag) {
-            lab[i] = r;
-          } else if (r != i) {
-            // a tile-local root that was merged into another tree: fold its partial stats into the global root
-            atomicAdd(&st_area[base + r], st_area[base + i]);
-            atomicMin(&st_x0[base + r], st_x0[base + i]);
-            atomicMin(&st_y0[base + r], st_y0[base + i]);
-            atomicMax(&st_x1[base + r], st_x1[base + i]);
-            atomicMax(&st_y1[base + r], st_y1[base + i]);
-            lab[i] = r;
-          } else {
-            rootmask |= 1u << k;
-            ++nroot;
+        for (int k = 0; k < 4; ++k)
+          if (nx[k] != x[k]) {
+            x[k] = nx[k];
+            moved |= 1u << k;
           }
+        if (!moved) break;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (moved & (1u << k)) nx[k] = labv[x[k]];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = e4[k], i = i0 + k, r = x[k];
+        if (e < 0) continue;
+        if (e & kTag) {
+          lab[i] = r;
+        } else if (r != i) {
+          // a tile-local root that was merged into another tree: fold its partial stats into the global root
+          atomicAdd(&st_area[base + r], st_area[base + i]);
+          atomicMin(&st_x0[base + r], st_x0[base + i]);
+          atomicMin(&st_y0[base + r], st_y0[base + i]);
+          atomicMax(&st_x1[base + r], st_x1[base + i]);
+          atomicMax(&st_y1[base + r], st_y1[base + i]);
+          lab[i] = r;
+        } else {
+          rootmask |= 1u << k;
+          ++nroot;
         }
       }
-      if (!__any_sync(kFull, nroot != 0)) continue;
-      int inc = nroot;  // inclusive prefix of the per-lane root counts
+    }
+    int inc = nroot;  // inclusive prefix of the root counts over the eight lanes of the row
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int n = __shfl_up_sync(kFull, inc, o);
-        if (lane >= o) inc += n;
-      }
-      int pos = total + inc - nroot;
+    for (int o = 1; o < 8; o <<= 1) {
+      const int n = __shfl_up_sync(kFull, inc, o, 8);
+      if (tq >= o) inc += n;
+    }
+    if (by < g.bh) {
+      const size_t seg = (size_t)by * seg_pitch + tx;
+      int* out = roots_tmp + ((size_t)fr * seg_fstride + seg) * 32;
+      int pos = inc - nroot;
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         if (rootmask & (1u << k)) out[pos++] = i0 + k;
-      total += __shfl_sync(kFull, inc, 31);
+      if (tq == 7) sf[seg] = (uint8_t)(0x80 | inc);
     }
   }
-  if (lane == 0) span_count[fr * spans_per_frame + span] = total;
 }
 
 __device__ __forceinline__ int block_exclusive_scan_1024(int v, int* total, int* sh /*33 ints*/) {
@@ -486,52 +456,61 @@ __device__ __forceinline__ int block_exclusive_scan_1024(int v, int* total, int*
 }
 
 // One CTA per frame.  legal[frame][k] = {root, area, x0, y0, x1, y1} in ascending root order (= OpenCV label order).
+// Thread t owns a run of consecutive row segments (raster order: block row, tile column), so one scan orders everything.
 __global__ void __launch_bounds__(1024) ccl_list_kernel(FrameGeom g, const int* __restrict__ st_area,
                                                         const int* __restrict__ st_x0, const int* __restrict__ st_y0,
                                                         const int* __restrict__ st_x1, const int* __restrict__ st_y1,
-                                                        const int* __restrict__ roots_tmp, const int* __restrict__ span_count,
-                                                        int spans_per_frame, int* __restrict__ legal, int legal_cap,
+                                                        const int* __restrict__ roots_tmp, const uint8_t* __restrict__ seg_flags,
+                                                        int segs, int* __restrict__ legal, int legal_cap,
                                                         int* __restrict__ counters /* [frame][4]: n_comp, n_legal, overflow */) {
   __shared__ int sh[33];
   const int t = threadIdx.x, fr = blockIdx.x;
   const size_t base = (size_t)fr * g.nblocks;
-  int comp_base = 0, legal_base = 0;
-  for (int s0 = 0; s0 < spans_per_frame; s0 += 1024) {
-    int s = s0 + t;
-    int c = (s < spans_per_frame) ? span_count[fr * spans_per_frame + s] : 0;
-    int lc = 0;
-    for (int k = 0; k < c; ++k) {
-      int a = st_area[base + roots_tmp[base + (size_t)s * 1024 + k]];
+  const uint8_t* sf = seg_flags + (size_t)fr * segs;
+  const int* roots = roots_tmp + (size_t)fr * segs * 32;
+  const int per = (segs + 1023) / 1024;
+  const int s_lo = min(t * per, segs), s_hi = min(s_lo + per, segs);
+  int c = 0, lc = 0;
+  for (int s = s_lo; s < s_hi; ++s) {
+    const int f = sf[s];
+    if (!(f & 0x80)) continue;
+    const int n = f & 0x7f;
+    c += n;
+    for (int k = 0; k < n; ++k) {
+      const int a = st_area[base + roots[(size_t)s * 32 + k]];
       lc += (a >= kAreaMin && a <= g.area_max) ? 1 : 0;
     }
-    int tot_c, tot_l;
-    (void)block_exclusive_scan_1024(c, &tot_c, sh);
-    int loff = block_exclusive_scan_1024(lc, &tot_l, sh);
-    int o = legal_base + loff;
-    for (int k = 0; k < c; ++k) {
-      int r = roots_tmp[base + (size_t)s * 1024 + k];
-      int a = st_area[base + r];
-      if (a >= kAreaMin && a <= g.area_max) {
-        if (o < legal_cap) {
-          int* dst = legal + ((size_t)fr * legal_cap + o) * 6;
-          dst[0] = r;
-          dst[1] = a;
-          dst[2] = st_x0[base + r];
-          dst[3] = st_y0[base + r];
-          dst[4] = st_x1[base + r];
-          dst[5] = st_y1[base + r];
+  }
+  int tot_c, tot_l;
+  (void)block_exclusive_scan_1024(c, &tot_c, sh);
+  int o = block_exclusive_scan_1024(lc, &tot_l, sh);
+  if (lc) {
+    for (int s = s_lo; s < s_hi; ++s) {
+      const int f = sf[s];
+      if (!(f & 0x80)) continue;
+      const int n = f & 0x7f;
+      for (int k = 0; k < n; ++k) {
+        const int r = roots[(size_t)s * 32 + k];
+        const int a = st_area[base + r];
+        if (a >= kAreaMin && a <= g.area_max) {
+          if (o < legal_cap) {
+            int* dst = legal + ((size_t)fr * legal_cap + o) * 6;
+            dst[0] = r;
+            dst[1] = a;
+            dst[2] = st_x0[base + r];
+            dst[3] = st_y0[base + r];
+            dst[4] = st_x1[base + r];
+            dst[5] = st_y1[base + r];
+          }
+          ++o;
         }
-        ++o;
       }
     }
-    comp_base += tot_c;
-    legal_base += tot_l;
-    __syncthreads();
   }
   if (t == 0) {
-    counters[fr * 4 + 0] = comp_base;
-    counters[fr * 4 + 1] = legal_base < legal_cap ? legal_base : legal_cap;
-    counters[fr * 4 + 2] = legal_base > legal_cap ? 1 : 0;
+    counters[fr * 4 + 0] = tot_c;
+    counters[fr * 4 + 1] = tot_l < legal_cap ? tot_l : legal_cap;
+    counters[fr * 4 + 2] = tot_l > legal_cap ? 1 : 0;
     counters[fr * 4 + 3] = 0;
   }
 }
@@ -546,9 +525,12 @@ TileHint ccl_tile_hint(const FrameGeom& g, uint8_t* buf) {
   return h;
 }
 
+size_t ccl_roots_ints(const FrameGeom& g) { return ccl_seg_flag_bytes(g) * 32; }
+size_t ccl_tile_list_ints(const FrameGeom& g, int frames) { return 4 + ccl_tile_hint_bytes(g) * (size_t)frames; }
+
 int launch_ccl(const uint8_t* bin, size_t bin_fstride, int n, const FrameGeom& g, int* labels, int* st_area, int* st_x0,
-               int* st_y0, int* st_x1, int* st_y1, int* roots_tmp, int* span_count, uint8_t* seg_flags, const uint8_t* tile_any, int* legal, int legal_cap,
-               int* counters, cudaStream_t stream, int* launches) {
+               int* st_y0, int* st_x1, int* st_y1, int* roots_tmp, int* tile_list, uint8_t* seg_flags, const uint8_t* tile_any,
+               int* legal, int legal_cap, int* counters, cudaStream_t stream, int* launches) {
   const int tiles_x = (g.bw + 31) / 32, tiles_y = (g.bh + 31) / 32, ntiles = tiles_x * tiles_y * n;
   const int seg_pitch = tiles_x;
   static int sms_cache[64] = {0};
@@ -558,19 +540,22 @@ int launch_ccl(const uint8_t* bin, size_t bin_fstride, int n, const FrameGeom& g
   if (!sms_cache[dev]) CTAG_CUDA_CHECK(cudaDeviceGetAttribute(&sms_cache[dev], cudaDevAttrMultiProcessorCount, dev));
   const int sms = sms_cache[dev];
   const size_t seg_fstride = ccl_seg_flag_bytes(g);
+  int* tile_count = tile_list;  // [0] = number of entries, the entries start at [4]
+  int* tiles = tile_list + 4;
   CTAG_CUDA_CHECK(cudaMemsetAsync(seg_flags, 0, seg_fstride * n, stream));
-  // one wave of resident CTAs (8 per SM for ccl_local: 26 KB of shared memory each)
+  CTAG_CUDA_CHECK(cudaMemsetAsync(tile_count, 0, 16, stream));
+  ccl_tiles_kernel<<<(ntiles + 255) / 256, 256, 0, stream>>>(tile_any, ntiles, tiles, tile_count);
+  // one wave of resident CTAs each (ccl_local: 8 per SM, 26 KB of shared memory each)
   ccl_local_kernel<<<min(ntiles, 8 * sms), 256, 0, stream>>>(bin, bin_fstride, g, labels, st_area, st_x0, st_y0, st_x1, st_y1,
-                                                              seg_flags, seg_pitch, seg_fstride, tile_any, tiles_x, tiles_y, ntiles);
-  ccl_merge_kernel<<<min((ntiles + 1) / 2, 8 * sms), 128, 0, stream>>>(bin, bin_fstride, g, labels, seg_flags, seg_pitch,
-                                                                        seg_fstride, tiles_x, tiles_y, ntiles);
-  int spans = (g.nblocks + 1023) / 1024;
-  ccl_final_kernel<<<dim3((spans + 7) / 8, n), 256, 0, stream>>>(g, labels, st_area, st_x0, st_y0, st_x1, st_y1, roots_tmp,
-                                                        span_count, spans, seg_flags, seg_pitch, seg_fstride);
-  ccl_list_kernel<<<n, 1024, 0, stream>>>(g, st_area, st_x0, st_y0, st_x1, st_y1, roots_tmp, span_count, spans, legal,
+                                                              seg_flags, seg_pitch, seg_fstride, tiles, tile_count, tiles_x, tiles_y);
+  ccl_merge_kernel<<<min(ntiles, 16 * sms), 64, 0, stream>>>(bin, bin_fstride, g, labels, seg_flags, seg_pitch, seg_fstride, tiles,
+                                                              tile_count, tiles_x, tiles_y);
+  ccl_final_kernel<<<min(ntiles, 8 * sms), 256, 0, stream>>>(g, labels, st_area, st_x0, st_y0, st_x1, st_y1, roots_tmp, seg_flags,
+                                                              seg_pitch, seg_fstride, tiles, tile_count, tiles_x, tiles_y);
+  ccl_list_kernel<<<n, 1024, 0, stream>>>(g, st_area, st_x0, st_y0, st_x1, st_y1, roots_tmp, seg_flags, (int)seg_fstride, legal,
                                           legal_cap, counters);
   CTAG_CUDA_CHECK(cudaGetLastError());
-  if (launches) *launches += 4;
+  if (launches) *launches += 5;
   return CTAG_OK;
 }
 
