@@ -44,9 +44,15 @@ __device__ __forceinline__ int block_pattern(const uint8_t* __restrict__ bin, co
   return p;
 }
 
+// Find with path halving: every visited node is re-pointed at its grandparent.  Safe next to concurrent unions: only a
+// non-root is written (it can never become a root again), and what is stored is one of its ancestors.
 __device__ __forceinline__ int uf_find(volatile int* L, int x) {
   int p;
-  while ((p = L[x]) != x) x = p;
+  while ((p = L[x]) != x) {
+    const int gp = L[p];
+    if (gp != p) L[x] = gp;
+    x = gp;
+  }
   return x;
 }
 
@@ -229,9 +235,9 @@ __device__ __forceinline__ void ccl_local_tile(const uint8_t* __restrict__ bin, 
   }
 }
 
-// tile_list[0 .. *tile_count) = ids ((frame * tiles_y + tile row) * tiles_x + tile column) of the tiles to look at: those
+// tile_list[0 .. *tile_count) = (frame << 16 | tile row << 8 | tile column) of the tiles to look at: those
 // the front kernel flagged (TileHint), or all of them when there are no flags.  Order does not matter.
-__global__ void __launch_bounds__(256) ccl_tiles_kernel(const uint8_t* __restrict__ tile_any, int ntiles,
+__global__ void __launch_bounds__(256) ccl_tiles_kernel(const uint8_t* __restrict__ tile_any, int ntiles, int tiles_x, int tiles_y,
                                                         int* __restrict__ tile_list, int* __restrict__ tile_count) {
   const int tile = blockIdx.x * 256 + threadIdx.x, lane = threadIdx.x & 31;
   const bool live = tile < ntiles && (!tile_any || tile_any[tile]);
@@ -240,7 +246,10 @@ __global__ void __launch_bounds__(256) ccl_tiles_kernel(const uint8_t* __restric
   int at = 0;
   if (lane == 0) at = atomicAdd(tile_count, __popc(m));
   at = __shfl_sync(0xffffffffu, at, 0);
-  if (live) tile_list[at + __popc(m & ((1u << lane) - 1u))] = tile;
+  if (live) {
+    const int tpf = tiles_x * tiles_y, fr = tile / tpf, rem = tile - fr * tpf, ty = rem / tiles_x;
+    tile_list[at + __popc(m & ((1u << lane) - 1u))] = (fr << 16) | (ty << 8) | (rem - ty * tiles_x);  // tiles_x, tiles_y <= 64
+  }
 }
 
 // Persistent grid: CTA c works on list entries c, c + G, c + 2G, ... (neighbouring tiles go to different CTAs).
@@ -249,14 +258,12 @@ __global__ void __launch_bounds__(256, 8) ccl_local_kernel(const uint8_t* __rest
                                                            int* __restrict__ st_x0, int* __restrict__ st_y0,
                                                            int* __restrict__ st_x1, int* __restrict__ st_y1,
                                                            uint8_t* __restrict__ seg_flags, int seg_pitch, size_t seg_fstride,
-                                                           const int* __restrict__ tile_list, const int* __restrict__ tile_count,
-                                                           int tiles_x, int tiles_y) {
-  const int count = *tile_count, tpf = tiles_x * tiles_y;
+                                                           const int* __restrict__ tile_list, const int* __restrict__ tile_count) {
+  const int count = *tile_count;
   for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
     const int tile = tile_list[idx];
-    const int fr = tile / tpf, rem = tile - fr * tpf, ty = rem / tiles_x;
     ccl_local_tile(bin, bin_fstride, g, labels, st_area, st_x0, st_y0, st_x1, st_y1, seg_flags, seg_pitch, seg_fstride,
-                   rem - ty * tiles_x, ty, fr);
+                   tile & 255, (tile >> 8) & 255, tile >> 16);
     __syncthreads();  // the tile's shared arrays are reused by the next one
   }
 }
@@ -269,10 +276,21 @@ __device__ __forceinline__ int gfind(volatile int* lab, int x) {
   return x;
 }
 
+// both roots at once: the two searches advance in lockstep so that their loads overlap
+__device__ __forceinline__ void gfind2(volatile int* lab, int& a, int& b) {
+  int ea = lab[a], eb = lab[b];
+  if (ea & kTag) a = ea & ~kTag;
+  if (eb & kTag) b = eb & ~kTag;
+  ea = lab[a], eb = lab[b];
+  while (ea != a || eb != b) {
+    a = ea, b = eb;
+    ea = lab[a], eb = lab[b];
+  }
+}
+
 __device__ __forceinline__ void gunite(int* lab, int a, int b) {
   while (true) {
-    a = gfind(lab, a);
-    b = gfind(lab, b);
+    gfind2(lab, a, b);
     if (a == b) return;
     if (a < b) {
       int t = a;
@@ -300,35 +318,43 @@ __device__ __forceinline__ void ccl_merge_tile(const uint8_t* __restrict__ bin, 
     by = tile_y * 32 + (t - 32);
   }
   if (bx >= g.bw || by >= g.bh) return;
-  int p = block_pattern(b, g, bx, by);
-  if (!p) return;
-  int i = by * g.bw + bx;
+  // the block's own pattern and the three neighbours across the border, loaded together (one memory latency)
+  const int i = by * g.bw + bx;
+  int p = block_pattern(b, g, bx, by), q0 = 0, q1 = 0, q2 = 0;
   if (toprow) {
-    if (by == 0) return;
-    int q = block_pattern(b, g, bx, by - 1);
-    if ((p & 3) && (q & 12)) gunite(lab, i, i - g.bw);
-    if (bx > 0 && (p & 1) && (block_pattern(b, g, bx - 1, by - 1) & 8)) gunite(lab, i, i - g.bw - 1);
-    if (bx < g.bw - 1 && (p & 2) && (block_pattern(b, g, bx + 1, by - 1) & 4)) gunite(lab, i, i - g.bw + 1);
+    if (by > 0) {
+      q0 = block_pattern(b, g, bx, by - 1);
+      if (bx > 0) q1 = block_pattern(b, g, bx - 1, by - 1);
+      if (bx < g.bw - 1) q2 = block_pattern(b, g, bx + 1, by - 1);
+    }
+    if (!p) return;
+    if ((p & 3) && (q0 & 12)) gunite(lab, i, i - g.bw);
+    if ((p & 1) && (q1 & 8)) gunite(lab, i, i - g.bw - 1);
+    if ((p & 2) && (q2 & 4)) gunite(lab, i, i - g.bw + 1);
   } else {
-    if (bx == 0) return;
-    int q = block_pattern(b, g, bx - 1, by);
-    if ((p & 5) && (q & 10)) gunite(lab, i, i - 1);
-    if (by > 0 && (p & 1) && (block_pattern(b, g, bx - 1, by - 1) & 8)) gunite(lab, i, i - g.bw - 1);
-    if (by < g.bh - 1 && (p & 4) && (block_pattern(b, g, bx - 1, by + 1) & 2)) gunite(lab, i, i + g.bw - 1);
+    if (bx > 0) {
+      q0 = block_pattern(b, g, bx - 1, by);
+      if (by > 0) q1 = block_pattern(b, g, bx - 1, by - 1);
+      if (by < g.bh - 1) q2 = block_pattern(b, g, bx - 1, by + 1);
+    }
+    if (!p) return;
+    if ((p & 5) && (q0 & 10)) gunite(lab, i, i - 1);
+    if ((p & 1) && (q1 & 8)) gunite(lab, i, i - g.bw - 1);
+    if ((p & 4) && (q2 & 2)) gunite(lab, i, i + g.bw - 1);
   }
 }
 
-// 64 threads per listed tile; a tile whose first segment flag is clear holds no foreground (its first block row is always
-// inside the frame) and has nothing on its border either.
+// 64 threads per listed tile.  Without TileHint flags (exact == false) the list holds every tile: one whose first segment
+// flag is clear holds no foreground (its first block row is always inside the frame) and has nothing on its border.
 __global__ void __launch_bounds__(64) ccl_merge_kernel(const uint8_t* __restrict__ bin, size_t bin_fstride, FrameGeom g,
                                                        int* __restrict__ labels, const uint8_t* __restrict__ seg_flags,
                                                        int seg_pitch, size_t seg_fstride, const int* __restrict__ tile_list,
-                                                       const int* __restrict__ tile_count, int tiles_x, int tiles_y) {
-  const int count = *tile_count, tpf = tiles_x * tiles_y;
+                                                       const int* __restrict__ tile_count, bool exact) {
+  const int count = *tile_count;
   for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
     const int tile = tile_list[idx];
-    const int fr = tile / tpf, rem = tile - fr * tpf, ty = rem / tiles_x, tx = rem - ty * tiles_x;
-    if (!seg_flags[(size_t)fr * seg_fstride + (size_t)(ty * 32) * seg_pitch + tx]) continue;
+    const int fr = tile >> 16, ty = (tile >> 8) & 255, tx = tile & 255;
+    if (!exact && !seg_flags[(size_t)fr * seg_fstride + (size_t)(ty * 32) * seg_pitch + tx]) continue;
     ccl_merge_tile(bin, bin_fstride, g, labels, tx, ty, fr, threadIdx.x);
   }
 }
@@ -341,15 +367,15 @@ __global__ void __launch_bounds__(256) ccl_final_kernel(FrameGeom g, int* __rest
                                                         int* __restrict__ st_x1, int* __restrict__ st_y1,
                                                         int* __restrict__ roots_tmp, uint8_t* __restrict__ seg_flags,
                                                         int seg_pitch, size_t seg_fstride, const int* __restrict__ tile_list,
-                                                        const int* __restrict__ tile_count, int tiles_x, int tiles_y) {
+                                                        const int* __restrict__ tile_count, bool exact) {
   constexpr unsigned kFull = 0xffffffffu;
   const int tq = threadIdx.x & 7, trow = threadIdx.x >> 3;
-  const int count = *tile_count, tpf = tiles_x * tiles_y;
+  const int count = *tile_count;
   for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
     const int tile = tile_list[idx];
-    const int fr = tile / tpf, rem = tile - fr * tpf, ty = rem / tiles_x, tx = rem - ty * tiles_x;
+    const int fr = tile >> 16, ty = (tile >> 8) & 255, tx = tile & 255;
     uint8_t* sf = seg_flags + (size_t)fr * seg_fstride;
-    if (!sf[(size_t)(ty * 32) * seg_pitch + tx]) continue;  // no foreground after all (only without TileHint)
+    if (!exact && !sf[(size_t)(ty * 32) * seg_pitch + tx]) continue;  // no foreground after all
     const int by = ty * 32 + trow, bx0 = tx * 32 + 4 * tq, i0 = by * g.bw + bx0;
     const size_t base = (size_t)fr * g.nblocks;
     int* lab = labels + base;
@@ -544,14 +570,14 @@ int launch_ccl(const uint8_t* bin, size_t bin_fstride, int n, const FrameGeom& g
   int* tiles = tile_list + 4;
   CTAG_CUDA_CHECK(cudaMemsetAsync(seg_flags, 0, seg_fstride * n, stream));
   CTAG_CUDA_CHECK(cudaMemsetAsync(tile_count, 0, 16, stream));
-  ccl_tiles_kernel<<<(ntiles + 255) / 256, 256, 0, stream>>>(tile_any, ntiles, tiles, tile_count);
+  ccl_tiles_kernel<<<(ntiles + 255) / 256, 256, 0, stream>>>(tile_any, ntiles, tiles_x, tiles_y, tiles, tile_count);
   // one wave of resident CTAs each (ccl_local: 8 per SM, 26 KB of shared memory each)
   ccl_local_kernel<<<min(ntiles, 8 * sms), 256, 0, stream>>>(bin, bin_fstride, g, labels, st_area, st_x0, st_y0, st_x1, st_y1,
-                                                              seg_flags, seg_pitch, seg_fstride, tiles, tile_count, tiles_x, tiles_y);
+                                                              seg_flags, seg_pitch, seg_fstride, tiles, tile_count);
   ccl_merge_kernel<<<min(ntiles, 16 * sms), 64, 0, stream>>>(bin, bin_fstride, g, labels, seg_flags, seg_pitch, seg_fstride, tiles,
-                                                              tile_count, tiles_x, tiles_y);
+                                                              tile_count, tile_any != nullptr);
   ccl_final_kernel<<<min(ntiles, 8 * sms), 256, 0, stream>>>(g, labels, st_area, st_x0, st_y0, st_x1, st_y1, roots_tmp, seg_flags,
-                                                              seg_pitch, seg_fstride, tiles, tile_count, tiles_x, tiles_y);
+                                                              seg_pitch, seg_fstride, tiles, tile_count, tile_any != nullptr);
   ccl_list_kernel<<<n, 1024, 0, stream>>>(g, st_area, st_x0, st_y0, st_x1, st_y1, roots_tmp, seg_flags, (int)seg_fstride, legal,
                                           legal_cap, counters);
   CTAG_CUDA_CHECK(cudaGetLastError());
