@@ -265,6 +265,17 @@ def roofline_of(front_ms, w, h, n, ch, traffic=None, traffic_source=None):
             "algorithmic_bytes_per_pixel": 4.25 if ch == 3 else 1.25, "kernel_ms_per_launch": front_ms}
 
 
+def gray_traffic(n):
+    """DRAM bytes of one launch of the gray front kernel: the committed ncu capture (profiles/front_traffic.json)."""
+    try:
+        td = json.load(open(os.path.join(ROOT, "profiles", "front_traffic.json"))).get("4k_gray")
+        if td and td.get("frames_per_launch") == n:
+            return td["dram_bytes_total"], f"constant from {td.get('source')}"
+    except Exception:
+        pass
+    return None, None
+
+
 def measure_traffic(kernel_regex):
     """dram__bytes of ONE launch of the front kernel on this workload, measured now: re-runs this script under ncu with
     --traffic-probe (two batches of the cached ring, the second one captured).  None when ncu is not usable."""
@@ -558,7 +569,7 @@ def main():
         msg, _, _, _, _ = rg.pipelined(a.steps, barrier)
         st = rg.stage_times(5)
         variants["4k_gray"] = {"workload": "the same ring as 8-bit gray frames (detect()'s own contract), batch 64", "value": n * a.steps / (msg / 1000.0),
-                               "unit": "frames/s", "ms_per_step": msg / a.steps, "roofline": roofline_of(st["front"], w, h, n, 1),
+                               "unit": "frames/s", "ms_per_step": msg / a.steps, "roofline": roofline_of(st["front"], w, h, n, 1, *gray_traffic(n)),
                                "stages_ms_per_step_unoverlapped": st}
         del rg
         # config 3 as written: 256 frames 1920x1080 BGR, one marker each
