@@ -221,6 +221,9 @@ static int ensure_workspace(ctag_detector* d, Slot* s, int n, int w, int h) {
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_gray, s->gray_fstride * cap));
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_bin, s->bin_fstride * cap));
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_labels, nb));
+  // CCL writes labels only inside tiles that hold foreground; the quad stage loads the label next to every pixel word it
+  // reads and uses it only where the pixel is set.  Background once, so that those loads never see unwritten memory.
+  CTAG_CUDA_CHECK(cudaMemset(s->d_labels, 0xFF, nb * sizeof(int)));
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_st_area, nb));
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_st_x0, nb));
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_st_y0, nb));
@@ -540,6 +543,9 @@ static int grow(T** p, size_t* cap, size_t need) {
   *cap = 0;
   const size_t want = need + need / 4;
   CTAG_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(p), want * sizeof(T)));
+  // zero once: the JPEG byte buffer is read in 16-byte pieces that reach into the alignment gaps between frames and a few
+  // bytes past the last one (never consumed), and those bytes should not be unwritten memory
+  CTAG_CUDA_CHECK(cudaMemset(*p, 0, want * sizeof(T)));
   *cap = want;
   return CTAG_OK;
 }

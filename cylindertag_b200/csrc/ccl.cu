@@ -44,13 +44,15 @@ __device__ __forceinline__ int block_pattern(const uint8_t* __restrict__ bin, co
   return p;
 }
 
-// Find with path halving: every visited node is re-pointed at its grandparent.  Safe next to concurrent unions: only a
-// non-root is written (it can never become a root again), and what is stored is one of its ancestors.
-__device__ __forceinline__ int uf_find(volatile int* L, int x) {
+// Find with path halving: every visited node is re-pointed at its grandparent.  Parents always have smaller indices than
+// their children (union by minimum index), so the update is an atomicMin like the unions themselves: it can only move a
+// node closer to its root, whatever else runs next to it.
+__device__ __forceinline__ int uf_find(int* L, int x) {
+  volatile int* Lv = L;
   int p;
-  while ((p = L[x]) != x) {
-    const int gp = L[p];
-    if (gp != p) L[x] = gp;
+  while ((p = Lv[x]) != x) {
+    const int gp = Lv[p];
+    if (gp != p) atomicMin(&L[x], gp);
     x = gp;
   }
   return x;
@@ -496,15 +498,25 @@ __global__ void __launch_bounds__(1024) ccl_list_kernel(FrameGeom g, const int* 
   const int* roots = roots_tmp + (size_t)fr * segs * 32;
   const int per = (segs + 1023) / 1024;
   const int s_lo = min(t * per, segs), s_hi = min(s_lo + per, segs);
+  // Almost all segments are empty: the flag bytes are read sixteen at a time (independent loads), then only the
+  // segments that hold roots are visited.
   int c = 0, lc = 0;
-  for (int s = s_lo; s < s_hi; ++s) {
-    const int f = sf[s];
-    if (!(f & 0x80)) continue;
-    const int n = f & 0x7f;
-    c += n;
-    for (int k = 0; k < n; ++k) {
-      const int a = st_area[base + roots[(size_t)s * 32 + k]];
-      lc += (a >= kAreaMin && a <= g.area_max) ? 1 : 0;
+  for (int s0 = s_lo; s0 < s_hi; s0 += 16) {
+    unsigned nz = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int f = s0 + j < s_hi ? sf[s0 + j] : 0;
+      if (f & 0x80) nz |= 1u << j;
+    }
+    while (nz) {
+      const int s = s0 + __ffs(nz) - 1;
+      nz &= nz - 1;
+      const int n = sf[s] & 0x7f;
+      c += n;
+      for (int k = 0; k < n; ++k) {
+        const int a = st_area[base + roots[(size_t)s * 32 + k]];
+        lc += (a >= kAreaMin && a <= g.area_max) ? 1 : 0;
+      }
     }
   }
   int tot_c, tot_l;
