@@ -859,16 +859,20 @@ int ctag_detect_batch_multi(ctag_detector* const* dets, int n_det, const void* f
                             size_t frame_stride, int channels, int adaptive_thresh, int corner_subpix, int subpix_dist,
                             ctag_marker* out, int cap_per_frame, int* n_out, ctag_frame_info* info) {
   if (!dets || n_det <= 0 || !frames || n <= 0) return CTAG_ERR_ARG;
-  for (int g = 0; g < n_det; ++g)
+  for (int g = 0; g < n_det; ++g) {
     if (!dets[g]) return CTAG_ERR_ARG;
+    for (int k = 0; k < g; ++k)
+      if (dets[k] == dets[g]) return CTAG_ERR_ARG;  // a detector is not re-entrant: every block needs its own
+  }
   if (frame_stride == 0) frame_stride = pitch * (size_t)h;
   std::vector<int> rcs(n_det, CTAG_OK);
+  std::vector<std::string> errs(n_det);  // ctag_last_error() is per thread: carry the workers' texts back to the caller
   std::vector<std::thread> threads;
   // contiguous blocks, frame f -> detector floor(f * n_det / n) (video locality); one host thread per detector
   for (int g = 0; g < n_det; ++g) {
     const int first = (int)((long long)n * g / n_det), last = (int)((long long)n * (g + 1) / n_det);
     if (last <= first) continue;
-    threads.emplace_back([=, &rcs]() {
+    threads.emplace_back([=, &rcs, &errs]() {
       rcs[g] = ctag_detect_batch(dets[g], static_cast<const uint8_t*>(frames) + frame_stride * first, last - first, w, h, pitch,
                                  frame_stride, channels, 0, adaptive_thresh, corner_subpix, subpix_dist,
                                  out ? out + (size_t)first * cap_per_frame : nullptr, cap_per_frame, n_out ? n_out + first : nullptr,
@@ -876,11 +880,15 @@ int ctag_detect_batch_multi(ctag_detector* const* dets, int n_det, const void* f
       if (rcs[g] == CTAG_OK && out && n_out)
         for (int f = first; f < last; ++f)
           for (int k = 0; k < n_out[f] && k < cap_per_frame; ++k) out[(size_t)f * cap_per_frame + k].frame = f;
+      if (rcs[g] != CTAG_OK) errs[g] = g_last_error;
     });
   }
   for (auto& t : threads) t.join();
   for (int g = 0; g < n_det; ++g)
-    if (rcs[g] != CTAG_OK) return rcs[g];
+    if (rcs[g] != CTAG_OK) {
+      set_last_error_text(errs[g].c_str());
+      return rcs[g];
+    }
   return CTAG_OK;
 }
 

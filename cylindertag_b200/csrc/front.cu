@@ -630,6 +630,8 @@ static int resident_ctas(const void* kernel, int smem_bytes, int slot, int* out)
     CTAG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     CTAG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, front::NT, smem_bytes));
     if (per_sm < 1) per_sm = 1;
+    static const int cap = getenv("CTAG_FRONT_CTAS") ? atoi(getenv("CTAG_FRONT_CTAS")) : 0;  // A/B knob, read once
+    if (cap >= 1 && cap < per_sm) per_sm = cap;
     if (dev < 0 || dev >= kMaxDev) {
       *out = sms * per_sm;
       return CTAG_OK;

@@ -145,7 +145,8 @@ CTAG_API int ctag_detect_batch(ctag_detector* det, const void* frames, int n, in
  * floor(f * n_det / n); each block runs ctag_detect_batch(is_device = 0) on its own host thread and there is no exchange
  * between devices.  `frames` is a HOST pointer; out / n_out / info are indexed by the global frame number and
  * ctag_marker::frame is the global index, i.e. the result equals the single-detector call on the whole batch.
- * n_out is required when out is given.  Returns the first non-OK block status. */
+ * n_out is required when out is given.  The detectors must be distinct objects (CTAG_ERR_ARG otherwise: a detector is not
+ * re-entrant).  Returns the first non-OK block status; ctag_last_error() then holds that block's message. */
 CTAG_API int ctag_detect_batch_multi(ctag_detector* const* dets, int n_det, const void* frames, int n, int w, int h,
                                      size_t pitch, size_t frame_stride, int channels, int adaptive_thresh, int corner_subpix,
                                      int subpix_dist, ctag_marker* out, int cap_per_frame, int* n_out, ctag_frame_info* info);

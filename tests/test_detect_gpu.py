@@ -31,6 +31,17 @@ def test_testbmp_known_answers(detector, test_gray, golden_testbmp):
         assert np.abs(m["corners"][:n[k]] - g["mk_corners"][sl]).max() <= 1e-3
 
 
+@pytest.mark.parametrize("win", [4, 7])
+def test_other_threshold_windows_full_dump_parity(detector, test_gray, marker_path, win):
+    """adaptiveThresh != 5: the unfused front kernels write no tile flags, so the component stage lists every tile and
+    finds the empty ones itself -- every stage must still equal the reference's."""
+    state, fs = o.load_marker_file(marker_path)
+    dump = o.detect(test_gray, state, fs, win, True, 5)
+    markers, counts, info = detector.detect_batch(test_gray[None], win, True, 5)
+    worst = assert_frame_matches(detector, 0, info, markers, counts, dump, True, ctx=f"window={win}")
+    assert worst <= 1e-3
+
+
 def test_testbmp_full_dump_parity(detector, test_gray, marker_path):
     state, fs = o.load_marker_file(marker_path)
     for subpix, dist in ((True, 5), (False, 3), (True, 3)):

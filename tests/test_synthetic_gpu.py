@@ -133,5 +133,8 @@ def test_multi_detector_call_equals_single_detector(marker_path):
     got_m, got_c, got_i = detect_batch_multi(dets, frames, 5, True, 5, cap_per_frame=8)
     assert np.array_equal(got_c, want_c) and got_c.sum() >= 23 and np.array_equal(got_i, want_i)
     assert np.array_equal(got_m.view(np.uint8), want_m.view(np.uint8))
+    from cylindertag_b200 import CtagError
+    with pytest.raises(CtagError):  # the same detector for two blocks: refused, a detector is not re-entrant
+        detect_batch_multi([dets[0], dets[0]], frames, 5, True, 5, cap_per_frame=8)
     for d in dets:
         d.close()
