@@ -81,7 +81,7 @@ struct Slot {
   size_t gray_fstride = 0, bin_fstride = 0;
   int *d_labels = nullptr, *d_st_area = nullptr, *d_st_x0 = nullptr, *d_st_y0 = nullptr, *d_st_x1 = nullptr,
       *d_st_y1 = nullptr, *d_roots_tmp = nullptr, *d_tile_list = nullptr, *d_legal = nullptr, *d_counters = nullptr;
-  int legal_cap = 0, spans = 0;
+  int legal_cap = 0;
   int *d_prefix = nullptr, *d_qctl = nullptr, *d_quad_status = nullptr, *d_quad_comp = nullptr, *d_n_quads = nullptr,
       *d_exact_list = nullptr, *d_fit_order = nullptr, *d_frame_fit = nullptr, *d_pool = nullptr;
   float *d_quad_corners = nullptr, *d_quads = nullptr, *d_lines = nullptr;
@@ -215,7 +215,6 @@ static int ensure_workspace(ctag_detector* d, Slot* s, int n, int w, int h) {
   s->gray_fstride = (size_t)g.gpitch * g.h;
   s->bin_fstride = (size_t)g.bpitch * g.hh;
   const size_t nb = (size_t)g.nblocks * cap;
-  s->spans = (g.nblocks + 1023) / 1024;
   s->legal_cap = g.hw * g.hh / kAreaMin + 1;  // every legal component has >= 30 pixels
   if (s->legal_cap > 65536) s->legal_cap = 65536;
   CTAG_CUDA_CHECK(slot_alloc(s, &s->d_gray, s->gray_fstride * cap));

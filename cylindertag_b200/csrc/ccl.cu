@@ -76,7 +76,8 @@ __device__ __forceinline__ void uf_unite(int* L, int a, int b) {
 }
 
 // 256 threads per 32x32-block tile; thread t owns the four horizontally adjacent blocks (4*(t&7) .. +3, t>>3) so that the
-// binary image is read with 8-byte loads and empty tiles (the common case) write their labels with 16-byte stores.
+// binary image is read with 8-byte loads.  A tile that turns out to hold no foreground (possible only without the front
+// kernel's flags) is left after that read and writes nothing.
 __device__ __forceinline__ void ccl_local_tile(const uint8_t* __restrict__ bin, size_t bin_fstride, const FrameGeom& g,
                                                int* __restrict__ labels, int* __restrict__ st_area, int* __restrict__ st_x0,
                                                int* __restrict__ st_y0, int* __restrict__ st_x1, int* __restrict__ st_y1,
@@ -96,9 +97,10 @@ __device__ __forceinline__ void ccl_local_tile(const uint8_t* __restrict__ bin, 
     a = *reinterpret_cast<const uint2*>(r0);
     if (2 * by + 1 < g.hh) b = *reinterpret_cast<const uint2*>(r0 + g.bpitch);
   }
-  // Empty tile (the common case): nothing is written at all.  seg_flags[by][tile column] (zeroed per batch) says which
-  // 32-block row segments belong to a tile that holds foreground; only those have valid labels, and every reader of the
-  // label array either checks the flag (ccl_merge, ccl_final) or looks at foreground pixels only (the quad stage).
+  // Empty tile: nothing is written at all.  seg_flags[by][tile column] (zeroed per batch) says which 32-block row
+  // segments belong to a tile that holds foreground; only those have valid labels, and every reader of the label array
+  // either works from the tile list / checks the flag (ccl_merge, ccl_final, ccl_list) or uses a label only where the
+  // pixel is set (the quad stage).
   if (!__syncthreads_or((a.x | a.y | b.x | b.y) != 0u)) return;
   {
     const uint32_t aw[2] = {a.x, a.y}, bw_[2] = {b.x, b.y};

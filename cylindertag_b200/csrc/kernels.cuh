@@ -27,8 +27,8 @@ TileHint ccl_tile_hint(const FrameGeom& g, uint8_t* buf);
 size_t ccl_roots_ints(const FrameGeom& g);                  // roots_tmp, per frame
 size_t ccl_tile_list_ints(const FrameGeom& g, int frames);  // tile_list, per batch
 int launch_ccl(const uint8_t* bin, size_t bin_fstride, int n, const FrameGeom& g, int* labels, int* st_area, int* st_x0,
-               int* st_y0, int* st_x1, int* st_y1, int* roots_tmp, int* tile_list, uint8_t* seg_flags, const uint8_t* tile_any, int* legal, int legal_cap,
-               int* counters, cudaStream_t stream, int* launches);
+               int* st_y0, int* st_x1, int* st_y1, int* roots_tmp, int* tile_list, uint8_t* seg_flags, const uint8_t* tile_any,
+               int* legal, int legal_cap, int* counters, cudaStream_t stream, int* launches);
 
 // K4 (quad.cu): edges (warp per component) -> Welsch fits (thread per restart, merge, exact fallback) -> corner
 // selection -> ordered compaction.
