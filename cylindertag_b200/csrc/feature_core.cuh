@@ -164,43 +164,57 @@ __device__ __forceinline__ float lut255_byte(uint32_t v) {
 CT_HD float lut255_byte(uint32_t v) { return lut255f((int)v); }
 #endif
 
+// One sample: the ladder of NM pixels along the normal through (x0, y0).  INSIDE = the caller has checked that both ends
+// of the ladder (hence, x and y being monotone in m, all of it) lie inside the image: no per-pixel bounds tests then.
+template <int WIN, bool INSIDE>
+CT_HD void edge_ladder(const uint8_t* gray, int pitch, int cols, int rows, double x0, double y0, double nx, double ny, double& Mn,
+                       double& Mcount) {
+  constexpr int NM = 8 * WIN + 9;
+  float ring[9];
+  bool okr[9];
+  double mb = -(double)(WIN + 1);  // m of the first pixel of the block: multiples of 0.25 are exact
+#pragma unroll 1
+  for (int blk = 0; blk < NM; blk += 9, mb += 2.25) {  // ring slot = i mod 9 is a compile-time constant inside the body
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const int i = blk + j;
+      if (i < NM) {
+        const double m = mb + 0.25 * j;
+        const int x = (int)(x0 + m * nx);
+        const int y = (int)(y0 + m * ny);
+        const bool ok = INSIDE || !(x < 0 || x >= cols || y < 0 || y >= rows);
+        // a frame is smaller than 2^32 bytes: a 32-bit offset keeps the address arithmetic short
+        const float gv = ok ? lut255_byte(gray[(uint32_t)(y * pitch + x)]) : 0.f;
+        if (i >= 8) {
+          const double n = m - 1;
+          const float g1 = gv, g2 = ring[(j + 1) % 9];
+          if (ok && (INSIDE || okr[(j + 1) % 9]) && !(g1 < g2)) {
+            double weight = (g2 - g1) * (g2 - g1);
+            Mn += weight * n;
+            Mcount += weight;
+          }
+        }
+        ring[j] = gv;
+        okr[j] = ok;
+      }
+    }
+  }
+}
+
 template <int WIN>
 CT_HD void edge_samples_w(const uint8_t* gray, int pitch, int cols, int rows, float ax, float ay, float bx, float by,
                           int first, int step, double nx, double ny, int nsamples, EdgeMoments& nextm, EdgeMoments& lastm) {
-  constexpr int NM = 8 * WIN + 9;
   for (int s = first; s < nsamples; s += step) {
     double alpha = (15.0 + s) / (nsamples + 30);
     double x0 = alpha * ax + (1 - alpha) * bx;
     double y0 = alpha * ay + (1 - alpha) * by;
     double Mn = 0, Mcount = 0;
-    float ring[9];
-    bool okr[9];
-    double mb = -(double)(WIN + 1);  // m of the first pixel of the block: multiples of 0.25 are exact
-#pragma unroll 1
-    for (int blk = 0; blk < NM; blk += 9, mb += 2.25) {  // ring slot = i mod 9 is a compile-time constant inside the body
-#pragma unroll
-      for (int j = 0; j < 9; ++j) {
-        const int i = blk + j;
-        if (i < NM) {
-          const double m = mb + 0.25 * j;
-          const int x = (int)(x0 + m * nx);
-          const int y = (int)(y0 + m * ny);
-          const bool ok = !(x < 0 || x >= cols || y < 0 || y >= rows);
-          const float gv = ok ? lut255_byte(gray[(size_t)y * pitch + x]) : 0.f;
-          if (i >= 8) {
-            const double n = m - 1;
-            const float g1 = gv, g2 = ring[(j + 1) % 9];
-            if (ok && okr[(j + 1) % 9] && !(g1 < g2)) {
-              double weight = (g2 - g1) * (g2 - g1);
-              Mn += weight * n;
-              Mcount += weight;
-            }
-          }
-          ring[j] = gv;
-          okr[j] = ok;
-        }
-      }
-    }
+    // the two ends of the ladder, computed exactly as the ladder computes them
+    const double me = (double)(WIN + 1);
+    const int xa = (int)(x0 + (-me) * nx), xb = (int)(x0 + me * nx), ya = (int)(y0 + (-me) * ny), yb = (int)(y0 + me * ny);
+    const bool inside = xa >= 0 && xa < cols && xb >= 0 && xb < cols && ya >= 0 && ya < rows && yb >= 0 && yb < rows;
+    if (inside) edge_ladder<WIN, true>(gray, pitch, cols, rows, x0, y0, nx, ny, Mn, Mcount);
+    else edge_ladder<WIN, false>(gray, pitch, cols, rows, x0, y0, nx, ny, Mn, Mcount);
     if (Mcount == 0) continue;
     double n0 = Mn / Mcount;
     em_add(nextm, lastm, x0 + n0 * nx, y0 + n0 * ny, alpha);
