@@ -173,7 +173,7 @@ CT_HD void edge_ladder(const uint8_t* gray, int pitch, int cols, int rows, doubl
   float ring[9];
   bool okr[9];
   double mb = -(double)(WIN + 1);  // m of the first pixel of the block: multiples of 0.25 are exact
-#pragma unroll 1
+#pragma unroll
   for (int blk = 0; blk < NM; blk += 9, mb += 2.25) {  // ring slot = i mod 9 is a compile-time constant inside the body
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
