@@ -511,14 +511,34 @@ CT_HD void quad_stage_edges(const CompView& cv, const QuadScratch& sc, Lanes ln,
     P[n++] = pt_pack(fx + cv.x0, fy + cv.y0);
     sc.vis[fy * wpr] &= ~1u;
     --remaining;
+    // The walk moves one pixel at a time, so the three bit-map words around the current position (word column cw, rows
+    // cy-1..cy+1) are kept in registers: a horizontal move needs no load at all, a vertical one loads a single new word,
+    // and clearing a visited bit is a plain store.  Memory stays authoritative (every change is stored); the registers
+    // are reloaded after a pop and when the walk crosses into another word column.
+    int cw = 0, cy = fy;
+    uint32_t w0 = cy > 0 ? sc.vis[(cy - 1) * wpr] : 0u, w1 = sc.vis[cy * wpr], w2 = cy + 1 < h ? sc.vis[(cy + 1) * wpr] : 0u;
     while (remaining > 0) {
       // Directions fj..7 are probed at a fixed position and the bit map only changes inside a recursive call, so
       // the first hit is the first set bit of the 8-neighbour mask at or after fj.
-      uint32_t m = fj < 8 ? (nbr_mask(sc.vis, wpr, h, fx, fy) >> fj) : 0u;
+      uint32_t m = 0u;
+      if (fj < 8) {
+        const int xb = fx & 31;
+        if (xb >= 1 && xb <= 30) {  // the 3x3 neighbourhood lies inside the cached words
+          const uint32_t t0 = (w0 >> (xb - 1)) & 7u, t1 = (w1 >> (xb - 1)) & 7u, t2 = (w2 >> (xb - 1)) & 7u;
+          m = ((t0 >> 1) & 1u) | (((t0 >> 2) & 1u) << 1) | (((t1 >> 2) & 1u) << 2) | (((t2 >> 2) & 1u) << 3) |
+              (((t2 >> 1) & 1u) << 4) | ((t2 & 1u) << 5) | ((t1 & 1u) << 6) | ((t0 & 1u) << 7);
+        } else {
+          m = nbr_mask(sc.vis, wpr, h, fx, fy);
+        }
+        m >>= fj;
+      }
       if (m == 0) {
         if (sp == 0) break;
         int fr = sc.stack[--sp];
         fx = fr & 0xFFF, fy = (fr >> 12) & 0xFFF, fj = fr >> 24;
+        cw = fx >> 5, cy = fy;
+        w0 = cy > 0 ? sc.vis[(cy - 1) * wpr + cw] : 0u, w1 = sc.vis[cy * wpr + cw];
+        w2 = cy + 1 < h ? sc.vis[(cy + 1) * wpr + cw] : 0u;
         continue;
       }
 #ifdef __CUDA_ARCH__
@@ -528,7 +548,28 @@ CT_HD void quad_stage_edges(const CompView& cv, const QuadScratch& sc, Lanes ln,
 #endif
       const int nx = fx + (int)((0x1A9u >> (2 * j)) & 3u) - 1;
       const int ny = fy + (int)((0x1A90u >> (2 * j)) & 3u) - 1;
-      sc.vis[ny * wpr + (nx >> 5)] &= ~(1u << (nx & 31));
+      const uint32_t clr = ~(1u << (nx & 31));
+      if ((nx >> 5) == cw) {
+        // the visited bit lies in one of the cached words (ny is cy-1, cy or cy+1): clear it there and store that word
+        const int dy = ny - cy;
+        if (dy < 0) w0 &= clr;
+        else if (dy == 0) w1 &= clr;
+        else w2 &= clr;
+        sc.vis[ny * wpr + cw] = dy < 0 ? w0 : (dy == 0 ? w1 : w2);
+        if (dy < 0) {
+          w2 = w1, w1 = w0;
+          w0 = ny > 0 ? sc.vis[(ny - 1) * wpr + cw] : 0u;
+        } else if (dy > 0) {
+          w0 = w1, w1 = w2;
+          w2 = ny + 1 < h ? sc.vis[(ny + 1) * wpr + cw] : 0u;
+        }
+        cy = ny;
+      } else {
+        sc.vis[ny * wpr + (nx >> 5)] &= clr;
+        cw = nx >> 5, cy = ny;
+        w0 = cy > 0 ? sc.vis[(cy - 1) * wpr + cw] : 0u, w1 = sc.vis[cy * wpr + cw];
+        w2 = cy + 1 < h ? sc.vis[(cy + 1) * wpr + cw] : 0u;
+      }
       P[n++] = pt_pack(nx + cv.x0, ny + cv.y0);
       sc.stack[sp++] = nx | (ny << 12) | ((j + 1) << 24);  // caller resumes at direction j+1 from the new position
       fx = nx, fy = ny, fj = 0;
