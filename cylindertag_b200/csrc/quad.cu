@@ -100,7 +100,7 @@ __global__ void quad_prefix_kernel(const int* __restrict__ counters, int n, int*
 // lists in shared memory; large ones use the warp's global scratch (same code, different pointers).  Components with
 // four edges append a FitRec and copy their clusters to the point pool.
 constexpr int kEdgeWarps = 4;
-constexpr int kEdgeCtasPerSm = 8;  // the serial trace is latency bound: more resident warps, 64 registers each
+constexpr int kEdgeCtasPerSm = 6;  // 80 registers per thread: at 8 CTAs (64 registers) the trace loop spills and rematerialises pointers
 constexpr int kSmemPts = 256;       // points per list on the shared-memory fast path
 constexpr int kSmemVisWords = 256;  // bit-map words on the shared-memory fast path
 

@@ -178,6 +178,30 @@ CT_HD uint32_t row_bits3(const uint32_t* vis, int wpr, int h, int y, int x) {
   return (uint32_t)(v >> sh) & 7u;
 }
 
+// The 8-neighbour mask as a function of the three 3-bit row windows, v = t0 | t1 << 3 | t2 << 6 (t = bits x-1, x, x+1):
+// one table look-up instead of eight bit moves in the trace's dependent chain.
+struct NbrLut {
+  uint8_t m[512];
+  constexpr NbrLut() : m() {
+    for (int v = 0; v < 512; ++v) {
+      const int t0 = v & 7, t1 = (v >> 3) & 7, t2 = v >> 6;
+      m[v] = (uint8_t)(((t0 >> 1) & 1) | (((t0 >> 2) & 1) << 1) | (((t1 >> 2) & 1) << 2) | (((t2 >> 2) & 1) << 3) |
+                       (((t2 >> 1) & 1) << 4) | ((t2 & 1) << 5) | ((t1 & 1) << 6) | ((t0 & 1) << 7));
+    }
+  }
+};
+#if defined(__CUDACC__)
+static __constant__ NbrLut kNbrLutDev = NbrLut();
+#endif
+static const NbrLut kNbrLutHost = NbrLut();
+CT_HD uint32_t nbr_lut(uint32_t v) {
+#ifdef __CUDA_ARCH__
+  return kNbrLutDev.m[v];
+#else
+  return kNbrLutHost.m[v];
+#endif
+}
+
 // 8-neighbour occupancy of (x,y) in the reference's probing order N,NE,E,SE,S,SW,W,NW (corner_detector.h:84-85)
 CT_HD uint32_t nbr_mask(const uint32_t* vis, int wpr, int h, int x, int y) {
   uint32_t t0, t1, t2;
@@ -524,9 +548,8 @@ CT_HD void quad_stage_edges(const CompView& cv, const QuadScratch& sc, Lanes ln,
       if (fj < 8) {
         const int xb = fx & 31;
         if (xb >= 1 && xb <= 30) {  // the 3x3 neighbourhood lies inside the cached words
-          const uint32_t t0 = (w0 >> (xb - 1)) & 7u, t1 = (w1 >> (xb - 1)) & 7u, t2 = (w2 >> (xb - 1)) & 7u;
-          m = ((t0 >> 1) & 1u) | (((t0 >> 2) & 1u) << 1) | (((t1 >> 2) & 1u) << 2) | (((t2 >> 2) & 1u) << 3) |
-              (((t2 >> 1) & 1u) << 4) | ((t2 & 1u) << 5) | ((t1 & 1u) << 6) | ((t0 & 1u) << 7);
+          const int sh = xb - 1;
+          m = nbr_lut(((w0 >> sh) & 7u) | (((w1 >> sh) & 7u) << 3) | (((w2 >> sh) & 7u) << 6));
         } else {
           m = nbr_mask(sc.vis, wpr, h, fx, fy);
         }
