@@ -657,7 +657,9 @@ def main():
             try:
                 cpu_reference_pass(ref_ring[:cores], state, fs, cores)  # warm-up
                 v, _ = cpu_reference_pass(ref_ring, state, fs, cores)
-                line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": cpu_sample_text(len(ref_ring), cores)}
+                v1, _ = cpu_reference_pass(ref_ring[:4], state, fs, 1)  # also one thread (4 frames)
+                line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": cpu_sample_text(len(ref_ring), cores),
+                                        "value_1_thread": v1}
             except Exception as exc:  # pragma: no cover
                 line["cpu_baseline"] = {"error": str(exc)}
         print(json.dumps(line))
